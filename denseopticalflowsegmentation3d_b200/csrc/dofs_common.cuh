@@ -1,0 +1,71 @@
+// Common definitions of the sm_100a hot path (kernels are in the dofs_*.cuh headers, the context,
+// orchestration and C ABI in dofs3d.cu).
+//
+// Exact arithmetic: the segmentation and lifting stages must reproduce the reference's host
+// arithmetic bit for bit (plain x86-64 build: every float/double operation rounds once, no FMA
+// contraction).  All such operations go through the *_rn helpers below, which nvcc never contracts.
+#pragma once
+
+#include <stdint.h>
+
+#ifdef DOFS_EMUL
+// Test-only build: tests/emul/cuda_emul.h supplies the CUDA vocabulary for a host compiler so that
+// the non-cooperative kernels can be exercised without a GPU.  Never part of the shipped library.
+#include "cuda_emul.h"
+#else
+#include <cuda_runtime.h>
+#endif
+
+typedef uint8_t u8;
+typedef uint16_t u16;
+typedef uint32_t u32;
+typedef uint64_t u64;
+
+#define DOFS_INF32 0xFFFFFFFFu
+
+#define DOFS_HD __host__ __device__ __forceinline__
+#define DOFS_D __device__ __forceinline__
+
+// float ops, one rounding each
+DOFS_D float fadd(float a, float b) { return __fadd_rn(a, b); }
+DOFS_D float fsub(float a, float b) { return __fsub_rn(a, b); }
+DOFS_D float fmul(float a, float b) { return __fmul_rn(a, b); }
+DOFS_D float fdiv(float a, float b) { return __fdiv_rn(a, b); }
+// double ops, one rounding each
+DOFS_D double dadd(double a, double b) { return __dadd_rn(a, b); }
+DOFS_D double dsub(double a, double b) { return __dsub_rn(a, b); }
+DOFS_D double dmul(double a, double b) { return __dmul_rn(a, b); }
+DOFS_D double ddiv(double a, double b) { return __ddiv_rn(a, b); }
+DOFS_D double dsqrt(double a) { return __dsqrt_rn(a); }
+
+// sqrt((double)x*x + (double)y*y): cv::norm(Point2f) / cv::norm(Vec2f) and diff (segment.cpp:25-29).
+// The two products of floats are exact in double, so the sum rounds once either way.
+DOFS_D double norm2d(float x, float y) {
+    double dx = (double)x, dy = (double)y;
+    return dsqrt(dadd(dmul(dx, dx), dmul(dy, dy)));
+}
+
+struct Homographies {
+    float persp[9];
+    float inv[9];
+    float upper[3][9];
+};
+
+struct SegParams {
+    Homographies hg;
+    int cls_size[3][2];
+    double cls_min_convexity[3];
+    double score_threshold;
+    int min_size;
+    int neighbors;
+};
+
+// One merge that passed the size / row / move gates of Forest::new_merge (graph.cpp:280-300).
+struct __align__(16) Candidate {
+    u32 root;
+    u32 time;      // position of the merging edge in the sorted edge list
+    int size;
+    float fx, fy;  // mean flow of the merged set
+    u16 bbox[4];   // xmin, ymin, xmax, ymax
+    u32 pad;
+};

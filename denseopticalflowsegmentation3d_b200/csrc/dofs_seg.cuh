@@ -1,0 +1,610 @@
+// Flow-graph clustering on the device (stages K6-K12 of SURVEY.md section 2.2).
+//
+// The reference (cpp/src/graph.cpp) is a strictly sequential Kruskal loop with union by rank, a
+// running float mean per set and a per-merge scoring hook.  This file computes the SAME merge
+// sequence and per-merge state in parallel, using one structural fact (checked against the reference
+// in tests/ and tools/proto_parallel.py):
+//
+//   Boruvka levels on the (weight, insertion-order)-ranked edges are exactly the union-by-rank ranks.
+//   In level k every current component S (all have rank k) picks its minimum outgoing edge m_k(S).
+//     * a pick that is not mutual: S loses at time m_k(S) to whatever component holds the other
+//       endpoint at that time (it has rank > k);
+//     * a mutual pick (S and S' pick the same edge): a rank tie; the component holding `edge.end`
+//       survives (graph.cpp:177-182) and becomes a level k+1 component.
+//   So every root id loses exactly once, at loss_time[c] (position of its edge in the sorted list),
+//   and `up[c]` = root of the next-level component it is contracted into.  The root of any pixel's
+//   set at time t is found by climbing `up` while loss_time < t (<= max rank hops).
+//
+// Merge events are then grouped into per-root chains ordered by time, and the chains are replayed
+// in waves of increasing final rank (a chain only absorbs roots of strictly lower final rank), which
+// reproduces sizes, bounding boxes and the order-dependent float mean flow (graph.cpp:184-190)
+// bit for bit.
+#pragma once
+#include "dofs_common.cuh"
+#include "dofs_lift.cuh"
+
+#define SEG_THREADS 256
+
+struct SegFrame {  // per-frame strided views: element i of frame f at [f * stride + i]
+    int W, H, N;   // N = W*H pixels; 4N edge slots
+};
+
+// ---------------------------------------------------------------------------------------------
+// K6  cv::GaussianBlur(flow, flow, Size(0,0), sigma) (segment.cpp:52): separable, BORDER_REFLECT_101.
+// taps: 2*radius+1 float coefficients (host-computed like cv::getGaussianKernel, CV_32F).
+// ---------------------------------------------------------------------------------------------
+#define BLUR_MAX_RADIUS 32
+struct BlurTaps {
+    int radius;
+    float k[2 * BLUR_MAX_RADIUS + 1];
+};
+
+DOFS_D int reflect101(int i, int n) {
+    if (n == 1) return 0;
+    while (i < 0 || i >= n) {
+        if (i < 0) i = -i;
+        if (i >= n) i = 2 * (n - 1) - i;
+    }
+    return i;
+}
+
+// horizontal pass: one thread per pixel (float2), rows are contiguous so neighbouring loads coalesce/L1-hit
+__global__ void __launch_bounds__(SEG_THREADS)
+k_blur_rows(const float2* __restrict__ src, float2* __restrict__ dst, int W, int H, BlurTaps taps) {
+    const int frame = blockIdx.y;
+    const int N = W * H;
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= N) return;
+    const int y = p / W, x = p - y * W;
+    const float2* row = src + (size_t)frame * N + (size_t)y * W;
+    float sx = 0.f, sy = 0.f;
+    const int r = taps.radius;
+    if (x >= r && x + r < W) {
+        for (int k = -r; k <= r; ++k) {
+            float2 v = row[x + k];
+            float c = taps.k[k + r];
+            sx = fmaf(c, v.x, sx);
+            sy = fmaf(c, v.y, sy);
+        }
+    } else {
+        for (int k = -r; k <= r; ++k) {
+            float2 v = row[reflect101(x + k, W)];
+            float c = taps.k[k + r];
+            sx = fmaf(c, v.x, sx);
+            sy = fmaf(c, v.y, sy);
+        }
+    }
+    dst[(size_t)frame * N + p] = make_float2(sx, sy);
+}
+
+__global__ void __launch_bounds__(SEG_THREADS)
+k_blur_cols(const float2* __restrict__ src, float2* __restrict__ dst, int W, int H, BlurTaps taps) {
+    const int frame = blockIdx.y;
+    const int N = W * H;
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= N) return;
+    const int y = p / W, x = p - y * W;
+    const float2* img = src + (size_t)frame * N;
+    float sx = 0.f, sy = 0.f;
+    const int r = taps.radius;
+    for (int k = -r; k <= r; ++k) {
+        int yy = y + k;
+        if (yy < 0 || yy >= H) yy = reflect101(yy, H);
+        float2 v = img[(size_t)yy * W + x];
+        float c = taps.k[k + r];
+        sx = fmaf(c, v.x, sx);
+        sy = fmaf(c, v.y, sy);
+    }
+    dst[(size_t)frame * N + p] = make_float2(sx, sy);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K7  edge weights: build_graph's enumeration (graph.cpp:62-93) with diff (segment.cpp:20-32).
+// Slot 4*p+d of pixel p=(x,y): d=0 left (x-1,y), d=1 up (x,y-1), d=2 up-left (x-1,y-1),
+// d=3 down-left (x-1,y+1); the slot index IS the reference's insertion sequence number.
+// Non-existent border edges (and slots 2,3 in 4-neighbour mode) get +inf so they sort last.
+// key = bit pattern of the f64 weight (non-negative doubles order like unsigned integers).
+// ---------------------------------------------------------------------------------------------
+DOFS_D u64 edge_key(float2 a, float2 b) {
+    float dx = fsub(a.x, b.x), dy = fsub(a.y, b.y);
+    return (u64)__double_as_longlong(norm2d(dx, dy));
+}
+
+#define EDGE_KEY_INVALID 0x7FF0000000000000ull
+
+__global__ void __launch_bounds__(SEG_THREADS)
+k_edge_keys(const float2* __restrict__ flow, u64* __restrict__ keys, size_t key_stride, int W, int H, int neighbors8) {
+    const int frame = blockIdx.y;
+    const int N = W * H;
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= N) return;
+    const int y = p / W, x = p - y * W;
+    const float2* f = flow + (size_t)frame * N;
+    const float2 c = f[p];
+    u64 k0 = EDGE_KEY_INVALID, k1 = EDGE_KEY_INVALID, k2 = EDGE_KEY_INVALID, k3 = EDGE_KEY_INVALID;
+    if (x > 0) k0 = edge_key(c, f[p - 1]);
+    if (y > 0) k1 = edge_key(c, f[p - W]);
+    if (neighbors8) {
+        if (x > 0 && y > 0) k2 = edge_key(c, f[p - W - 1]);
+        if (x > 0 && y < H - 1) k3 = edge_key(c, f[p + W - 1]);
+    }
+    ulonglong2* out = reinterpret_cast<ulonglong2*>(keys + (size_t)frame * key_stride + 4 * (size_t)p);
+    out[0] = make_ulonglong2(k0, k1);
+    out[1] = make_ulonglong2(k2, k3);
+}
+
+DOFS_D int edge_other(int s, int d, int W) {
+    return d == 0 ? s - 1 : d == 1 ? s - W : d == 2 ? s - W - 1 : s + W - 1;
+}
+
+// rank[seq] = position in the sorted list (INF for the non-existent slots, which sort last)
+__global__ void __launch_bounds__(SEG_THREADS)
+k_rank_scatter(const u32* __restrict__ sorted_seq, u32* __restrict__ rank, size_t stride, int n_slots, int n_edges) {
+    const int frame = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_slots) return;
+    u32 seq = sorted_seq[(size_t)frame * stride + i];
+    rank[(size_t)frame * stride + seq] = i < n_edges ? (u32)i : DOFS_INF32;
+}
+
+// parity hook: sorted (start, end) from the sorted sequence numbers
+__global__ void __launch_bounds__(SEG_THREADS)
+k_edges_decode(const u32* __restrict__ sorted_seq, int* __restrict__ start, int* __restrict__ end, int W, int n_edges) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_edges) return;
+    u32 seq = sorted_seq[i];
+    int s = (int)(seq >> 2);
+    start[i] = s;
+    end[i] = edge_other(s, (int)(seq & 3u), W);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K9a  Boruvka levels
+// ---------------------------------------------------------------------------------------------
+struct BorState {
+    u32* comp;       // [F][N] current component root of each pixel
+    u32* best;       // [F][N] per root: minimum rank of an outgoing edge in this level
+    u32* newp;       // [F][N] per root: hook target in this level
+    u32* loss_time;  // [F][N] per root id: sorted position of the edge at which it loses (INF: never)
+    u32* up;         // [F][N] per root id: root of the next-level component it is contracted into
+    u8* lvl;         // [F][N] per root id: level at which it loses == its final union-find rank
+    int* n_roots;    // [F] number of roots after the current level
+};
+
+__global__ void __launch_bounds__(SEG_THREADS)
+k_bor_init(BorState S, const float2* __restrict__ flow, int* __restrict__ rsize, ushort4* __restrict__ rbbox,
+           float2* __restrict__ rflow, u64* __restrict__ best_score, u32* __restrict__ sel_time,
+           int* __restrict__ sel_box, int W, int N) {
+    const int frame = blockIdx.y;
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= N) return;
+    const size_t g = (size_t)frame * N + p;
+    S.comp[g] = (u32)p;
+    S.best[g] = DOFS_INF32;
+    S.newp[g] = (u32)p;
+    S.loss_time[g] = DOFS_INF32;
+    S.up[g] = (u32)p;
+    S.lvl[g] = 0;
+    // Forest::Forest (graph.cpp:129-148): singleton sets
+    rsize[g] = 1;
+    const int y = p / W, x = p - y * W;
+    rbbox[g] = make_ushort4((u16)x, (u16)y, (u16)x, (u16)y);
+    rflow[g] = flow[g];
+    best_score[g] = 0ull;
+    sel_time[g] = DOFS_INF32;
+    sel_box[g] = -1;
+}
+
+// every edge whose endpoints are in different components offers its rank to both components
+__global__ void __launch_bounds__(SEG_THREADS)
+k_bor_pixel(BorState S, const u32* __restrict__ rank, size_t rank_stride, int W, int N) {
+    const int frame = blockIdx.y;
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= N) return;
+    const u32* comp = S.comp + (size_t)frame * N;
+    u32* best = S.best + (size_t)frame * N;
+    const uint4 r4 = *reinterpret_cast<const uint4*>(rank + (size_t)frame * rank_stride + 4 * (size_t)p);
+    const u32 r[4] = {r4.x, r4.y, r4.z, r4.w};
+    const u32 cp = comp[p];
+    u32 mine = DOFS_INF32;
+#pragma unroll
+    for (int d = 0; d < 4; ++d) {
+        if (r[d] != DOFS_INF32) {
+            u32 cq = comp[edge_other(p, d, W)];
+            if (cq != cp) {
+                mine = min(mine, r[d]);
+                atomicMin(&best[cq], r[d]);
+            }
+        }
+    }
+    if (mine != DOFS_INF32) atomicMin(&best[cp], mine);
+}
+
+// per root: classify its pick (mutual winner / loser), record the loss
+__global__ void __launch_bounds__(SEG_THREADS)
+k_bor_root(BorState S, const u32* __restrict__ sorted_seq, size_t seq_stride, int W, int N, int level) {
+    const int frame = blockIdx.y;
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= N) return;
+    const size_t fo = (size_t)frame * N;
+    const u32* comp = S.comp + fo;
+    if (comp[c] != (u32)c) return;
+    const u32 t = S.best[fo + c];
+    if (t == DOFS_INF32) {  // the last component
+        S.newp[fo + c] = (u32)c;
+        return;
+    }
+    const u32 seq = sorted_seq[(size_t)frame * seq_stride + t];
+    const int s = (int)(seq >> 2);
+    const int e = edge_other(s, (int)(seq & 3u), W);
+    const u32 cs = comp[s], ce = comp[e];
+    const u32 other = (cs == (u32)c) ? ce : cs;
+    const bool mutual = S.best[fo + other] == t;
+    if (mutual && ce == (u32)c) {
+        S.newp[fo + c] = (u32)c;  // rank tie: the `end` side survives (graph.cpp:177-182, 210-213)
+    } else {
+        S.newp[fo + c] = other;
+        S.loss_time[fo + c] = t;
+        S.lvl[fo + c] = (u8)level;
+    }
+}
+
+// contract: every pixel follows the hooks to the group root; losers remember it in `up`
+__global__ void __launch_bounds__(SEG_THREADS)
+k_bor_relabel(BorState S, int N) {
+    const int frame = blockIdx.y;
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= N) return;
+    const size_t fo = (size_t)frame * N;
+    const u32 c = S.comp[fo + p];
+    const volatile u32* newp = S.newp + fo;
+    u32 g = c;
+    for (;;) {
+        u32 nx = newp[g];
+        if (nx == g) break;
+        g = nx;
+    }
+    if (c == (u32)p) {  // p was a root in this level
+        S.best[fo + p] = DOFS_INF32;
+        if (g != (u32)p) S.up[fo + p] = g;
+        else atomicAdd(&S.n_roots[frame], 1);
+    }
+    if (g != c) S.comp[fo + p] = g;
+}
+
+// final root: its level is the number of levels
+__global__ void __launch_bounds__(SEG_THREADS)
+k_bor_finish(BorState S, int N, int levels) {
+    const int frame = blockIdx.y;
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= N) return;
+    const size_t g = (size_t)frame * N + p;
+    if (S.loss_time[g] == DOFS_INF32) S.lvl[g] = (u8)levels;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K9b  winner of every merge event (one event per losing root) and the event sort key
+//      key = lvl[winner] << 56 | winner << 32 | time ; payload = loser
+// ---------------------------------------------------------------------------------------------
+#define EV_KEY_NONE 0xFFFFFFFFFFFFFFFFull
+
+__global__ void __launch_bounds__(SEG_THREADS)
+k_event_keys(BorState S, u32* __restrict__ win, u64* __restrict__ ev_key, int N) {
+    const int frame = blockIdx.y;
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= N) return;
+    const size_t fo = (size_t)frame * N;
+    const u32 t = S.loss_time[fo + c];
+    if (t == DOFS_INF32) {
+        win[fo + c] = (u32)c;
+        ev_key[fo + c] = EV_KEY_NONE;
+        return;
+    }
+    u32 cur = S.up[fo + c];
+    while (S.loss_time[fo + cur] < t) cur = S.up[fo + cur];
+    win[fo + c] = cur;
+    ev_key[fo + c] = ((u64)S.lvl[fo + cur] << 56) | ((u64)cur << 32) | (u64)t;
+}
+
+// first event index of every wave (events are sorted by key; wave = key >> 56)
+__global__ void __launch_bounds__(SEG_THREADS)
+k_wave_starts(const u64* __restrict__ ev_key, int* __restrict__ wave_start /* [F][64] */, int N) {
+    const int frame = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const u64* k = ev_key + (size_t)frame * N;
+    const u64 ki = k[i];
+    const int wi = ki == EV_KEY_NONE ? 63 : (int)(ki >> 56);
+    const int wp = i == 0 ? -1 : (k[i - 1] == EV_KEY_NONE ? 63 : (int)(k[i - 1] >> 56));
+    // waves without events keep the start of the next non-empty wave
+    for (int w = wp + 1; w <= wi; ++w) wave_start[frame * 64 + w] = i;
+    if (i == N - 1)
+        for (int w = wi + 1; w < 64; ++w) wave_start[frame * 64 + w] = N;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K9c + K10  chain replay of one wave: thread per chain head.  Forest::merge (graph.cpp:170-218)
+// state update per absorbed root, then the size / row / move gates of Forest::new_merge
+// (graph.cpp:280-300); survivors are queued for lifting.
+// ---------------------------------------------------------------------------------------------
+struct ReplayArgs {
+    const u64* ev_key;     // [F][N] sorted
+    const u32* ev_loser;   // [F][N] sorted payload
+    const int* wave_start; // [F][64]
+    int* rsize;            // [F][N]
+    ushort4* rbbox;        // [F][N]
+    float2* rflow;         // [F][N]
+    Candidate* cand;       // [F][cand_cap]
+    int* n_cand;           // [F]
+    int* longest_chain;    // [F]
+    int cand_cap;
+    int W, H, N;
+    int min_size;
+};
+
+__global__ void __launch_bounds__(SEG_THREADS)
+k_replay_wave(ReplayArgs A, int wave) {
+    const int frame = blockIdx.y;
+    const int w0 = A.wave_start[frame * 64 + wave], w1 = A.wave_start[frame * 64 + wave + 1];
+    const int i = w0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= w1) return;
+    const size_t fo = (size_t)frame * A.N;
+    const u64* key = A.ev_key + fo;
+    const u64 k0 = key[i];
+    const u32 chain = (u32)(k0 >> 32);  // wave | winner
+    if (i > w0 && (u32)(key[i - 1] >> 32) == chain) return;  // not the head of its chain
+    const u32 r = chain & 0x00FFFFFFu;
+    int s = A.rsize[fo + r];
+    float2 f = A.rflow[fo + r];
+    ushort4 bb = A.rbbox[fo + r];
+    const int y = (int)r / A.W;
+    const bool row_ok = !(y < A.H / 10);                                  // graph.cpp:288
+    const double move_min = ddiv((double)(3 * (y + 1)), (double)A.H);     // graph.cpp:296
+    int j = i;
+    u64 kj = k0;
+    for (;;) {
+        const u32 a = A.ev_loser[fo + j];
+        const int sa = A.rsize[fo + a];
+        const float2 fa = A.rflow[fo + a];
+        const ushort4 ba = A.rbbox[fo + a];
+        // (flow_a * size_a + flow_b * size_b) / (size_a + size_b) with OpenCV's Vec2f rounding
+        const float fsa = (float)sa, fsb = (float)s;
+        const float sx = fadd(fmul(fa.x, fsa), fmul(f.x, fsb));
+        const float sy = fadd(fmul(fa.y, fsa), fmul(f.y, fsb));
+        const double inv = ddiv(1.0, (double)(sa + s));
+        f.x = (float)dmul((double)sx, inv);
+        f.y = (float)dmul((double)sy, inv);
+        s += sa;
+        bb.x = min(bb.x, ba.x);
+        bb.y = min(bb.y, ba.y);
+        bb.z = max(bb.z, ba.z);
+        bb.w = max(bb.w, ba.w);
+        if (s >= A.min_size && row_ok) {
+            const double move = norm2d(f.x, f.y);
+            if (!(move < move_min)) {
+                int slot = atomicAdd(&A.n_cand[frame], 1);
+                if (slot < A.cand_cap) {
+                    Candidate c;
+                    c.root = r;
+                    c.time = (u32)kj;
+                    c.size = s;
+                    c.fx = f.x;
+                    c.fy = f.y;
+                    c.bbox[0] = bb.x;
+                    c.bbox[1] = bb.y;
+                    c.bbox[2] = bb.z;
+                    c.bbox[3] = bb.w;
+                    c.pad = 0;
+                    A.cand[(size_t)frame * A.cand_cap + slot] = c;
+                }
+            }
+        }
+        ++j;
+        if (j >= w1) break;
+        kj = key[j];
+        if ((u32)(kj >> 32) != chain) break;
+    }
+    A.rsize[fo + r] = s;
+    A.rflow[fo + r] = f;
+    A.rbbox[fo + r] = bb;
+    atomicMax(&A.longest_chain[frame], j - i);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K11 + K12  lifting of the queued merges, per-root first-maximum selection, box records, labels
+// ---------------------------------------------------------------------------------------------
+struct SelectArgs {
+    const Candidate* cand;  // [F][cand_cap]
+    const int* n_cand;      // [F]
+    double* cand_score;     // [F][cand_cap]  score if the merge passed every gate, else -1
+    u64* best_score;        // [F][N] bit pattern of the best score per root (0 = none)
+    u32* sel_time;          // [F][N] time of the first merge reaching the best score
+    int* sel_box;           // [F][N] index of the root's box in the sorted box list
+    int* n_scored;          // [F]
+    int* n_boxes;           // [F]
+    int cand_cap;
+    int N;
+};
+
+// graph.cpp:302-348: convexity, get_score, class-dependent convexity gate, score threshold
+__global__ void __launch_bounds__(128)
+k_lift_score(SelectArgs A, SegParams P) {
+    const int frame = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = min(A.n_cand[frame], A.cand_cap);
+    if (i >= n) return;
+    const Candidate c = A.cand[(size_t)frame * A.cand_cap + i];
+    const int xmin = c.bbox[0], ymin = c.bbox[1], xmax = c.bbox[2], ymax = c.bbox[3];
+    const double rect_area = (double)((xmax - xmin + 1) * (ymax - ymin + 1));
+    const double convexity = ddiv((double)c.size, rect_area);
+    LiftSolution sol;
+    const double score = lift_get_score(c.fx, c.fy, xmin, ymin, xmax, ymax, P, &sol);
+    double kept = -1.0;
+    if (score != -1.0) {
+        const double min_convexity = P.cls_min_convexity[sol.cls];
+        if (!(convexity < min_convexity) && score > P.score_threshold) kept = score;
+    }
+    A.cand_score[(size_t)frame * A.cand_cap + i] = kept;
+    if (kept > 0.0) {
+        atomicMax((unsigned long long*)&A.best_score[(size_t)frame * A.N + c.root],
+                  (unsigned long long)__double_as_longlong(kept));
+        atomicAdd(&A.n_scored[frame], 1);
+    }
+}
+
+// history keeps the FIRST merge (in time) that reaches the maximum score (strict '<', graph.cpp:352)
+__global__ void __launch_bounds__(SEG_THREADS)
+k_select_time(SelectArgs A) {
+    const int frame = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = min(A.n_cand[frame], A.cand_cap);
+    if (i >= n) return;
+    const double sc = A.cand_score[(size_t)frame * A.cand_cap + i];
+    if (!(sc > 0.0)) return;
+    const Candidate c = A.cand[(size_t)frame * A.cand_cap + i];
+    if ((u64)__double_as_longlong(sc) == A.best_score[(size_t)frame * A.N + c.root])
+        atomicMin(&A.sel_time[(size_t)frame * A.N + c.root], c.time);
+}
+
+struct BoxRec;  // == dofs3d_box (include/dofs3d.h); defined in dofs3d.cu
+
+template <typename Box>
+DOFS_D void fill_box(Box* b, const Candidate& c, double score, const LiftSolution& s) {
+    b->root = (int)c.root;
+    b->size = c.size;
+    b->cls = s.cls;
+    b->parent_box = -1;
+    b->bbox[0] = c.bbox[0];
+    b->bbox[1] = c.bbox[1];
+    b->bbox[2] = c.bbox[2];
+    b->bbox[3] = c.bbox[3];
+    b->time = c.time;
+    b->mean_flow[0] = c.fx;
+    b->mean_flow[1] = c.fy;
+    b->pad_ = 0.f;
+    b->score = score;
+    b->move = norm2d(c.fx, c.fy);
+    b->orient = s.orient;
+    b->w_error = s.w_error;
+    b->h_error = s.h_error;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        b->ps_bev[2 * k] = s.ps_bev[k].x;
+        b->ps_bev[2 * k + 1] = s.ps_bev[k].y;
+        b->rectangle[2 * k] = s.rect[k].x;
+        b->rectangle[2 * k + 1] = s.rect[k].y;
+        b->lower_face[2 * k] = s.lower[k].x;
+        b->lower_face[2 * k + 1] = s.lower[k].y;
+        b->upper_face[2 * k] = s.upper[k].x;
+        b->upper_face[2 * k + 1] = s.upper[k].y;
+    }
+}
+
+// the selected merge of every root emits its box (unsorted) — lifting recomputed for the few winners
+template <typename Box>
+__global__ void __launch_bounds__(128)
+k_emit_boxes(SelectArgs A, SegParams P, Box* __restrict__ tmp_boxes, int box_cap) {
+    const int frame = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = min(A.n_cand[frame], A.cand_cap);
+    if (i >= n) return;
+    const double sc = A.cand_score[(size_t)frame * A.cand_cap + i];
+    if (!(sc > 0.0)) return;
+    const Candidate c = A.cand[(size_t)frame * A.cand_cap + i];
+    const size_t g = (size_t)frame * A.N + c.root;
+    if ((u64)__double_as_longlong(sc) != A.best_score[g] || c.time != A.sel_time[g]) return;
+    const int slot = atomicAdd(&A.n_boxes[frame], 1);
+    if (slot >= box_cap) return;
+    LiftSolution sol;
+    const double score = lift_get_score(c.fx, c.fy, c.bbox[0], c.bbox[1], c.bbox[2], c.bbox[3], P, &sol);
+    fill_box(&tmp_boxes[(size_t)frame * box_cap + slot], c, score, sol);
+}
+
+// order boxes by ascending root (the order of the reference's history vector) — counting rank, the
+// list is a few hundred entries; then the nesting parent of every box
+template <typename Box>
+__global__ void __launch_bounds__(SEG_THREADS)
+k_sort_boxes(const Box* __restrict__ tmp_boxes, Box* __restrict__ boxes, const int* __restrict__ n_boxes, int box_cap,
+             int* __restrict__ sel_box, int N) {
+    const int frame = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = min(n_boxes[frame], box_cap);
+    if (i >= n) return;
+    const Box* src = tmp_boxes + (size_t)frame * box_cap;
+    const int root = src[i].root;
+    int pos = 0;
+    for (int j = 0; j < n; ++j) pos += src[j].root < root ? 1 : 0;
+    boxes[(size_t)frame * box_cap + pos] = src[i];
+    sel_box[(size_t)frame * N + root] = pos;
+}
+
+// Walk the union-find link forest (parent = winner at loss time, <= max-rank hops): a pixel / set that
+// entered root a's set at time t_in belongs to a's snapshot taken at sel_time[a] iff t_in <= sel_time[a].
+DOFS_D int first_box_above(const u32* loss_time, const u32* win, const u32* sel_time, const int* sel_box, u32 cur,
+                           bool include_self) {
+    u32 t_in = 0;
+    bool first = include_self;
+    if (!include_self) {
+        t_in = loss_time[cur];
+        if (t_in == DOFS_INF32) return -1;
+        cur = win[cur];
+    }
+    for (;;) {
+        const u32 st = sel_time[cur];
+        if (st != DOFS_INF32 && (first || st >= t_in)) return sel_box[cur];
+        first = false;
+        t_in = loss_time[cur];
+        if (t_in == DOFS_INF32) return -1;
+        cur = win[cur];
+    }
+}
+
+template <typename Box>
+__global__ void __launch_bounds__(SEG_THREADS)
+k_box_parents(Box* __restrict__ boxes, const int* __restrict__ n_boxes, int box_cap, const u32* __restrict__ loss_time,
+              const u32* __restrict__ win, const u32* __restrict__ sel_time, const int* __restrict__ sel_box, int N) {
+    const int frame = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = min(n_boxes[frame], box_cap);
+    if (i >= n) return;
+    const size_t fo = (size_t)frame * N;
+    Box* b = boxes + (size_t)frame * box_cap + i;
+    b->parent_box = first_box_above(loss_time + fo, win + fo, sel_time + fo, sel_box + fo, (u32)b->root, false);
+}
+
+__global__ void __launch_bounds__(SEG_THREADS)
+k_labels(int* __restrict__ labels, const u32* __restrict__ loss_time, const u32* __restrict__ win,
+         const u32* __restrict__ sel_time, const int* __restrict__ sel_box, int N) {
+    const int frame = blockIdx.y;
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= N) return;
+    const size_t fo = (size_t)frame * N;
+    labels[fo + p] = first_box_above(loss_time + fo, win + fo, sel_time + fo, sel_box + fo, (u32)p, true);
+}
+
+// dofs3d_lift: get_bottom_variants for n independent problems
+template <typename Box>
+__global__ void __launch_bounds__(128)
+k_lift_problems(const float2* __restrict__ dir, const int4* __restrict__ bbox, const int* __restrict__ cls, int n,
+                SegParams P, Box* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int c = cls[i];
+    const int4 b = bbox[i];
+    LiftSolution s;
+    lift_bottom_variants(dir[i].x, dir[i].y, b.x, b.y, b.z, b.w, P.hg.persp, P.hg.inv, P.hg.upper[c], c,
+                         P.cls_size[c][0], P.cls_size[c][1], &s);
+    Candidate cd;
+    cd.root = 0;
+    cd.time = 0;
+    cd.size = s.has_rect;
+    cd.fx = dir[i].x;
+    cd.fy = dir[i].y;
+    cd.bbox[0] = (u16)b.x;
+    cd.bbox[1] = (u16)b.y;
+    cd.bbox[2] = (u16)b.z;
+    cd.bbox[3] = (u16)b.w;
+    cd.pad = 0;
+    fill_box(&out[i], cd, ddiv(dadd(s.w_error, s.h_error), 2.0), s);
+    if (!s.has_rect) out[i].cls = c;
+}

@@ -1,0 +1,169 @@
+/* dofs3d.h — C ABI of the B200 (sm_100a) implementation of the hot path of
+ * DmitriyZhuravlev/DenseOpticalFlowSegmentation3D:
+ *
+ *     frame pair -> dense Farneback flow -> flow-graph clustering -> per-cluster 3D box lifting
+ *
+ * The reference has no FFI layer; its boundary for this path is the set of C++ symbols in cpp/inc
+ * (see SURVEY.md section 8b).  Each entry point below names the reference interface it stands in
+ * for (file:line under the reference tree).  All pointers are plain HOST pointers unless the
+ * function name ends in `_dev` (then every data pointer is a DEVICE pointer on the context's GPU and
+ * the call is asynchronous on the context's stream; dofs3d_sync() waits for it).
+ *
+ * All functions return 0 on success and a negative dofs3d_status on failure; there is NO CPU
+ * fallback: without a CUDA device every call fails with DOFS3D_ERR_CUDA.
+ * A context is bound to one GPU and is thread-compatible (one thread at a time per context).
+ */
+#ifndef DOFS3D_H
+#define DOFS3D_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dofs3d_ctx dofs3d_ctx;
+
+typedef enum {
+    DOFS3D_OK = 0,
+    DOFS3D_ERR_ARG = -1,      /* bad argument (null pointer, size out of range, n_pairs > max_pairs) */
+    DOFS3D_ERR_CUDA = -2,     /* CUDA runtime error, or no CUDA device present */
+    DOFS3D_ERR_NOMEM = -3,    /* device allocation failed */
+    DOFS3D_ERR_OVERFLOW = -4, /* more boxes/candidates than the caller-provided capacity */
+    DOFS3D_ERR_INTERNAL = -5
+} dofs3d_status;
+
+/* Every constant the reference hard-codes on this path, in one POD (SURVEY.md section 5 "Config"). */
+typedef struct {
+    float persp[9];        /* get_mat().first            lifting_3d.cpp:482-514 */
+    float inv[9];          /* get_mat().second           lifting_3d.cpp:482-514 */
+    float inv_upper[3][9]; /* get_mat_upper(cls)         lifting_3d.cpp:441-480 */
+    double pyr_scale;      /* 0.5   calcOpticalFlowFarneback arguments, segment.cpp:101 */
+    int levels;            /* 3   */
+    int winsize;           /* 15  */
+    int iters;             /* 3   */
+    int poly_n;            /* 5   */
+    double poly_sigma;     /* 1.2 */
+    double blur_sigma;     /* 3.0   GaussianBlur(flow, Size(0,0), 3.0), segment.cpp:52 */
+    int neighbors;         /* 8     get_segmented_array(..., neighbor = 8), segment.cpp:36,154 */
+    int min_size;          /* 500   Forest::new_merge default, graph.hpp:94 */
+    double score_threshold;/* 0.3   Forest::new_merge default, graph.hpp:93 */
+    int cls_size[3][2];    /* {258,84},{349,165},{370,180}   getObjSize, lifting_3d.cpp:255-259 */
+    double cls_min_convexity[3]; /* 3/4, 1/2, 20/29          graph.cpp:328-339 */
+} dofs3d_params;
+
+/* One entry of Forest::get_best_segments() (graph.cpp:391-429) without its pixel set: a
+ * SegmentData{score, seg, sol, move} (graph.hpp:48-57) with sol = Solution (graph.hpp:25-46).
+ * The pixel set is carried by the label image, see dofs3d_segment. */
+typedef struct {
+    int32_t root;        /* union-find root id = y*W + x of the representative pixel (index into history) */
+    int32_t size;        /* |seg| at the snapshot */
+    int32_t cls;         /* Solution::cls */
+    int32_t parent_box;  /* index (in this frame's box list) of the smallest box whose pixel set strictly
+                            contains this one, or -1; segments nest because they are merge-tree nodes */
+    int32_t bbox[4];     /* xmin, ymin, xmax, ymax of the pixel set (Forest::get_bounding_box, graph.cpp:446) */
+    uint32_t time;       /* position of the merging edge in the sorted edge list (snapshot instant) */
+    float mean_flow[2];  /* Node::flow_value of the root at the snapshot (graph.cpp:184-190) */
+    float pad_;
+    double score;        /* (w_error + h_error) / 2            graph.cpp:257-260 */
+    double move;         /* |mean_flow|                        graph.cpp:294 */
+    double orient;       /* Solution::orient (yaw, rad, BEV)   lifting_3d.cpp:244 */
+    double w_error;      /* Solution::w_error */
+    double h_error;      /* Solution::h_error */
+    float ps_bev[8];     /* Solution::ps_bev      4 x (x, y) */
+    float rectangle[8];  /* Solution::rectangle   4 x (x, y), BEV ground rectangle */
+    float lower_face[8]; /* Solution::lower_face  4 x (x, y), image */
+    float upper_face[8]; /* Solution::upper_face  4 x (x, y), image */
+} dofs3d_box;
+
+/* Work counters of one frame pair: the gates of Forest::new_merge (graph.cpp:280-375). */
+typedef struct {
+    int32_t n_edges;       /* edges built by build_graph (graph.cpp:62-93) */
+    int32_t n_merges;      /* calls of Forest::new_merge that merged (== W*H - 1) */
+    int32_t n_levels;      /* number of Boruvka levels == maximum union-find rank reached */
+    int32_t n_candidates;  /* merges that passed the size, row and move gates (== get_score calls) */
+    int32_t n_scored;      /* ... of those with a valid rectangle that passed convexity and score gates */
+    int32_t n_boxes;       /* history entries (roots with a kept snapshot) */
+    int32_t longest_chain; /* longest run of merges won by one root (serial depth of the replay) */
+    int32_t pad_;
+} dofs3d_stats;
+
+/* Fills *p with the reference's constants (homographies from get_mat/get_mat_upper, etc.). */
+void dofs3d_default_params(dofs3d_params* p);
+
+/* Context for frames of width x height on GPU `device`; at most max_pairs frame pairs per call.
+ * params == NULL selects dofs3d_default_params. */
+int dofs3d_create(dofs3d_ctx** out, int device, int width, int height, int max_pairs, const dofs3d_params* params);
+void dofs3d_destroy(dofs3d_ctx* ctx);
+int dofs3d_sync(dofs3d_ctx* ctx);
+const char* dofs3d_last_error(const dofs3d_ctx* ctx);
+/* Raw cudaStream_t of the context (as void*), for callers that time with CUDA events. */
+void* dofs3d_stream(dofs3d_ctx* ctx);
+/* Number of kernel launches issued by this context so far. */
+long long dofs3d_launch_count(const dofs3d_ctx* ctx);
+/* Bytes of device memory held by the context. */
+long long dofs3d_device_bytes(const dofs3d_ctx* ctx);
+
+/* cv::cvtColor(BGR2GRAY) (segment.cpp:97-98) for n frames: bgr [n][H][W][3] -> gray [n][H][W]. */
+int dofs3d_gray(dofs3d_ctx* ctx, const uint8_t* bgr, int n_frames, uint8_t* gray_out);
+
+/* cv::calcOpticalFlowFarneback(gray0, gray1, flow, pyr_scale, levels, winsize, iters, poly_n,
+ * poly_sigma, 0) (segment.cpp:101) for n_pairs independent pairs:
+ * gray0/gray1 [n][H][W] u8 -> flow_out [n][H][W][2] f32 (x, y interleaved, CV_32FC2). */
+int dofs3d_flow(dofs3d_ctx* ctx, const uint8_t* gray0, const uint8_t* gray1, int n_pairs, float* flow_out);
+
+/* cv::GaussianBlur(flow, flow, Size(0,0), blur_sigma) (segment.cpp:52): [n][H][W][2] f32. */
+int dofs3d_blur(dofs3d_ctx* ctx, const float* flow_in, int n_pairs, float* flow_out);
+
+/* get_segmented_array (segment.cpp:34-72) + Forest::get_best_segments (graph.cpp:391-429) for
+ * n_pairs flow fields.  already_blurred != 0 skips the GaussianBlur of segment.cpp:52 (the parity
+ * tests feed both sides the same blurred bits).  Outputs, all optional (NULL to skip):
+ *   labels_out   [n][H][W] int32: index of the SMALLEST box of that frame containing the pixel, -1 if
+ *                none.  Pixel set of box b = pixels labelled b or labelled with a box whose parent_box
+ *                chain reaches b.
+ *   boxes_out    [n][max_boxes] boxes sorted by ascending root (the order of the history vector)
+ *   n_boxes_out  [n]
+ *   stats_out    [n]
+ *   flow_blurred_out [n][H][W][2]: the blurred field the graph was built on. */
+int dofs3d_segment(dofs3d_ctx* ctx, const float* flow, int already_blurred, int n_pairs, int32_t* labels_out,
+                   dofs3d_box* boxes_out, int32_t* n_boxes_out, int max_boxes, dofs3d_stats* stats_out,
+                   float* flow_blurred_out);
+
+/* get_bottom_variants (lifting_3d.cpp:350-439) for n independent (direction, box, cls) problems:
+ * dir2 [n][2], bbox4 [n][4] = xmin,ymin,xmax,ymax, cls [n].  out[i].score = (w_error+h_error)/2,
+ * out[i].size = 1 when the solution has a rectangle, 0 otherwise (Solution::rectangle.empty()). */
+int dofs3d_lift(dofs3d_ctx* ctx, const float* dir2, const int32_t* bbox4, const int32_t* cls, int n, dofs3d_box* out);
+
+/* build_graph (graph.cpp:51-103) on one blurred flow field: the sorted edge list.  Outputs hold
+ * 4*W*H entries; returns the number of edges (>= 0) or a negative status. */
+long long dofs3d_edges_sorted(dofs3d_ctx* ctx, const float* flow_blurred, int32_t* start, int32_t* end,
+                              uint64_t* weight_bits);
+
+/* The whole path of main()/main1() (segment.cpp:97-101,154 / 222-226,250): n_frames consecutive BGR
+ * frames [n][H][W][3] -> n_frames-1 pairs (pair i = frames i, i+1): gray, Farneback, blur, graph,
+ * segmentation, lifting.  Outputs as dofs3d_segment with n = n_frames - 1. */
+int dofs3d_process(dofs3d_ctx* ctx, const uint8_t* bgr_frames, int n_frames, int32_t* labels_out,
+                   dofs3d_box* boxes_out, int32_t* n_boxes_out, int max_boxes, dofs3d_stats* stats_out);
+
+/* Device-pointer variants (inputs and outputs resident in HBM, asynchronous on dofs3d_stream). */
+int dofs3d_process_dev(dofs3d_ctx* ctx, const uint8_t* d_bgr_frames, int n_frames, int32_t* d_labels_out,
+                       dofs3d_box* d_boxes_out, int32_t* d_n_boxes_out, int max_boxes, dofs3d_stats* d_stats_out);
+int dofs3d_segment_dev(dofs3d_ctx* ctx, const float* d_flow, int already_blurred, int n_pairs, int32_t* d_labels_out,
+                       dofs3d_box* d_boxes_out, int32_t* d_n_boxes_out, int max_boxes, dofs3d_stats* d_stats_out);
+int dofs3d_flow_dev(dofs3d_ctx* ctx, const uint8_t* d_gray0, const uint8_t* d_gray1, int n_pairs, float* d_flow_out);
+
+/* Synthetic video of SURVEY.md section 8d (integer-defined, bit-identical to the host generator
+ * denseopticalflowsegmentation3d_b200/synth.py): frames first_frame .. first_frame+n_frames-1 of the
+ * stream `seed`, written as BGR u8 [n][H][W][3] to DEVICE memory. */
+int dofs3d_synth_frames_dev(dofs3d_ctx* ctx, uint32_t seed, int n_objects, int first_frame, int n_frames,
+                            uint8_t* d_bgr_out);
+
+/* Per-stage device time (ms, CUDA events on the context's stream) of the last process/segment/flow
+ * call when timing was enabled with dofs3d_set_timing(ctx, 1): names/values of up to cap stages. */
+int dofs3d_set_timing(dofs3d_ctx* ctx, int enabled);
+int dofs3d_get_timing(dofs3d_ctx* ctx, const char** names, float* ms, int cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DOFS3D_H */
