@@ -1,0 +1,904 @@
+// dofs3d.cu — context, orchestration and the C ABI (include/dofs3d.h) of the sm_100a hot path.
+//
+// One context per GPU.  A call processes a batch of up to max_pairs independent frame pairs; every
+// kernel takes the frame index from blockIdx.y, so one launch covers the whole batch and the grid is
+// many multiples of the 148 SMs.  All per-frame arrays are [frame][element] in HBM.
+//
+// There is no CPU path in this file: without a CUDA device dofs3d_create fails.
+#include "../../include/dofs3d.h"
+
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "dofs_common.cuh"
+#include "dofs_flow.cuh"
+#include "dofs_lift.cuh"
+#include "dofs_seg.cuh"
+#include "dofs_sort.cuh"
+#include "dofs_synth.cuh"
+
+static_assert(sizeof(dofs3d_box) == 216, "dofs3d_box layout");
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+// host-side setup arithmetic (once per context)
+// ---------------------------------------------------------------------------------------------
+
+// cv::getPerspectiveTransform as the reference uses it (lifting_3d.cpp:479,510-511): the 8x8 system
+// of the four point correspondences solved by LU with partial pivoting in double, M[8] = 1, result
+// rounded to float.
+void perspective_transform(const double src[4][2], const double dst[4][2], float out[9]) {
+    double a[8][9];
+    for (int i = 0; i < 4; ++i) {
+        const double x = src[i][0], y = src[i][1], u = dst[i][0], v = dst[i][1];
+        const double top[9] = {x, y, 1, 0, 0, 0, -x * u, -y * u, u};
+        const double bot[9] = {0, 0, 0, x, y, 1, -x * v, -y * v, v};
+        memcpy(a[i], top, sizeof top);
+        memcpy(a[i + 4], bot, sizeof bot);
+    }
+    for (int col = 0; col < 8; ++col) {
+        int piv = col;
+        for (int r = col + 1; r < 8; ++r)
+            if (fabs(a[r][col]) > fabs(a[piv][col])) piv = r;
+        if (piv != col)
+            for (int c = col; c < 9; ++c) std::swap(a[col][c], a[piv][c]);
+        const double d = -1.0 / a[col][col];
+        for (int r = col + 1; r < 8; ++r) {
+            const double f = a[r][col] * d;
+            for (int c = col + 1; c < 9; ++c) a[r][c] += f * a[col][c];
+        }
+    }
+    double sol[8];
+    for (int r = 7; r >= 0; --r) {
+        double s = a[r][8];
+        for (int c = r + 1; c < 8; ++c) s -= a[r][c] * sol[c];
+        sol[r] = s / a[r][r];
+    }
+    for (int i = 0; i < 8; ++i) out[i] = (float)sol[i];
+    out[8] = 1.0f;
+}
+
+// cv::getGaussianKernel(ksize, sigma, CV_32F): taps rounded to float, normalised by the double sum
+// of the rounded taps.
+void gaussian_taps(int ksize, double sigma, float* out) {
+    if (sigma <= 0) sigma = ((ksize - 1) * 0.5 - 1) * 0.3 + 0.8;
+    if (ksize == 3 && sigma <= 0) {  // unreachable after the line above; small fixed kernels only for sigma <= 0
+    }
+    const double scale2x = -0.5 / (sigma * sigma);
+    double sum = 0;
+    for (int i = 0; i < ksize; ++i) {
+        const double x = i - (ksize - 1) * 0.5;
+        out[i] = (float)exp(scale2x * x * x);
+        sum += out[i];
+    }
+    sum = 1.0 / sum;
+    for (int i = 0; i < ksize; ++i) out[i] = (float)(out[i] * sum);
+}
+
+int ceil_log2(unsigned long long v) {
+    int b = 0;
+    while ((1ull << b) < v) ++b;
+    return b;
+}
+
+struct StageTimer {
+    std::vector<std::pair<const char*, cudaEvent_t>> marks;
+    struct Row {
+        std::string name;
+        float ms;
+        int count;
+    };
+    std::vector<Row> result;
+    bool enabled = false;
+};
+
+}  // namespace
+
+struct dofs3d_ctx {
+    int device = 0, W = 0, H = 0, N = 0, F = 0;
+    size_t S = 0;  // edge slots per frame = 4N
+    dofs3d_params prm;
+    SegParams seg;
+    BlurTaps taps;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    long long launches = 0;
+    long long bytes = 0;
+    std::vector<void*> allocs;
+    StageTimer timer;
+
+    // segmentation buffers
+    float2 *flow_in = nullptr, *flow_tmp = nullptr, *flow_blur = nullptr;
+    u64 *keysA = nullptr, *keysB = nullptr;
+    u32 *valsA = nullptr, *valsB = nullptr;
+    u32 *tile_hist = nullptr, *digit_tot = nullptr;
+    int num_tiles = 0;
+    BorState bor;
+    u32* win = nullptr;
+    int* wave_start = nullptr;
+    int* rsize = nullptr;
+    ushort4* rbbox = nullptr;
+    float2* rflow = nullptr;
+    u64* best_score = nullptr;
+    u32* sel_time = nullptr;
+    int* sel_box = nullptr;
+    Candidate* cand = nullptr;
+    double* cand_score = nullptr;
+    int cand_cap = 0, box_cap = 0;
+    int* counters = nullptr;    // [5][F]: n_cand, longest_chain, n_scored, n_boxes, n_roots
+    int* h_counters = nullptr;  // pinned mirror
+    dofs3d_box *boxes_tmp = nullptr, *boxes = nullptr;
+    int32_t* labels = nullptr;
+    dofs3d_stats* stats = nullptr;
+    std::vector<int> levels_of_frame;
+
+    // flow buffers
+    FlowBuffers fb;
+    u8 *bgr = nullptr, *gray = nullptr;  // [F+1] frames
+    float2* flow_raw = nullptr;          // [F][N] Farneback output
+};
+
+namespace {
+
+#define CK(call)                                                                                      \
+    do {                                                                                              \
+        cudaError_t e_ = (call);                                                                      \
+        if (e_ != cudaSuccess) {                                                                      \
+            ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_);                            \
+            return e_ == cudaErrorMemoryAllocation ? DOFS3D_ERR_NOMEM : DOFS3D_ERR_CUDA;               \
+        }                                                                                             \
+    } while (0)
+
+#define LAUNCH(ctx, kernel, grid, block, smem, ...)                        \
+    do {                                                                   \
+        kernel<<<grid, block, smem, (ctx)->stream>>>(__VA_ARGS__);         \
+        (ctx)->launches++;                                                 \
+    } while (0)
+
+template <typename T>
+int dalloc(dofs3d_ctx* ctx, T** p, size_t count) {
+    void* q = nullptr;
+    size_t bytes = std::max<size_t>(count * sizeof(T), 16);
+    CK(cudaMalloc(&q, bytes));
+    ctx->allocs.push_back(q);
+    ctx->bytes += (long long)bytes;
+    *p = static_cast<T*>(q);
+    return 0;
+}
+
+#define DA(ptr, count)                               \
+    do {                                             \
+        int r_ = dalloc(ctx, &(ptr), (count));       \
+        if (r_) return r_;                           \
+    } while (0)
+
+inline dim3 grid1(size_t n, int threads, int frames) { return dim3((unsigned)((n + threads - 1) / threads), frames); }
+
+void mark(dofs3d_ctx* ctx, const char* name) {
+    if (!ctx->timer.enabled) return;
+    cudaEvent_t ev;
+    cudaEventCreate(&ev);
+    cudaEventRecord(ev, ctx->stream);
+    ctx->timer.marks.push_back({name, ev});
+}
+
+void timer_begin(dofs3d_ctx* ctx) {
+    for (auto& m : ctx->timer.marks) cudaEventDestroy(m.second);
+    ctx->timer.marks.clear();
+    mark(ctx, "begin");
+}
+
+void timer_collect(dofs3d_ctx* ctx) {
+    if (!ctx->timer.enabled) return;
+    cudaStreamSynchronize(ctx->stream);
+    ctx->timer.result.clear();
+    for (size_t i = 1; i < ctx->timer.marks.size(); ++i) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ctx->timer.marks[i - 1].second, ctx->timer.marks[i].second);
+        bool found = false;
+        for (auto& r : ctx->timer.result)
+            if (r.name == ctx->timer.marks[i].first) {
+                r.ms += ms;
+                r.count += 1;
+                found = true;
+            }
+        if (!found) ctx->timer.result.push_back({ctx->timer.marks[i].first, ms, 1});
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// stable LSD radix sort of `frames` independent arrays of n (u64 key, u32 payload) pairs on key bits
+// [0, key_bits).  Input in (kA, vA) (payload = index when iota), ping-pong with (kB, vB).
+// Returns 0 if the result is in A, 1 if in B.
+// ---------------------------------------------------------------------------------------------
+int radix_sort(dofs3d_ctx* ctx, u64* kA, u32* vA, u64* kB, u32* vB, size_t stride, int n, int frames, int key_bits,
+               bool iota, const char* tag_hist, const char* tag_scan, const char* tag_scatter) {
+    const int tiles = (n + RS_TILE - 1) / RS_TILE;
+    int side = 0;
+    for (int shift = 0; shift < key_bits; shift += 8) {
+        const u64* kin = side ? kB : kA;
+        const u32* vin = side ? vB : vA;
+        u64* kout = side ? kA : kB;
+        u32* vout = side ? vA : vB;
+        LAUNCH(ctx, k_radix_hist, dim3(tiles, frames), RS_THREADS, 0, kin, stride, ctx->tile_hist, n, shift, tiles);
+        mark(ctx, tag_hist);
+        LAUNCH(ctx, k_radix_scan, dim3(RS_BINS, frames), RS_THREADS, 0, ctx->tile_hist, ctx->digit_tot, tiles);
+        mark(ctx, tag_scan);
+        LAUNCH(ctx, k_radix_scatter, dim3(tiles, frames), RS_THREADS, RS_SMEM_BYTES, kin, vin, kout, vout, stride,
+               ctx->tile_hist, ctx->digit_tot, n, shift, tiles, (iota && shift == 0) ? 1 : 0);
+        mark(ctx, tag_scatter);
+        side ^= 1;
+    }
+    return side;
+}
+
+int n_edges_of(int W, int H, int neighbors) {
+    return neighbors == 8 ? 4 * W * H - 3 * W - 3 * H + 2 : 2 * W * H - W - H;
+}
+
+// K7 + K8: blurred flow (ctx->flow_blur) -> sorted keys in keysA, sorted sequence numbers in valsA,
+// rank of every slot in valsB.
+int build_sorted_edges(dofs3d_ctx* ctx, int n) {
+    const int N = ctx->N;
+    LAUNCH(ctx, k_edge_keys, grid1(N, SEG_THREADS, n), SEG_THREADS, 0, ctx->flow_blur, ctx->keysA, ctx->S, ctx->W,
+           ctx->H, ctx->seg.neighbors == 8 ? 1 : 0);
+    mark(ctx, "edge_keys");
+    int side = radix_sort(ctx, ctx->keysA, ctx->valsA, ctx->keysB, ctx->valsB, ctx->S, (int)ctx->S, n, 64, true,
+                          "edge_sort.hist", "edge_sort.scan", "edge_sort.scatter");
+    if (side != 0) {
+        ctx->err = "internal: odd number of sort passes";
+        return DOFS3D_ERR_INTERNAL;
+    }
+    LAUNCH(ctx, k_rank_scatter, grid1(ctx->S, SEG_THREADS, n), SEG_THREADS, 0, ctx->valsA, ctx->valsB, ctx->S,
+           (int)ctx->S, n_edges_of(ctx->W, ctx->H, ctx->seg.neighbors));
+    mark(ctx, "edge_rank");
+    return 0;
+}
+
+enum { CNT_CAND = 0, CNT_CHAIN = 1, CNT_SCORED = 2, CNT_BOXES = 3, CNT_ROOTS = 4, CNT_KINDS = 5 };
+
+// get_segmented_array (segment.cpp:34-72) for n frames whose (unblurred or blurred) flow is at d_flow.
+int segment_dev(dofs3d_ctx* ctx, const float* d_flow, int already_blurred, int n) {
+    const int N = ctx->N, W = ctx->W, H = ctx->H, F = ctx->F;
+    const dim3 gN = grid1(N, SEG_THREADS, n);
+    const float2* src = reinterpret_cast<const float2*>(d_flow);
+    if (already_blurred) {
+        CK(cudaMemcpyAsync(ctx->flow_blur, src, (size_t)n * N * sizeof(float2), cudaMemcpyDeviceToDevice, ctx->stream));
+    } else {
+        LAUNCH(ctx, k_blur_rows, gN, SEG_THREADS, 0, src, ctx->flow_tmp, W, H, ctx->taps);
+        LAUNCH(ctx, k_blur_cols, gN, SEG_THREADS, 0, ctx->flow_tmp, ctx->flow_blur, W, H, ctx->taps);
+    }
+    mark(ctx, "flow_blur");
+    int rc = build_sorted_edges(ctx, n);
+    if (rc) return rc;
+
+    // K9a Boruvka levels (== union-by-rank ranks)
+    BorState& B = ctx->bor;
+    LAUNCH(ctx, k_bor_init, gN, SEG_THREADS, 0, B, ctx->flow_blur, ctx->rsize, ctx->rbbox, ctx->rflow, ctx->best_score,
+           ctx->sel_time, ctx->sel_box, W, N);
+    CK(cudaMemsetAsync(ctx->counters, 0, sizeof(int) * CNT_KINDS * F, ctx->stream));
+    ctx->levels_of_frame.assign(n, 0);
+    int levels = 0;
+    for (;;) {
+        if (levels >= EV_MAX_WAVES - 2) {
+            ctx->err = "internal: Boruvka did not converge";
+            return DOFS3D_ERR_INTERNAL;
+        }
+        CK(cudaMemsetAsync(ctx->counters + CNT_ROOTS * F, 0, sizeof(int) * F, ctx->stream));
+        LAUNCH(ctx, k_bor_pixel, gN, SEG_THREADS, 0, B, ctx->valsB, ctx->S, W, N);
+        LAUNCH(ctx, k_bor_root, gN, SEG_THREADS, 0, B, ctx->valsA, ctx->S, W, N, levels);
+        LAUNCH(ctx, k_bor_relabel, gN, SEG_THREADS, 0, B, N);
+        ++levels;
+        CK(cudaMemcpyAsync(ctx->h_counters + CNT_ROOTS * F, ctx->counters + CNT_ROOTS * F, sizeof(int) * n,
+                           cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        bool done = true;
+        for (int f = 0; f < n; ++f) {
+            if (ctx->h_counters[CNT_ROOTS * F + f] == 1) {
+                if (ctx->levels_of_frame[f] == 0) ctx->levels_of_frame[f] = levels;
+            } else {
+                done = false;
+            }
+        }
+        if (done) break;
+    }
+    LAUNCH(ctx, k_bor_finish, gN, SEG_THREADS, 0, B, N, levels);
+    mark(ctx, "boruvka");
+
+    // K9b events: winner of every loss, sorted by (wave, winner, time); buffers alias the edge keys
+    EvBits eb;
+    eb.tb = ceil_log2(ctx->S);
+    eb.wb = ceil_log2((unsigned long long)N);
+    u64* evA = ctx->keysA;
+    u64* evB = ctx->keysB;
+    u32* evlA = reinterpret_cast<u32*>(ctx->keysA + (size_t)F * N);  // losers, after the F*N keys
+    u32* evlB = reinterpret_cast<u32*>(ctx->keysB + (size_t)F * N);
+    LAUNCH(ctx, k_event_keys, gN, SEG_THREADS, 0, B, ctx->win, evA, N, eb);
+    mark(ctx, "event_keys");
+    int side = radix_sort(ctx, evA, evlA, evB, evlB, (size_t)N, N, n, eb.tb + eb.wb + 5, true, "event_sort.hist",
+                          "event_sort.scan", "event_sort.scatter");
+    const u64* ev_key = side ? evB : evA;
+    const u32* ev_loser = side ? evlB : evlA;
+    LAUNCH(ctx, k_wave_starts, gN, SEG_THREADS, 0, ev_key, ctx->wave_start, N, eb);
+    mark(ctx, "event_waves");
+
+    // K9c + K10 chain replay, wave by wave
+    ReplayArgs R;
+    R.ev_key = ev_key;
+    R.ev_loser = ev_loser;
+    R.wave_start = ctx->wave_start;
+    R.rsize = ctx->rsize;
+    R.rbbox = ctx->rbbox;
+    R.rflow = ctx->rflow;
+    R.cand = ctx->cand;
+    R.n_cand = ctx->counters + CNT_CAND * F;
+    R.longest_chain = ctx->counters + CNT_CHAIN * F;
+    R.cand_cap = ctx->cand_cap;
+    R.W = W;
+    R.H = H;
+    R.N = N;
+    R.min_size = ctx->seg.min_size;
+    R.eb = eb;
+    for (int wave = 1; wave <= levels; ++wave) LAUNCH(ctx, k_replay_wave, gN, SEG_THREADS, 0, R, wave);
+    mark(ctx, "chain_replay");
+
+    // K11 + K12 lifting, selection, boxes, labels
+    SelectArgs A;
+    A.cand = ctx->cand;
+    A.n_cand = ctx->counters + CNT_CAND * F;
+    A.cand_score = ctx->cand_score;
+    A.best_score = ctx->best_score;
+    A.sel_time = ctx->sel_time;
+    A.sel_box = ctx->sel_box;
+    A.n_scored = ctx->counters + CNT_SCORED * F;
+    A.n_boxes = ctx->counters + CNT_BOXES * F;
+    A.cand_cap = ctx->cand_cap;
+    A.N = N;
+    const dim3 gC128 = grid1(ctx->cand_cap, 128, n);
+    const dim3 gC = grid1(ctx->cand_cap, SEG_THREADS, n);
+    LAUNCH(ctx, k_lift_score, gC128, 128, 0, A, ctx->seg);
+    LAUNCH(ctx, k_select_time, gC, SEG_THREADS, 0, A);
+    LAUNCH(ctx, k_emit_boxes<dofs3d_box>, gC128, 128, 0, A, ctx->seg, ctx->boxes_tmp, ctx->box_cap);
+    mark(ctx, "lifting");
+    const dim3 gB = grid1(ctx->box_cap, SEG_THREADS, n);
+    LAUNCH(ctx, k_sort_boxes<dofs3d_box>, gB, SEG_THREADS, 0, ctx->boxes_tmp, ctx->boxes, A.n_boxes, ctx->box_cap,
+           ctx->sel_box, N);
+    LAUNCH(ctx, k_box_parents<dofs3d_box>, gB, SEG_THREADS, 0, ctx->boxes, A.n_boxes, ctx->box_cap, B.loss_time,
+           ctx->win, ctx->sel_time, ctx->sel_box, N);
+    LAUNCH(ctx, k_labels, gN, SEG_THREADS, 0, ctx->labels, B.loss_time, ctx->win, ctx->sel_time, ctx->sel_box, N);
+    mark(ctx, "labels");
+
+    // counters -> stats (host knows n_levels)
+    CK(cudaMemcpyAsync(ctx->h_counters, ctx->counters, sizeof(int) * CNT_KINDS * F, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (int f = 0; f < n; ++f) {
+        if (ctx->h_counters[CNT_CAND * F + f] > ctx->cand_cap) {
+            ctx->err = "candidate queue overflow";
+            return DOFS3D_ERR_OVERFLOW;
+        }
+        if (ctx->h_counters[CNT_BOXES * F + f] > ctx->box_cap) {
+            ctx->err = "box list overflow";
+            return DOFS3D_ERR_OVERFLOW;
+        }
+    }
+    return 0;
+}
+
+void fill_stats(dofs3d_ctx* ctx, int n, dofs3d_stats* out) {
+    const int F = ctx->F;
+    for (int f = 0; f < n; ++f) {
+        dofs3d_stats s;
+        memset(&s, 0, sizeof s);
+        s.n_edges = n_edges_of(ctx->W, ctx->H, ctx->seg.neighbors);
+        s.n_merges = ctx->N - ctx->h_counters[CNT_ROOTS * F + f];
+        s.n_levels = ctx->levels_of_frame[f];
+        s.n_candidates = ctx->h_counters[CNT_CAND * F + f];
+        s.n_scored = ctx->h_counters[CNT_SCORED * F + f];
+        s.n_boxes = ctx->h_counters[CNT_BOXES * F + f];
+        s.longest_chain = ctx->h_counters[CNT_CHAIN * F + f];
+        out[f] = s;
+    }
+}
+
+// copy results of the last segment_dev to caller memory (kind = cudaMemcpyDeviceToHost / DeviceToDevice)
+int export_results(dofs3d_ctx* ctx, int n, int32_t* labels_out, dofs3d_box* boxes_out, int32_t* n_boxes_out,
+                   int max_boxes, dofs3d_stats* stats_out, cudaMemcpyKind kind) {
+    const int F = ctx->F;
+    if (labels_out)
+        CK(cudaMemcpyAsync(labels_out, ctx->labels, (size_t)n * ctx->N * sizeof(int32_t), kind, ctx->stream));
+    if (boxes_out && max_boxes > 0) {
+        const int cols = std::min(max_boxes, ctx->box_cap);
+        CK(cudaMemcpy2DAsync(boxes_out, (size_t)max_boxes * sizeof(dofs3d_box), ctx->boxes,
+                             (size_t)ctx->box_cap * sizeof(dofs3d_box), (size_t)cols * sizeof(dofs3d_box), n, kind,
+                             ctx->stream));
+    }
+    std::vector<dofs3d_stats> st(n);
+    fill_stats(ctx, n, st.data());
+    if (kind == cudaMemcpyDeviceToHost) {
+        if (n_boxes_out)
+            for (int f = 0; f < n; ++f) n_boxes_out[f] = ctx->h_counters[CNT_BOXES * F + f];
+        if (stats_out) memcpy(stats_out, st.data(), sizeof(dofs3d_stats) * n);
+    } else {
+        if (n_boxes_out)
+            CK(cudaMemcpyAsync(n_boxes_out, ctx->counters + CNT_BOXES * F, sizeof(int) * n, cudaMemcpyDeviceToDevice,
+                               ctx->stream));
+        if (stats_out) {
+            CK(cudaMemcpyAsync(ctx->stats, st.data(), sizeof(dofs3d_stats) * n, cudaMemcpyHostToDevice, ctx->stream));
+            CK(cudaMemcpyAsync(stats_out, ctx->stats, sizeof(dofs3d_stats) * n, cudaMemcpyDeviceToDevice, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));  // st goes out of scope
+        }
+    }
+    if (boxes_out) {
+        for (int f = 0; f < n; ++f)
+            if (ctx->h_counters[CNT_BOXES * F + f] > max_boxes) {
+                CK(cudaStreamSynchronize(ctx->stream));
+                ctx->err = "more boxes than max_boxes";
+                return DOFS3D_ERR_OVERFLOW;
+            }
+    }
+    return 0;
+}
+
+// cvtColor + Farneback for n pairs out of n+1 consecutive gray frames already in ctx->gray
+int flow_dev(dofs3d_ctx* ctx, const u8* d_gray0, const u8* d_gray1, size_t pair_stride1, int n, float2* d_flow_out) {
+    FlowLaunchStats st;
+    int rc = farneback_run(ctx->fb, d_gray0, d_gray1, n, d_flow_out, ctx->stream, &st);
+    ctx->launches += st.launches;
+    if (rc) {
+        ctx->err = "farneback_run failed";
+        return DOFS3D_ERR_CUDA;
+    }
+    (void)pair_stride1;
+    mark(ctx, "farneback");
+    return 0;
+}
+
+int check_batch(dofs3d_ctx* ctx, int n) {
+    if (!ctx) return DOFS3D_ERR_ARG;
+    if (n < 0 || n > ctx->F) {
+        ctx->err = "n_pairs out of range (0..max_pairs)";
+        return DOFS3D_ERR_ARG;
+    }
+    CK(cudaSetDevice(ctx->device));
+    return 0;
+}
+
+}  // namespace
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" {
+
+void dofs3d_default_params(dofs3d_params* p) {
+    if (!p) return;
+    memset(p, 0, sizeof *p);
+    // get_mat (lifting_3d.cpp:482-514): image quad <-> bird's-eye-view rectangle
+    const double img[4][2] = {{215, 265}, {90, 121}, {294, 120}, {625, 265}};
+    const double bev[4][2] = {{100, 13000}, {100, 6000}, {800, 6000}, {800, 13000}};
+    perspective_transform(img, bev, p->persp);
+    perspective_transform(bev, img, p->inv);
+    // get_mat_upper (lifting_3d.cpp:441-480): the same BEV rectangle to the roof-height image quads
+    const double roof_y[3][2] = {{176, 85}, {185, 80}, {140, 55}};
+    for (int c = 0; c < 3; ++c) {
+        const double roof[4][2] = {{215, roof_y[c][0]}, {90, roof_y[c][1]}, {294, roof_y[c][1]}, {625, roof_y[c][0]}};
+        perspective_transform(bev, roof, p->inv_upper[c]);
+    }
+    p->pyr_scale = 0.5;
+    p->levels = 3;
+    p->winsize = 15;
+    p->iters = 3;
+    p->poly_n = 5;
+    p->poly_sigma = 1.2;
+    p->blur_sigma = 3.0;
+    p->neighbors = 8;
+    p->min_size = 500;
+    p->score_threshold = 0.3;
+    const int sizes[3][2] = {{258, 84}, {349, 165}, {370, 180}};
+    memcpy(p->cls_size, sizes, sizeof sizes);
+    p->cls_min_convexity[0] = 3.0 / 4.0;
+    p->cls_min_convexity[1] = 1.0 / 2.0;
+    p->cls_min_convexity[2] = 20.0 / 29.0;
+}
+
+int dofs3d_create(dofs3d_ctx** out, int device, int width, int height, int max_pairs, const dofs3d_params* params) {
+    if (!out) return DOFS3D_ERR_ARG;
+    *out = nullptr;
+    if (width < 2 || height < 2 || width > 65535 || height > 65535 || max_pairs < 1) return DOFS3D_ERR_ARG;
+    if ((unsigned long long)width * height > (1ull << 27)) return DOFS3D_ERR_ARG;
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || device < 0 || device >= n_dev) return DOFS3D_ERR_CUDA;
+    dofs3d_ctx* ctx = new dofs3d_ctx();
+    *out = ctx;  // returned even on failure so that dofs3d_last_error can be read; destroy it either way
+    ctx->device = device;
+    ctx->W = width;
+    ctx->H = height;
+    ctx->N = width * height;
+    ctx->S = 4 * (size_t)ctx->N;
+    ctx->F = max_pairs;
+    if (params) ctx->prm = *params;
+    else dofs3d_default_params(&ctx->prm);
+    const dofs3d_params& p = ctx->prm;
+    if (p.neighbors != 4 && p.neighbors != 8) {
+        ctx->err = "neighbors must be 4 or 8";
+        return DOFS3D_ERR_ARG;
+    }
+    memcpy(ctx->seg.hg.persp, p.persp, sizeof p.persp);
+    memcpy(ctx->seg.hg.inv, p.inv, sizeof p.inv);
+    memcpy(ctx->seg.hg.upper, p.inv_upper, sizeof p.inv_upper);
+    memcpy(ctx->seg.cls_size, p.cls_size, sizeof p.cls_size);
+    memcpy(ctx->seg.cls_min_convexity, p.cls_min_convexity, sizeof p.cls_min_convexity);
+    ctx->seg.score_threshold = p.score_threshold;
+    ctx->seg.min_size = p.min_size;
+    ctx->seg.neighbors = p.neighbors;
+    // GaussianBlur(flow, Size(0,0), sigma) on CV_32F: ksize = cvRound(sigma*4*2 + 1) | 1
+    {
+        int ksize = ((int)lrint(p.blur_sigma * 8 + 1)) | 1;
+        if (ksize < 1 || ksize > 2 * BLUR_MAX_RADIUS + 1) {
+            ctx->err = "blur_sigma out of range";
+            return DOFS3D_ERR_ARG;
+        }
+        ctx->taps.radius = ksize / 2;
+        gaussian_taps(ksize, p.blur_sigma, ctx->taps.k);
+    }
+    CK(cudaSetDevice(device));
+    CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CK(cudaFuncSetAttribute(k_radix_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, RS_SMEM_BYTES));
+
+    const size_t F = ctx->F, N = ctx->N, S = ctx->S;
+    DA(ctx->flow_in, F * N);
+    DA(ctx->flow_tmp, F * N);
+    DA(ctx->flow_blur, F * N);
+    DA(ctx->keysA, F * S);
+    DA(ctx->keysB, F * S);
+    DA(ctx->valsA, F * S);
+    DA(ctx->valsB, F * S);
+    ctx->num_tiles = (int)((S + RS_TILE - 1) / RS_TILE);
+    DA(ctx->tile_hist, F * RS_BINS * ctx->num_tiles);
+    DA(ctx->digit_tot, F * RS_BINS);
+    DA(ctx->bor.comp, F * N);
+    DA(ctx->bor.best, F * N);
+    DA(ctx->bor.newp, F * N);
+    DA(ctx->bor.loss_time, F * N);
+    DA(ctx->bor.up, F * N);
+    DA(ctx->bor.lvl, F * N);
+    DA(ctx->win, F * N);
+    DA(ctx->wave_start, F * (EV_MAX_WAVES + 1));
+    DA(ctx->rsize, F * N);
+    DA(ctx->rbbox, F * N);
+    DA(ctx->rflow, F * N);
+    DA(ctx->best_score, F * N);
+    DA(ctx->sel_time, F * N);
+    DA(ctx->sel_box, F * N);
+    ctx->cand_cap = (int)std::max<size_t>(65536, N / 4);
+    ctx->box_cap = 4096;
+    DA(ctx->cand, F * ctx->cand_cap);
+    DA(ctx->cand_score, F * ctx->cand_cap);
+    DA(ctx->counters, (size_t)CNT_KINDS * F);
+    ctx->bor.n_roots = ctx->counters + CNT_ROOTS * F;
+    CK(cudaMallocHost(&ctx->h_counters, sizeof(int) * CNT_KINDS * F));
+    DA(ctx->boxes_tmp, F * ctx->box_cap);
+    DA(ctx->boxes, F * ctx->box_cap);
+    DA(ctx->labels, F * N);
+    DA(ctx->stats, F);
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+// buffers of the gray / flow stages, allocated on first use (a segmentation-only context never pays for them)
+static int ensure_flow(dofs3d_ctx* ctx) {
+    if (ctx->flow_raw) return 0;
+    const dofs3d_params& p = ctx->prm;
+    const size_t F = ctx->F, N = ctx->N;
+    const int width = ctx->W, height = ctx->H;
+    DA(ctx->bgr, (F + 1) * N * 3);
+    DA(ctx->gray, (F + 1) * N);
+    {
+        FlowConfig fc;
+        fc.pyr_scale = p.pyr_scale;
+        fc.levels = p.levels;
+        fc.winsize = p.winsize;
+        fc.iters = p.iters;
+        fc.poly_n = p.poly_n;
+        fc.poly_sigma = p.poly_sigma;
+        size_t fbytes = 0;
+        int rc = farneback_alloc(&ctx->fb, width, height, (int)F, fc, &fbytes);
+        ctx->bytes += (long long)fbytes;
+        if (rc) {
+            ctx->err = farneback_error(rc);
+            return rc == 1 ? DOFS3D_ERR_ARG : DOFS3D_ERR_NOMEM;
+        }
+    }
+    DA(ctx->flow_raw, F * N);
+    return 0;
+}
+
+void dofs3d_destroy(dofs3d_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (void* p : ctx->allocs) cudaFree(p);
+    farneback_free(&ctx->fb);
+    if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
+    for (auto& m : ctx->timer.marks) cudaEventDestroy(m.second);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int dofs3d_sync(dofs3d_ctx* ctx) {
+    if (!ctx) return DOFS3D_ERR_ARG;
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+const char* dofs3d_last_error(const dofs3d_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+void* dofs3d_stream(dofs3d_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+long long dofs3d_launch_count(const dofs3d_ctx* ctx) { return ctx ? ctx->launches : 0; }
+long long dofs3d_device_bytes(const dofs3d_ctx* ctx) { return ctx ? ctx->bytes : 0; }
+
+int dofs3d_set_timing(dofs3d_ctx* ctx, int enabled) {
+    if (!ctx) return DOFS3D_ERR_ARG;
+    ctx->timer.enabled = enabled != 0;
+    return 0;
+}
+
+int dofs3d_get_timing(dofs3d_ctx* ctx, const char** names, float* ms, int* counts, int cap) {
+    if (!ctx) return DOFS3D_ERR_ARG;
+    int n = 0;
+    for (auto& r : ctx->timer.result) {
+        if (n >= cap) break;
+        if (names) names[n] = r.name.c_str();
+        if (ms) ms[n] = r.ms;
+        if (counts) counts[n] = r.count;
+        ++n;
+    }
+    return n;
+}
+
+// ------------------------------------------------------------------------------------- gray
+int dofs3d_gray_dev(dofs3d_ctx* ctx, const uint8_t* d_bgr, int n_frames, uint8_t* d_gray_out) {
+    if (!ctx || !d_bgr || !d_gray_out || n_frames < 0) return DOFS3D_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    if (n_frames == 0) return 0;
+    LAUNCH(ctx, k_bgr2gray, grid1((size_t)ctx->N * n_frames / 4 + 1, 256, 1), 256, 0, d_bgr, d_gray_out,
+           (size_t)ctx->N * n_frames);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int dofs3d_gray(dofs3d_ctx* ctx, const uint8_t* bgr, int n_frames, uint8_t* gray_out) {
+    if (!ctx || !bgr || !gray_out) return DOFS3D_ERR_ARG;
+    if (n_frames < 0 || n_frames > ctx->F + 1) {
+        ctx->err = "n_frames out of range (0..max_pairs+1)";
+        return DOFS3D_ERR_ARG;
+    }
+    CK(cudaSetDevice(ctx->device));
+    if (int rc0 = ensure_flow(ctx)) return rc0;
+    const size_t px = (size_t)ctx->N * n_frames;
+    CK(cudaMemcpyAsync(ctx->bgr, bgr, px * 3, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = dofs3d_gray_dev(ctx, ctx->bgr, n_frames, ctx->gray);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(gray_out, ctx->gray, px, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------- flow
+int dofs3d_flow_dev(dofs3d_ctx* ctx, const uint8_t* d_gray0, const uint8_t* d_gray1, int n_pairs, float* d_flow_out) {
+    int rc = check_batch(ctx, n_pairs);
+    if (rc) return rc;
+    if (!d_gray0 || !d_gray1 || !d_flow_out) return DOFS3D_ERR_ARG;
+    if (n_pairs == 0) return 0;
+    if ((rc = ensure_flow(ctx))) return rc;
+    timer_begin(ctx);
+    rc = flow_dev(ctx, d_gray0, d_gray1, 0, n_pairs, reinterpret_cast<float2*>(d_flow_out));
+    if (rc) return rc;
+    CK(cudaGetLastError());
+    timer_collect(ctx);
+    return 0;
+}
+
+int dofs3d_flow(dofs3d_ctx* ctx, const uint8_t* gray0, const uint8_t* gray1, int n_pairs, float* flow_out) {
+    int rc = check_batch(ctx, n_pairs);
+    if (rc) return rc;
+    if (!gray0 || !gray1 || !flow_out) return DOFS3D_ERR_ARG;
+    if (n_pairs == 0) return 0;
+    if ((rc = ensure_flow(ctx))) return rc;
+    const size_t px = (size_t)ctx->N * n_pairs;
+    // staging: gray0 frames in ctx->gray, gray1 frames in ctx->bgr (3x larger than needed)
+    CK(cudaMemcpyAsync(ctx->gray, gray0, px, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->bgr, gray1, px, cudaMemcpyHostToDevice, ctx->stream));
+    rc = dofs3d_flow_dev(ctx, ctx->gray, ctx->bgr, n_pairs, reinterpret_cast<float*>(ctx->flow_raw));
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(flow_out, ctx->flow_raw, px * sizeof(float2), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------- blur
+int dofs3d_blur(dofs3d_ctx* ctx, const float* flow_in, int n_pairs, float* flow_out) {
+    int rc = check_batch(ctx, n_pairs);
+    if (rc) return rc;
+    if (!flow_in || !flow_out) return DOFS3D_ERR_ARG;
+    if (n_pairs == 0) return 0;
+    const size_t px = (size_t)ctx->N * n_pairs;
+    const dim3 gN = grid1(ctx->N, SEG_THREADS, n_pairs);
+    CK(cudaMemcpyAsync(ctx->flow_in, flow_in, px * sizeof(float2), cudaMemcpyHostToDevice, ctx->stream));
+    LAUNCH(ctx, k_blur_rows, gN, SEG_THREADS, 0, ctx->flow_in, ctx->flow_tmp, ctx->W, ctx->H, ctx->taps);
+    LAUNCH(ctx, k_blur_cols, gN, SEG_THREADS, 0, ctx->flow_tmp, ctx->flow_blur, ctx->W, ctx->H, ctx->taps);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(flow_out, ctx->flow_blur, px * sizeof(float2), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------- segment
+int dofs3d_segment_dev(dofs3d_ctx* ctx, const float* d_flow, int already_blurred, int n_pairs, int32_t* d_labels_out,
+                       dofs3d_box* d_boxes_out, int32_t* d_n_boxes_out, int max_boxes, dofs3d_stats* d_stats_out) {
+    int rc = check_batch(ctx, n_pairs);
+    if (rc) return rc;
+    if (!d_flow || max_boxes < 0) return DOFS3D_ERR_ARG;
+    if (n_pairs == 0) return 0;
+    timer_begin(ctx);
+    rc = segment_dev(ctx, d_flow, already_blurred, n_pairs);
+    if (rc) return rc;
+    rc = export_results(ctx, n_pairs, d_labels_out, d_boxes_out, d_n_boxes_out, max_boxes, d_stats_out,
+                        cudaMemcpyDeviceToDevice);
+    CK(cudaGetLastError());
+    timer_collect(ctx);
+    return rc;
+}
+
+int dofs3d_segment(dofs3d_ctx* ctx, const float* flow, int already_blurred, int n_pairs, int32_t* labels_out,
+                   dofs3d_box* boxes_out, int32_t* n_boxes_out, int max_boxes, dofs3d_stats* stats_out,
+                   float* flow_blurred_out) {
+    int rc = check_batch(ctx, n_pairs);
+    if (rc) return rc;
+    if (!flow || max_boxes < 0) return DOFS3D_ERR_ARG;
+    if (n_pairs == 0) return 0;
+    const size_t px = (size_t)ctx->N * n_pairs;
+    CK(cudaMemcpyAsync(ctx->flow_in, flow, px * sizeof(float2), cudaMemcpyHostToDevice, ctx->stream));
+    timer_begin(ctx);
+    rc = segment_dev(ctx, reinterpret_cast<const float*>(ctx->flow_in), already_blurred, n_pairs);
+    if (rc) return rc;
+    rc = export_results(ctx, n_pairs, labels_out, boxes_out, n_boxes_out, max_boxes, stats_out, cudaMemcpyDeviceToHost);
+    if (flow_blurred_out)
+        CK(cudaMemcpyAsync(flow_blurred_out, ctx->flow_blur, px * sizeof(float2), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaGetLastError());
+    timer_collect(ctx);
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------- lift
+int dofs3d_lift(dofs3d_ctx* ctx, const float* dir2, const int32_t* bbox4, const int32_t* cls, int n, dofs3d_box* out) {
+    if (!ctx || !dir2 || !bbox4 || !cls || !out || n < 0) return DOFS3D_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    if (n == 0) return 0;
+    for (int i = 0; i < n; ++i)
+        if (cls[i] < 0 || cls[i] > 2) {
+            ctx->err = "cls must be 0, 1 or 2";
+            return DOFS3D_ERR_ARG;
+        }
+    float2* d_dir = nullptr;
+    int4* d_box = nullptr;
+    int* d_cls = nullptr;
+    dofs3d_box* d_out = nullptr;
+    int rc = 0;
+    cudaError_t e;
+    if ((e = cudaMalloc(&d_dir, sizeof(float2) * n)) != cudaSuccess || (e = cudaMalloc(&d_box, sizeof(int4) * n)) != cudaSuccess ||
+        (e = cudaMalloc(&d_cls, sizeof(int) * n)) != cudaSuccess || (e = cudaMalloc(&d_out, sizeof(dofs3d_box) * n)) != cudaSuccess) {
+        ctx->err = cudaGetErrorString(e);
+        rc = DOFS3D_ERR_NOMEM;
+    }
+    if (!rc) {
+        cudaMemcpyAsync(d_dir, dir2, sizeof(float2) * n, cudaMemcpyHostToDevice, ctx->stream);
+        cudaMemcpyAsync(d_box, bbox4, sizeof(int4) * n, cudaMemcpyHostToDevice, ctx->stream);
+        cudaMemcpyAsync(d_cls, cls, sizeof(int) * n, cudaMemcpyHostToDevice, ctx->stream);
+        LAUNCH(ctx, k_lift_problems<dofs3d_box>, grid1(n, 128, 1), 128, 0, d_dir, d_box, d_cls, n, ctx->seg, d_out);
+        cudaMemcpyAsync(out, d_out, sizeof(dofs3d_box) * n, cudaMemcpyDeviceToHost, ctx->stream);
+        e = cudaStreamSynchronize(ctx->stream);
+        if (e == cudaSuccess) e = cudaGetLastError();
+        if (e != cudaSuccess) {
+            ctx->err = cudaGetErrorString(e);
+            rc = DOFS3D_ERR_CUDA;
+        }
+    }
+    cudaFree(d_dir);
+    cudaFree(d_box);
+    cudaFree(d_cls);
+    cudaFree(d_out);
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------- sorted edges
+long long dofs3d_edges_sorted(dofs3d_ctx* ctx, const float* flow_blurred, int32_t* start, int32_t* end,
+                              uint64_t* weight_bits) {
+    if (!ctx || !flow_blurred) return DOFS3D_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    const int N = ctx->N;
+    const int E = n_edges_of(ctx->W, ctx->H, ctx->seg.neighbors);
+    CK(cudaMemcpyAsync(ctx->flow_blur, flow_blurred, (size_t)N * sizeof(float2), cudaMemcpyHostToDevice, ctx->stream));
+    int rc = build_sorted_edges(ctx, 1);
+    if (rc) return rc;
+    // decode (start, end) into the dead B buffers
+    int* d_start = reinterpret_cast<int*>(ctx->keysB);
+    int* d_end = d_start + ctx->S;
+    LAUNCH(ctx, k_edges_decode, grid1(E, SEG_THREADS, 1), SEG_THREADS, 0, ctx->valsA, d_start, d_end, ctx->W, E);
+    CK(cudaGetLastError());
+    if (start) CK(cudaMemcpyAsync(start, d_start, sizeof(int) * (size_t)E, cudaMemcpyDeviceToHost, ctx->stream));
+    if (end) CK(cudaMemcpyAsync(end, d_end, sizeof(int) * (size_t)E, cudaMemcpyDeviceToHost, ctx->stream));
+    if (weight_bits)
+        CK(cudaMemcpyAsync(weight_bits, ctx->keysA, sizeof(u64) * (size_t)E, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return E;
+}
+
+// ------------------------------------------------------------------------------------- whole path
+int dofs3d_process_dev(dofs3d_ctx* ctx, const uint8_t* d_bgr_frames, int n_frames, int32_t* d_labels_out,
+                       dofs3d_box* d_boxes_out, int32_t* d_n_boxes_out, int max_boxes, dofs3d_stats* d_stats_out) {
+    if (!ctx || !d_bgr_frames || n_frames < 1) return DOFS3D_ERR_ARG;
+    const int n = n_frames - 1;
+    int rc = check_batch(ctx, n);
+    if (rc) return rc;
+    if (n == 0) return 0;
+    if ((rc = ensure_flow(ctx))) return rc;
+    timer_begin(ctx);
+    const size_t N = ctx->N;
+    LAUNCH(ctx, k_bgr2gray, grid1(N * n_frames / 4 + 1, 256, 1), 256, 0, d_bgr_frames, ctx->gray, N * n_frames);
+    mark(ctx, "gray");
+    rc = flow_dev(ctx, ctx->gray, ctx->gray + N, 0, n, ctx->flow_raw);  // pair i = frames (i, i+1)
+    if (rc) return rc;
+    rc = segment_dev(ctx, reinterpret_cast<const float*>(ctx->flow_raw), 0, n);
+    if (rc) return rc;
+    rc = export_results(ctx, n, d_labels_out, d_boxes_out, d_n_boxes_out, max_boxes, d_stats_out, cudaMemcpyDeviceToDevice);
+    CK(cudaGetLastError());
+    timer_collect(ctx);
+    return rc;
+}
+
+int dofs3d_process(dofs3d_ctx* ctx, const uint8_t* bgr_frames, int n_frames, int32_t* labels_out, dofs3d_box* boxes_out,
+                   int32_t* n_boxes_out, int max_boxes, dofs3d_stats* stats_out) {
+    if (!ctx || !bgr_frames || n_frames < 1) return DOFS3D_ERR_ARG;
+    const int n = n_frames - 1;
+    int rc = check_batch(ctx, n);
+    if (rc) return rc;
+    if (n == 0) return 0;
+    if ((rc = ensure_flow(ctx))) return rc;
+    const size_t N = ctx->N;
+    CK(cudaMemcpyAsync(ctx->bgr, bgr_frames, N * 3 * n_frames, cudaMemcpyHostToDevice, ctx->stream));
+    timer_begin(ctx);
+    LAUNCH(ctx, k_bgr2gray, grid1(N * n_frames / 4 + 1, 256, 1), 256, 0, ctx->bgr, ctx->gray, N * n_frames);
+    mark(ctx, "gray");
+    rc = flow_dev(ctx, ctx->gray, ctx->gray + N, 0, n, ctx->flow_raw);
+    if (rc) return rc;
+    rc = segment_dev(ctx, reinterpret_cast<const float*>(ctx->flow_raw), 0, n);
+    if (rc) return rc;
+    rc = export_results(ctx, n, labels_out, boxes_out, n_boxes_out, max_boxes, stats_out, cudaMemcpyDeviceToHost);
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaGetLastError());
+    timer_collect(ctx);
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------- synthetic video
+int dofs3d_synth_frames_dev(dofs3d_ctx* ctx, uint32_t seed, int n_objects, int first_frame, int n_frames,
+                            uint8_t* d_bgr_out) {
+    if (!ctx || !d_bgr_out || n_frames < 0 || n_objects < 0 || n_objects > SYNTH_MAX_OBJECTS) return DOFS3D_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    if (n_frames == 0) return 0;
+    SynthScene sc;
+    synth_make_scene(seed, n_objects, ctx->W, ctx->H, &sc);
+    LAUNCH(ctx, k_synth_frames, grid1(ctx->N, 256, n_frames), 256, 0, sc, first_frame, d_bgr_out, ctx->W, ctx->H);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+}  // extern "C"

@@ -8,13 +8,7 @@
 
 #include <stdint.h>
 
-#ifdef DOFS_EMUL
-// Test-only build: tests/emul/cuda_emul.h supplies the CUDA vocabulary for a host compiler so that
-// the non-cooperative kernels can be exercised without a GPU.  Never part of the shipped library.
-#include "cuda_emul.h"
-#else
 #include <cuda_runtime.h>
-#endif
 
 typedef uint8_t u8;
 typedef uint16_t u16;
@@ -27,22 +21,22 @@ typedef uint64_t u64;
 #define DOFS_D __device__ __forceinline__
 
 // float ops, one rounding each
-DOFS_D float fadd(float a, float b) { return __fadd_rn(a, b); }
-DOFS_D float fsub(float a, float b) { return __fsub_rn(a, b); }
-DOFS_D float fmul(float a, float b) { return __fmul_rn(a, b); }
-DOFS_D float fdiv(float a, float b) { return __fdiv_rn(a, b); }
+DOFS_D float xfadd(float a, float b) { return __fadd_rn(a, b); }
+DOFS_D float xfsub(float a, float b) { return __fsub_rn(a, b); }
+DOFS_D float xfmul(float a, float b) { return __fmul_rn(a, b); }
+DOFS_D float xfdiv(float a, float b) { return __fdiv_rn(a, b); }
 // double ops, one rounding each
-DOFS_D double dadd(double a, double b) { return __dadd_rn(a, b); }
-DOFS_D double dsub(double a, double b) { return __dsub_rn(a, b); }
-DOFS_D double dmul(double a, double b) { return __dmul_rn(a, b); }
-DOFS_D double ddiv(double a, double b) { return __ddiv_rn(a, b); }
-DOFS_D double dsqrt(double a) { return __dsqrt_rn(a); }
+DOFS_D double xdadd(double a, double b) { return __dadd_rn(a, b); }
+DOFS_D double xdsub(double a, double b) { return __dsub_rn(a, b); }
+DOFS_D double xdmul(double a, double b) { return __dmul_rn(a, b); }
+DOFS_D double xddiv(double a, double b) { return __ddiv_rn(a, b); }
+DOFS_D double xdsqrt(double a) { return __dsqrt_rn(a); }
 
 // sqrt((double)x*x + (double)y*y): cv::norm(Point2f) / cv::norm(Vec2f) and diff (segment.cpp:25-29).
 // The two products of floats are exact in double, so the sum rounds once either way.
 DOFS_D double norm2d(float x, float y) {
     double dx = (double)x, dy = (double)y;
-    return dsqrt(dadd(dmul(dx, dx), dmul(dy, dy)));
+    return xdsqrt(xdadd(xdmul(dx, dx), xdmul(dy, dy)));
 }
 
 struct Homographies {

@@ -1,0 +1,601 @@
+// Dense optical flow on the device (stages K0-K5 of SURVEY.md section 2.2): what the reference gets
+// from cv::cvtColor(BGR2GRAY) and cv::calcOpticalFlowFarneback(prev, next, flow, 0.5, 3, 15, 3, 5,
+// 1.2, 0) at cpp/src/segment.cpp:97-101 (and :222-226 in the video loop).  OpenCV is not part of the
+// reference tree and not version-pinned by it (cpp/CMakeLists.txt:14); the arithmetic below restates
+// the published algorithm of OpenCV 4.x modules/video/src/optflowgf.cpp (polynomial expansion,
+// update-matrices, box-filtered 2x2 solve, coarse-to-fine over a Gaussian pyramid) and is checked
+// against cv2 4.13 with an end-point-error tolerance (tests/test_flow.py).
+//
+// Layout in HBM (all row-major, one image after the other):
+//   gray   u8  [image][H][W]
+//   I      f32 [image][Hk][Wk]            pyramid level k of every image
+//   R      f32 [image][Hk][Wk][5]         polynomial expansion coefficients (OpenCV's channel order)
+//   M      f32 [pair][Hk][Wk][5]          G11, G12, G22, h1, h2 products
+//   flow   f32 [pair][Hk][Wk][2]
+// Every kernel takes the image / pair index from blockIdx.z (or .y), so one launch covers the batch.
+#pragma once
+#include <math.h>
+
+#include "dofs_common.cuh"
+
+// ---------------------------------------------------------------------------------------------
+// K0  cv::cvtColor(BGR2GRAY) on 8-bit data: (R*9798 + G*19235 + B*3735 + 2^14) >> 15
+// ---------------------------------------------------------------------------------------------
+DOFS_D u32 gray_of(u32 b, u32 g, u32 r) { return (r * 9798u + g * 19235u + b * 3735u + 16384u) >> 15; }
+
+// four pixels per thread: three aligned 32-bit loads, one 32-bit store
+__global__ void __launch_bounds__(256)
+k_bgr2gray(const u8* __restrict__ bgr, u8* __restrict__ gray, size_t n_px) {
+    const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t p = q * 4;
+    if (p >= n_px) return;
+    if (p + 4 <= n_px) {
+        const u32* in = reinterpret_cast<const u32*>(bgr) + q * 3;
+        const u32 w0 = in[0], w1 = in[1], w2 = in[2];
+        const u32 g0 = gray_of(w0 & 255u, (w0 >> 8) & 255u, (w0 >> 16) & 255u);
+        const u32 g1 = gray_of(w0 >> 24, w1 & 255u, (w1 >> 8) & 255u);
+        const u32 g2 = gray_of((w1 >> 16) & 255u, w1 >> 24, w2 & 255u);
+        const u32 g3 = gray_of((w2 >> 8) & 255u, (w2 >> 16) & 255u, w2 >> 24);
+        reinterpret_cast<u32*>(gray)[q] = g0 | (g1 << 8) | (g2 << 16) | (g3 << 24);
+    } else {
+        for (size_t i = p; i < n_px; ++i) gray[i] = (u8)gray_of(bgr[3 * i], bgr[3 * i + 1], bgr[3 * i + 2]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host-side configuration
+// ---------------------------------------------------------------------------------------------
+#define FLOW_MAX_LEVELS 8
+#define FLOW_MAX_SMOOTH_RADIUS 24
+#define FLOW_MAX_POLY_N 7
+
+struct FlowConfig {
+    double pyr_scale = 0.5;
+    int levels = 3;
+    int winsize = 15;
+    int iters = 3;
+    int poly_n = 5;
+    double poly_sigma = 1.2;
+};
+
+struct SmoothTaps {  // Gaussian of one pyramid level, cv::getGaussianKernel(smooth_sz, sigma, CV_32F)
+    int radius;
+    float k[2 * FLOW_MAX_SMOOTH_RADIUS + 1];
+};
+
+struct PolyCoef {  // FarnebackPrepareGaussian
+    int n;
+    float g[FLOW_MAX_POLY_N + 1], xg[FLOW_MAX_POLY_N + 1], xxg[FLOW_MAX_POLY_N + 1];
+    double ig11, ig03, ig33, ig55;
+};
+
+struct FlowLevel {
+    int w, h;
+    double scale;  // pyr_scale^k
+    SmoothTaps taps;
+};
+
+struct FlowBuffers {
+    int W = 0, H = 0, F = 0;
+    FlowConfig cfg;
+    int n_levels = 0;  // number of scales (coarsest index = n_levels - 1)
+    FlowLevel level[FLOW_MAX_LEVELS];
+    PolyCoef poly;
+    float* I = nullptr;      // [2F][N]
+    float* R = nullptr;      // [2F][N][5]
+    float* M = nullptr;      // [F][N][5]
+    float2* flowA = nullptr; // [F][N]
+    float2* flowB = nullptr; // [F][N]
+};
+
+struct FlowLaunchStats {
+    long long launches = 0;
+};
+
+inline int flow_cv_round(double v) { return (int)lrint(v); }  // round half to even, like cvRound
+
+inline void flow_gaussian_kernel(int ksize, double sigma, float* out) {
+    if (sigma <= 0 && ksize == 3) {  // OpenCV's fixed small kernel
+        out[0] = 0.25f;
+        out[1] = 0.5f;
+        out[2] = 0.25f;
+        return;
+    }
+    if (sigma <= 0) sigma = ((ksize - 1) * 0.5 - 1) * 0.3 + 0.8;
+    const double scale2x = -0.5 / (sigma * sigma);
+    double sum = 0;
+    for (int i = 0; i < ksize; ++i) {
+        const double x = i - (ksize - 1) * 0.5;
+        out[i] = (float)exp(scale2x * x * x);
+        sum += out[i];
+    }
+    sum = 1.0 / sum;
+    for (int i = 0; i < ksize; ++i) out[i] = (float)(out[i] * sum);
+}
+
+// FarnebackPrepareGaussian: separable basis taps and the four entries of inv(G) that are used.
+// G is 6x6 with the sparsity  [a . . b b .; . b . . . .; . . b . . .; b . . c d .; b . . d c .; . . . . . d]
+// so the needed entries of its inverse have closed forms (G is symmetric positive definite).
+inline void flow_poly_coef(int n, double sigma, PolyCoef* pc) {
+    if (sigma < 1.1920929e-07) sigma = n * 0.3;
+    pc->n = n;
+    float g[2 * FLOW_MAX_POLY_N + 1];
+    double s = 0;
+    for (int x = -n; x <= n; ++x) {
+        g[x + n] = (float)exp(-x * x / (2 * sigma * sigma));
+        s += g[x + n];
+    }
+    s = 1.0 / s;
+    for (int x = -n; x <= n; ++x) g[x + n] = (float)(g[x + n] * s);
+    for (int x = 0; x <= n; ++x) {
+        pc->g[x] = g[x + n];
+        pc->xg[x] = (float)(x * g[x + n]);
+        pc->xxg[x] = (float)(x * x * g[x + n]);
+    }
+    double a = 0, b = 0, c = 0, d = 0;
+    for (int y = -n; y <= n; ++y)
+        for (int x = -n; x <= n; ++x) {
+            // OpenCV forms these products in float (float * float * int ...) and accumulates in double
+            const volatile float gg = g[y + n] * g[x + n];
+            const volatile float gx2 = (float)(gg * (float)x) * (float)x;
+            const volatile float gx4 = (float)((float)(gx2 * (float)x) * (float)x);
+            const volatile float gx2y2 = (float)((float)(gx2 * (float)y) * (float)y);
+            a += gg;
+            b += gx2;
+            c += gx4;
+            d += gx2y2;
+        }
+    // rows/cols {0,3,4}: [a b b; b c d; b d c]; {1},{2}: b; {5}: d
+    const double det3 = a * (c * c - d * d) - b * (b * c - b * d) + b * (b * d - b * c);
+    pc->ig11 = 1.0 / b;
+    pc->ig03 = -(b * c - b * d) / det3;  // cofactor(3,0)/det, symmetric
+    pc->ig33 = (a * c - b * b) / det3;
+    pc->ig55 = 1.0 / d;
+}
+
+inline const char* farneback_error(int rc) {
+    return rc == 1 ? "unsupported Farneback parameters" : rc == 2 ? "device allocation failed (flow buffers)" : "flow error";
+}
+
+inline int farneback_alloc(FlowBuffers* fb, int W, int H, int F, const FlowConfig& cfg, size_t* bytes) {
+    fb->W = W;
+    fb->H = H;
+    fb->F = F;
+    fb->cfg = cfg;
+    if (cfg.poly_n < 1 || cfg.poly_n > FLOW_MAX_POLY_N || cfg.winsize < 1 || cfg.winsize > 63 || cfg.iters < 1 ||
+        cfg.levels < 1 || cfg.levels >= FLOW_MAX_LEVELS || !(cfg.pyr_scale > 0 && cfg.pyr_scale < 1))
+        return 1;
+    // number of scales: OpenCV stops when the next level would be smaller than 32 px
+    int k = 0;
+    double scale = 1;
+    for (; k < cfg.levels; ++k) {
+        scale *= cfg.pyr_scale;
+        if (W * scale < 32 || H * scale < 32) break;
+    }
+    fb->n_levels = k + 1;
+    for (int l = 0; l <= k; ++l) {
+        double sc = 1;
+        for (int i = 0; i < l; ++i) sc *= cfg.pyr_scale;
+        FlowLevel& L = fb->level[l];
+        L.scale = sc;
+        const double sigma = (1.0 / sc - 1) * 0.5;
+        int smooth = flow_cv_round(sigma * 5) | 1;
+        smooth = smooth < 3 ? 3 : smooth;
+        if (smooth / 2 > FLOW_MAX_SMOOTH_RADIUS) return 1;
+        L.taps.radius = smooth / 2;
+        flow_gaussian_kernel(smooth, sigma, L.taps.k);
+        L.w = flow_cv_round(W * sc);
+        L.h = flow_cv_round(H * sc);
+        if (L.w < 2 || L.h < 2) return 1;
+    }
+    flow_poly_coef(cfg.poly_n, cfg.poly_sigma, &fb->poly);
+    const size_t N = (size_t)W * H;
+    size_t total = 0;
+    auto alloc = [&](void** p, size_t b) {
+        total += b;
+        return cudaMalloc(p, b) == cudaSuccess;
+    };
+    if (!alloc((void**)&fb->I, 2 * F * N * sizeof(float)) || !alloc((void**)&fb->R, 2 * F * N * 5 * sizeof(float)) ||
+        !alloc((void**)&fb->M, F * N * 5 * sizeof(float)) || !alloc((void**)&fb->flowA, F * N * sizeof(float2)) ||
+        !alloc((void**)&fb->flowB, F * N * sizeof(float2)))
+        return 2;
+    if (bytes) *bytes = total;
+    return 0;
+}
+
+inline void farneback_free(FlowBuffers* fb) {
+    cudaFree(fb->I);
+    cudaFree(fb->R);
+    cudaFree(fb->M);
+    cudaFree(fb->flowA);
+    cudaFree(fb->flowB);
+    fb->I = fb->R = fb->M = nullptr;
+    fb->flowA = fb->flowB = nullptr;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1  pyramid level: convertTo(CV_32F) -> GaussianBlur(full resolution, smooth_sz, sigma,
+// BORDER_REFLECT_101) -> resize(level size, INTER_LINEAR), fused: one thread per level pixel evaluates
+// the (at most four) blurred full-resolution samples its bilinear footprint needs, rows first and then
+// columns like OpenCV's separable filter, and interpolates.  The blurred full-resolution image never
+// exists in HBM.
+// ---------------------------------------------------------------------------------------------
+struct ImageSet {  // image s of the batch lives at (s < split ? base0 + s*N : base1 + (s-split)*N)
+    const u8* base0;
+    const u8* base1;
+    int split;
+    int count;
+};
+
+DOFS_D int flow_reflect101(int i, int n) {
+    while (i < 0 || i >= n) {
+        if (i < 0) i = -i;
+        if (i >= n) i = 2 * (n - 1) - i;
+    }
+    return i;
+}
+
+// cv::resize INTER_LINEAR source coordinate: s = (d + 0.5) * (src/dst) - 0.5, clamped like OpenCV
+DOFS_D void flow_linear_coord(int d, double scale, int src_n, int* i0, float* frac) {
+    float f = (float)((d + 0.5) * scale - 0.5);
+    int i = (int)floorf(f);
+    f -= (float)i;
+    if (i < 0) {
+        i = 0;
+        f = 0.f;
+    }
+    if (i >= src_n - 1) {
+        i = src_n - 1;
+        f = 0.f;
+    }
+    *i0 = i;
+    *frac = f;
+}
+
+__global__ void __launch_bounds__(256)
+k_pyr_level(ImageSet imgs, float* __restrict__ I, int W, int H, int Wk, int Hk, SmoothTaps taps) {
+    const int img = blockIdx.z;
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= Wk || y >= Hk) return;
+    const size_t N = (size_t)W * H;
+    const u8* src = img < imgs.split ? imgs.base0 + (size_t)img * N : imgs.base1 + (size_t)(img - imgs.split) * N;
+    const int r = taps.radius;
+    int sx, sy;
+    float fx, fy;
+    if (Wk == W && Hk == H) {  // resize to the same size is a copy
+        sx = x;
+        sy = y;
+        fx = fy = 0.f;
+    } else {
+        flow_linear_coord(x, (double)W / Wk, W, &sx, &fx);
+        flow_linear_coord(y, (double)H / Hk, H, &sy, &fy);
+    }
+    const int nx = fx != 0.f ? 2 : 1, ny = fy != 0.f ? 2 : 1;
+    // column (vertical) filter of the row-filtered samples, for the nx x ny blurred samples
+    float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};  // [dy][dx]
+    for (int j = -r; j <= r + ny - 1; ++j) {
+        const int yy = flow_reflect101(sy + j, H);
+        const u8* row = src + (size_t)yy * W;
+        float h0 = 0.f, h1 = 0.f;  // row filter at columns sx and sx+1
+        const bool interior = sx - r >= 0 && sx + r + 1 < W;
+        if (interior) {
+            float prev = (float)row[sx - r];
+            for (int i = -r; i <= r; ++i) {
+                const float nxt = (float)row[sx + i + 1];
+                h0 = fmaf(taps.k[i + r], prev, h0);
+                h1 = fmaf(taps.k[i + r], nxt, h1);
+                prev = nxt;
+            }
+        } else {
+            for (int i = -r; i <= r; ++i) {
+                h0 = fmaf(taps.k[i + r], (float)row[flow_reflect101(sx + i, W)], h0);
+                if (nx == 2) h1 = fmaf(taps.k[i + r], (float)row[flow_reflect101(sx + 1 + i, W)], h1);
+            }
+        }
+        if (j <= r) {
+            acc[0][0] = fmaf(taps.k[j + r], h0, acc[0][0]);
+            acc[0][1] = fmaf(taps.k[j + r], h1, acc[0][1]);
+        }
+        if (ny == 2 && j >= -r + 1) {
+            acc[1][0] = fmaf(taps.k[j - 1 + r], h0, acc[1][0]);
+            acc[1][1] = fmaf(taps.k[j - 1 + r], h1, acc[1][1]);
+        }
+    }
+    // bilinear: horizontal, then vertical
+    const float top = nx == 2 ? fmaf(acc[0][1], fx, acc[0][0] * (1.f - fx)) : acc[0][0];
+    float v = top;
+    if (ny == 2) {
+        const float bot = nx == 2 ? fmaf(acc[1][1], fx, acc[1][0] * (1.f - fx)) : acc[1][0];
+        v = fmaf(bot, fy, top * (1.f - fy));
+    }
+    I[((size_t)img * Hk + y) * Wk + x] = v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2  FarnebackPolyExp: 3 vertical moment sums in float (rows clamped), 6 horizontal sums in double
+// (columns clamped), projected through inv(G).  Block = 32x8 pixels; the vertical pass of the tile
+// plus a halo of n columns is staged in shared memory.
+// ---------------------------------------------------------------------------------------------
+#define PE_TW 32
+#define PE_TH 8
+
+__global__ void __launch_bounds__(PE_TW * PE_TH)
+k_polyexp(const float* __restrict__ I, float* __restrict__ R, int Wk, int Hk, PolyCoef pc) {
+    __shared__ float s_row[3][PE_TH][PE_TW + 2 * FLOW_MAX_POLY_N];
+    const int img = blockIdx.z;
+    const int n = pc.n;
+    const int x0 = blockIdx.x * PE_TW, y0 = blockIdx.y * PE_TH;
+    const float* src = I + (size_t)img * Wk * Hk;
+    const int span = PE_TW + 2 * n;
+    for (int idx = threadIdx.x; idx < span * PE_TH; idx += PE_TW * PE_TH) {
+        const int ty = idx / span, cx = idx - ty * span;
+        const int y = min(y0 + ty, Hk - 1);
+        const int xs = min(max(x0 + cx - n, 0), Wk - 1);
+        const float c = src[(size_t)y * Wk + xs];
+        float t0 = xfmul(c, pc.g[0]), t1 = 0.f, t2 = 0.f;
+        for (int k = 1; k <= n; ++k) {
+            const float a = src[(size_t)max(y - k, 0) * Wk + xs];
+            const float b = src[(size_t)min(y + k, Hk - 1) * Wk + xs];
+            const float p = xfadd(a, b);
+            t0 = xfadd(t0, xfmul(pc.g[k], p));
+            t1 = xfadd(t1, xfmul(pc.xg[k], xfsub(b, a)));
+            t2 = xfadd(t2, xfmul(pc.xxg[k], p));
+        }
+        s_row[0][ty][cx] = t0;
+        s_row[1][ty][cx] = t1;
+        s_row[2][ty][cx] = t2;
+    }
+    __syncthreads();
+    const int tx = threadIdx.x & (PE_TW - 1), ty = threadIdx.x / PE_TW;
+    const int x = x0 + tx, y = y0 + ty;
+    if (x >= Wk || y >= Hk) return;
+    const float* r0 = &s_row[0][ty][tx + n];
+    const float* r1 = &s_row[1][ty][tx + n];
+    const float* r2 = &s_row[2][ty][tx + n];
+    double b1 = (double)xfmul(r0[0], pc.g[0]), b2 = 0, b3 = (double)xfmul(r1[0], pc.g[0]), b4 = 0;
+    double b5 = (double)xfmul(r2[0], pc.g[0]), b6 = 0;
+    for (int k = 1; k <= n; ++k) {
+        const double tg = (double)xfadd(r0[k], r0[-k]);
+        const float g0 = pc.g[k];
+        b1 = xdadd(b1, xdmul(tg, (double)g0));
+        b4 = xdadd(b4, xdmul(tg, (double)pc.xxg[k]));
+        b2 = xdadd(b2, (double)xfmul(xfsub(r0[k], r0[-k]), pc.xg[k]));
+        b3 = xdadd(b3, (double)xfmul(xfadd(r1[k], r1[-k]), g0));
+        b6 = xdadd(b6, (double)xfmul(xfsub(r1[k], r1[-k]), pc.xg[k]));
+        b5 = xdadd(b5, (double)xfmul(xfadd(r2[k], r2[-k]), g0));
+    }
+    float* out = R + (((size_t)img * Hk + y) * Wk + x) * 5;
+    out[0] = (float)xdmul(b3, pc.ig11);
+    out[1] = (float)xdmul(b2, pc.ig11);
+    out[2] = (float)xdadd(xdmul(b1, pc.ig03), xdmul(b5, pc.ig33));
+    out[3] = (float)xdadd(xdmul(b1, pc.ig03), xdmul(b4, pc.ig33));
+    out[4] = (float)xdmul(b6, pc.ig55);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3  flow of the next finer level: resize(prev_flow, size, INTER_LINEAR) * (1 / pyr_scale)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_flow_upsample(const float2* __restrict__ prev, float2* __restrict__ flow, int Wp, int Hp, int Wk, int Hk, double mul) {
+    const int pair = blockIdx.z;
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= Wk || y >= Hk) return;
+    int sx, sy;
+    float fx, fy;
+    flow_linear_coord(x, (double)Wp / Wk, Wp, &sx, &fx);
+    flow_linear_coord(y, (double)Hp / Hk, Hp, &sy, &fy);
+    const float2* src = prev + (size_t)pair * Wp * Hp;
+    const int sx1 = min(sx + 1, Wp - 1), sy1 = min(sy + 1, Hp - 1);
+    const float2 a = src[(size_t)sy * Wp + sx], b = src[(size_t)sy * Wp + sx1];
+    const float2 c = src[(size_t)sy1 * Wp + sx], d = src[(size_t)sy1 * Wp + sx1];
+    const float wx0 = 1.f - fx, wy0 = 1.f - fy;
+    const float tx = xfadd(xfmul(a.x, wx0), xfmul(b.x, fx)), ty = xfadd(xfmul(a.y, wx0), xfmul(b.y, fx));
+    const float bx = xfadd(xfmul(c.x, wx0), xfmul(d.x, fx)), by = xfadd(xfmul(c.y, wx0), xfmul(d.y, fx));
+    const float vx = xfadd(xfmul(tx, wy0), xfmul(bx, fy)), vy = xfadd(xfmul(ty, wy0), xfmul(by, fy));
+    flow[((size_t)pair * Hk + y) * Wk + x] = make_float2((float)xdmul((double)vx, mul), (float)xdmul((double)vy, mul));
+}
+
+// ---------------------------------------------------------------------------------------------
+// K4  FarnebackUpdateMatrices: warp R1 by the current flow (bilinear gather), average with R0, build
+// the five products; attenuate within 5 px of the border.
+// ---------------------------------------------------------------------------------------------
+struct PairSlots {  // pair p uses polynomial expansions of images (p + first0) and (p + first1)
+    int first0, first1;
+};
+
+DOFS_D float flow_border_scale(int x, int y, int w, int h) {
+    const float border[5] = {0.14f, 0.14f, 0.4472f, 0.4472f, 0.4472f};
+    float s = 1.f;
+    s = xfmul(s, x < 5 ? border[x] : 1.f);
+    s = xfmul(s, x >= w - 5 ? border[w - x - 1] : 1.f);
+    s = xfmul(s, y < 5 ? border[y] : 1.f);
+    s = xfmul(s, y >= h - 5 ? border[h - y - 1] : 1.f);
+    return s;
+}
+
+__global__ void __launch_bounds__(256)
+k_update_matrices(const float* __restrict__ R, const float2* __restrict__ flow, float* __restrict__ M, int Wk, int Hk,
+                  PairSlots ps) {
+    const int pair = blockIdx.z;
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= Wk || y >= Hk) return;
+    const size_t npx = (size_t)Wk * Hk;
+    const float* R0 = R + ((size_t)(pair + ps.first0) * npx + (size_t)y * Wk + x) * 5;
+    const float* R1 = R + (size_t)(pair + ps.first1) * npx * 5;
+    const float2 d = flow[(size_t)pair * npx + (size_t)y * Wk + x];
+    const float dx = d.x, dy = d.y;
+    float fx = xfadd((float)x, dx), fy = xfadd((float)y, dy);
+    const int x1 = (int)floorf(fx), y1 = (int)floorf(fy);
+    fx = xfsub(fx, (float)x1);
+    fy = xfsub(fy, (float)y1);
+    const float q0 = R0[0], q1 = R0[1], q2 = R0[2], q3 = R0[3], q4 = R0[4];
+    float r2, r3, r4, r5, r6;
+    if ((unsigned)x1 < (unsigned)(Wk - 1) && (unsigned)y1 < (unsigned)(Hk - 1)) {
+        const float a00 = xfmul(xfsub(1.f, fx), xfsub(1.f, fy)), a01 = xfmul(fx, xfsub(1.f, fy));
+        const float a10 = xfmul(xfsub(1.f, fx), fy), a11 = xfmul(fx, fy);
+        const float* p = R1 + ((size_t)y1 * Wk + x1) * 5;
+        const float* q = p + (size_t)Wk * 5;
+#define BIL(c) xfadd(xfadd(xfadd(xfmul(a00, p[c]), xfmul(a01, p[5 + c])), xfmul(a10, q[c])), xfmul(a11, q[5 + c]))
+        r2 = BIL(0);
+        r3 = BIL(1);
+        r4 = BIL(2);
+        r5 = BIL(3);
+        r6 = BIL(4);
+#undef BIL
+        r4 = xfmul(xfadd(q2, r4), 0.5f);
+        r5 = xfmul(xfadd(q3, r5), 0.5f);
+        r6 = xfmul(xfadd(q4, r6), 0.25f);
+    } else {
+        r2 = r3 = 0.f;
+        r4 = q2;
+        r5 = q3;
+        r6 = xfmul(q4, 0.5f);
+    }
+    r2 = xfmul(xfsub(q0, r2), 0.5f);
+    r3 = xfmul(xfsub(q1, r3), 0.5f);
+    r2 = xfadd(r2, xfadd(xfmul(r4, dy), xfmul(r6, dx)));
+    r3 = xfadd(r3, xfadd(xfmul(r6, dy), xfmul(r5, dx)));
+    if ((unsigned)(x - 5) >= (unsigned)(Wk - 10) || (unsigned)(y - 5) >= (unsigned)(Hk - 10)) {
+        const float s = flow_border_scale(x, y, Wk, Hk);
+        r2 = xfmul(r2, s);
+        r3 = xfmul(r3, s);
+        r4 = xfmul(r4, s);
+        r5 = xfmul(r5, s);
+        r6 = xfmul(r6, s);
+    }
+    float* out = M + ((size_t)pair * npx + (size_t)y * Wk + x) * 5;
+    out[0] = xfadd(xfmul(r4, r4), xfmul(r6, r6));
+    out[1] = xfmul(xfadd(r4, r5), r6);
+    out[2] = xfadd(xfmul(r5, r5), xfmul(r6, r6));
+    out[3] = xfadd(xfmul(r4, r2), xfmul(r6, r3));
+    out[4] = xfadd(xfmul(r6, r2), xfmul(r5, r3));
+}
+
+// ---------------------------------------------------------------------------------------------
+// K5  FarnebackUpdateFlow_Blur: winsize x winsize box mean of M (replicated borders) and the 2x2
+// solve, in double.  Block = 32x8 pixels; the M tile with its halo is staged in shared memory, the
+// vertical window sums are formed once per column and reused by the horizontal window.
+// ---------------------------------------------------------------------------------------------
+#define BX_TW 32
+#define BX_TH 8
+
+__global__ void __launch_bounds__(BX_TW * BX_TH)
+k_box_solve(const float* __restrict__ M, float2* __restrict__ flow, int Wk, int Hk, int m /* winsize/2 */) {
+    extern __shared__ __align__(16) unsigned char bx_smem[];
+    const int cols = BX_TW + 2 * m, rows = BX_TH + 2 * m;
+    float* s_m = reinterpret_cast<float*>(bx_smem);                         // [rows][cols][5]
+    double* s_v = reinterpret_cast<double*>(bx_smem + (((size_t)rows * cols * 5 * 4 + 15) & ~(size_t)15));  // [TH][cols][5]
+    const int pair = blockIdx.z;
+    const int x0 = blockIdx.x * BX_TW, y0 = blockIdx.y * BX_TH;
+    const float* src = M + (size_t)pair * Wk * Hk * 5;
+    for (int idx = threadIdx.x; idx < rows * cols; idx += BX_TW * BX_TH) {
+        const int ry = idx / cols, cx = idx - ry * cols;
+        const int yy = min(max(y0 + ry - m, 0), Hk - 1);
+        const int xx = min(max(x0 + cx - m, 0), Wk - 1);
+        const float* p = src + ((size_t)yy * Wk + xx) * 5;
+        float* d = s_m + (size_t)idx * 5;
+        d[0] = p[0];
+        d[1] = p[1];
+        d[2] = p[2];
+        d[3] = p[3];
+        d[4] = p[4];
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < BX_TH * cols * 5; idx += BX_TW * BX_TH) {
+        const int ty = idx / (cols * 5), rem = idx - ty * cols * 5;  // rem = cx*5 + c
+        double s = 0;
+        for (int j = 0; j <= 2 * m; ++j) s += (double)s_m[(size_t)(ty + j) * cols * 5 + rem];
+        s_v[idx] = s;
+    }
+    __syncthreads();
+    const int tx = threadIdx.x & (BX_TW - 1), ty = threadIdx.x / BX_TW;
+    const int x = x0 + tx, y = y0 + ty;
+    if (x >= Wk || y >= Hk) return;
+    double g11 = 0, g12 = 0, g22 = 0, h1 = 0, h2 = 0;
+    const double* v = s_v + ((size_t)ty * cols + tx) * 5;
+    for (int i = 0; i <= 2 * m; ++i) {
+        g11 += v[i * 5];
+        g12 += v[i * 5 + 1];
+        g22 += v[i * 5 + 2];
+        h1 += v[i * 5 + 3];
+        h2 += v[i * 5 + 4];
+    }
+    const int bs = 2 * m + 1;
+    const double scale = 1.0 / (double)(bs * bs);
+    g11 = xdmul(g11, scale);
+    g12 = xdmul(g12, scale);
+    g22 = xdmul(g22, scale);
+    h1 = xdmul(h1, scale);
+    h2 = xdmul(h2, scale);
+    const double idet = xddiv(1.0, xdadd(xdsub(xdmul(g11, g22), xdmul(g12, g12)), 1e-3));
+    const float u = (float)xdmul(xdsub(xdmul(g11, h2), xdmul(g12, h1)), idet);
+    const float w = (float)xdmul(xdsub(xdmul(g22, h1), xdmul(g12, h2)), idet);
+    flow[((size_t)pair * Hk + y) * Wk + x] = make_float2(u, w);
+}
+
+inline size_t box_solve_smem(int m) {
+    const size_t cols = BX_TW + 2 * m, rows = BX_TH + 2 * m;
+    return ((rows * cols * 5 * 4 + 15) & ~(size_t)15) + (size_t)BX_TH * cols * 5 * 8;
+}
+
+// ---------------------------------------------------------------------------------------------
+// driver: n pairs; images of pair p are gray0 + p*N and gray1 + p*N.  When gray1 == gray0 + N the
+// batch is a video (pair p = frames p, p+1) and every frame is expanded once instead of twice.
+// Returns 0, or non-zero after a launch error.
+// ---------------------------------------------------------------------------------------------
+inline int farneback_run(FlowBuffers& fb, const u8* d_gray0, const u8* d_gray1, int n, float2* d_flow_out,
+                         cudaStream_t stream, FlowLaunchStats* st) {
+    const size_t N = (size_t)fb.W * fb.H;
+    const bool video = d_gray1 == d_gray0 + N;
+    ImageSet imgs;
+    imgs.base0 = d_gray0;
+    imgs.base1 = d_gray1;
+    imgs.split = video ? n + 1 : n;
+    imgs.count = video ? n + 1 : 2 * n;
+    PairSlots ps;
+    ps.first0 = 0;
+    ps.first1 = video ? 1 : n;
+    const int m = fb.cfg.winsize / 2;
+    const size_t bx_smem = box_solve_smem(m);
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(k_box_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bx_smem) != cudaSuccess)
+            return 3;
+        attr_set = true;
+    }
+    float2* cur = nullptr;   // flow of the level being refined
+    float2* prev = nullptr;  // flow of the coarser level
+    int Wp = 0, Hp = 0;
+    for (int k = fb.n_levels - 1; k >= 0; --k) {
+        const FlowLevel& L = fb.level[k];
+        const dim3 blk(256);
+        const dim3 g_img((L.w + 31) / 32, (L.h + 7) / 8, imgs.count);
+        const dim3 g_pair((L.w + 31) / 32, (L.h + 7) / 8, n);
+        cur = (k == 0) ? d_flow_out : (prev == fb.flowA ? fb.flowB : fb.flowA);
+        if (!prev) {
+            if (cudaMemsetAsync(cur, 0, (size_t)n * L.w * L.h * sizeof(float2), stream) != cudaSuccess) return 3;
+        } else {
+            k_flow_upsample<<<g_pair, blk, 0, stream>>>(prev, cur, Wp, Hp, L.w, L.h, 1.0 / fb.cfg.pyr_scale);
+            st->launches++;
+        }
+        k_pyr_level<<<g_img, blk, 0, stream>>>(imgs, fb.I, fb.W, fb.H, L.w, L.h, L.taps);
+        k_polyexp<<<g_img, blk, 0, stream>>>(fb.I, fb.R, L.w, L.h, fb.poly);
+        k_update_matrices<<<g_pair, blk, 0, stream>>>(fb.R, cur, fb.M, L.w, L.h, ps);
+        st->launches += 3;
+        for (int it = 0; it < fb.cfg.iters; ++it) {
+            k_box_solve<<<g_pair, blk, bx_smem, stream>>>(fb.M, cur, L.w, L.h, m);
+            st->launches++;
+            if (it < fb.cfg.iters - 1) {
+                k_update_matrices<<<g_pair, blk, 0, stream>>>(fb.R, cur, fb.M, L.w, L.h, ps);
+                st->launches++;
+            }
+        }
+        prev = cur;
+        Wp = L.w;
+        Hp = L.h;
+    }
+    return cudaGetLastError() == cudaSuccess ? 0 : 3;
+}

@@ -28,8 +28,8 @@ DOFS_D P2f p2(float x, float y) {
     p.y = y;
     return p;
 }
-DOFS_D P2f p2sub(P2f a, P2f b) { return p2(fsub(a.x, b.x), fsub(a.y, b.y)); }
-DOFS_D P2f p2add(P2f a, P2f b) { return p2(fadd(a.x, b.x), fadd(a.y, b.y)); }
+DOFS_D P2f p2sub(P2f a, P2f b) { return p2(xfsub(a.x, b.x), xfsub(a.y, b.y)); }
+DOFS_D P2f p2add(P2f a, P2f b) { return p2(xfadd(a.x, b.x), xfadd(a.y, b.y)); }
 DOFS_D double p2norm(P2f a) { return norm2d(a.x, a.y); }
 
 DOFS_D float dofs_nanf() { return __int_as_float(0x7fc00000); }
@@ -37,25 +37,25 @@ DOFS_D float dofs_inff() { return __int_as_float(0x7f800000); }
 
 // Intersection of lines AB and CD, all float; (NaN, NaN) when |det| < 1e-9.
 DOFS_D P2f lift_isect(P2f A, P2f B, P2f C, P2f D) {
-    float a1 = fsub(B.y, A.y);
-    float b1 = fsub(A.x, B.x);
-    float c1 = fadd(fmul(a1, A.x), fmul(b1, A.y));
-    float a2 = fsub(D.y, C.y);
-    float b2 = fsub(C.x, D.x);
-    float c2 = fadd(fmul(a2, C.x), fmul(b2, C.y));
-    float det = fsub(fmul(a1, b2), fmul(a2, b1));
+    float a1 = xfsub(B.y, A.y);
+    float b1 = xfsub(A.x, B.x);
+    float c1 = xfadd(xfmul(a1, A.x), xfmul(b1, A.y));
+    float a2 = xfsub(D.y, C.y);
+    float b2 = xfsub(C.x, D.x);
+    float c2 = xfadd(xfmul(a2, C.x), xfmul(b2, C.y));
+    float det = xfsub(xfmul(a1, b2), xfmul(a2, b1));
     if ((double)fabsf(det) < 1e-9) return p2(dofs_nanf(), dofs_nanf());
-    float x = fdiv(fsub(fmul(b2, c1), fmul(b1, c2)), det);
-    float y = fdiv(fsub(fmul(a1, c2), fmul(a2, c1)), det);
+    float x = xfdiv(xfsub(xfmul(b2, c1), xfmul(b1, c2)), det);
+    float y = xfdiv(xfsub(xfmul(a1, c2), xfmul(a2, c1)), det);
     return p2(x, y);
 }
 
 // Homography applied to a point, float, summed left to right.
 DOFS_D P2f lift_warp(P2f p, const float* M) {
-    float den = fadd(fadd(fmul(M[6], p.x), fmul(M[7], p.y)), M[8]);
-    float nx = fadd(fadd(fmul(M[0], p.x), fmul(M[1], p.y)), M[2]);
-    float ny = fadd(fadd(fmul(M[3], p.x), fmul(M[4], p.y)), M[5]);
-    return p2(fdiv(nx, den), fdiv(ny, den));
+    float den = xfadd(xfadd(xfmul(M[6], p.x), xfmul(M[7], p.y)), M[8]);
+    float nx = xfadd(xfadd(xfmul(M[0], p.x), xfmul(M[1], p.y)), M[2]);
+    float ny = xfadd(xfadd(xfmul(M[3], p.x), xfmul(M[4], p.y)), M[5]);
+    return p2(xfdiv(nx, den), xfdiv(ny, den));
 }
 
 // Ground rectangle of prior size (w, h) = (dim_l, dim_w) anchored at the warped box corners.
@@ -63,31 +63,31 @@ DOFS_D bool lift_bottom(const P2f* bev, double orient, double w, double h, doubl
     P2f a0 = p2(bev[0].x, -bev[0].y), a1 = p2(bev[1].x, -bev[1].y);
     P2f a2 = p2(bev[2].x, -bev[2].y), a3 = p2(bev[3].x, -bev[3].y);
     const double co = cos(orient), si = sin(orient);
-    P2f k = lift_isect(a3, p2((float)dadd((double)a3.x, co), (float)dadd((double)a3.y, si)), a0, a1);
+    P2f k = lift_isect(a3, p2((float)xdadd((double)a3.x, co), (float)xdadd((double)a3.y, si)), a0, a1);
     if (k.x == dofs_inff() || k.y == dofs_inff()) return false;
     double l = p2norm(p2sub(a3, k));
     if (l == 0) return false;
-    const double lw = dsub(l, w);
-    P2f t0 = p2((float)dmul((double)a0.x, lw), (float)dmul((double)a0.y, lw));
-    P2f t1 = p2((float)dmul((double)a3.x, w), (float)dmul((double)a3.y, w));
+    const double lw = xdsub(l, w);
+    P2f t0 = p2((float)xdmul((double)a0.x, lw), (float)xdmul((double)a0.y, lw));
+    P2f t1 = p2((float)xdmul((double)a3.x, w), (float)xdmul((double)a3.y, w));
     P2f s = p2add(t0, t1);
-    P2f c = p2((float)ddiv((double)s.x, l), (float)ddiv((double)s.y, l));
-    P2f b = lift_isect(c, p2((float)dadd((double)c.x, co), (float)dadd((double)c.y, si)), a0, a1);
+    P2f c = p2((float)xddiv((double)s.x, l), (float)xddiv((double)s.y, l));
+    P2f b = lift_isect(c, p2((float)xdadd((double)c.x, co), (float)xdadd((double)c.y, si)), a0, a1);
     if (b.x == dofs_inff()) return false;
     double ew = p2norm(p2sub(c, b));
-    double error_w = (ew < w) ? ddiv(ew, w) : ddiv(w, ew);
-    P2f d = lift_isect(c, p2((float)dsub((double)c.x, si), (float)dadd((double)c.y, co)), a3, a2);
+    double error_w = (ew < w) ? xddiv(ew, w) : xddiv(w, ew);
+    P2f d = lift_isect(c, p2((float)xdsub((double)c.x, si), (float)xdadd((double)c.y, co)), a3, a2);
     if (d.x == dofs_inff()) return false;
     double el = p2norm(p2sub(c, d));
-    double error_l = (el < h) ? ddiv(el, h) : ddiv(h, el);
+    double error_l = (el < h) ? xddiv(el, h) : xddiv(h, el);
     P2f bd = p2add(b, d);
-    P2f center = p2(fdiv(bd.x, 2.0f), fdiv(bd.y, 2.0f));
-    P2f f = p2sub(p2(fmul(center.x, 2.0f), fmul(center.y, 2.0f)), c);
+    P2f center = p2(xfdiv(bd.x, 2.0f), xfdiv(bd.y, 2.0f));
+    P2f f = p2sub(p2(xfmul(center.x, 2.0f), xfmul(center.y, 2.0f)), c);
     out[0] = p2(c.x, -c.y);
     out[1] = p2(b.x, -b.y);
     out[2] = p2(f.x, -f.y);
     out[3] = p2(d.x, -d.y);
-    *error = dmul(error_w, error_l);
+    *error = xdmul(error_w, error_l);
     return true;
 }
 
@@ -102,11 +102,11 @@ DOFS_D void lift_bottom_variants(float dirx, float diry, int xmin, int ymin, int
     s->orient = 0.0;
     P2f center = p2((float)((xmin + xmax) / 2), (float)((ymin + ymax) / 2));
     double n = norm2d(dirx, diry);
-    P2f nd = p2((float)ddiv((double)dirx, n), (float)ddiv((double)diry, n));
+    P2f nd = p2((float)xddiv((double)dirx, n), (float)xddiv((double)diry, n));
     P2f t1 = lift_warp(center, mat);
     P2f t2 = lift_warp(p2add(center, nd), mat);
-    double vx = (double)fsub(t2.x, t1.x);
-    double vy = (double)fsub(t1.y, t2.y);
+    double vx = (double)xfsub(t2.x, t1.x);
+    double vy = (double)xfsub(t1.y, t2.y);
     double orient = atan2(vy, vx);
     if (isinf(orient)) return;
     s->cls = cls;
@@ -123,7 +123,7 @@ DOFS_D void lift_bottom_variants(float dirx, float diry, int xmin, int ymin, int
 #pragma unroll
     for (int i = 0; i < 4; ++i) s->lower[i] = lift_warp(s->rect[i], inv_mat);
     const P2f l0 = s->lower[0], l1 = s->lower[1], l2 = s->lower[2], l3 = s->lower[3];
-    P2f u2 = p2sub(l2, p2(0.0f, fsub(l2.y, (float)ymin)));
+    P2f u2 = p2sub(l2, p2(0.0f, xfsub(l2.y, (float)ymin)));
     P2f right_van = lift_isect(l1, l2, l0, l3);
     P2f u1 = lift_isect(u2, right_van, p2((float)xmin, (float)ymin), p2((float)xmin, (float)ymax));
     P2f left_van = lift_isect(l2, l3, l0, l1);
@@ -138,7 +138,7 @@ DOFS_D void lift_bottom_variants(float dirx, float diry, int xmin, int ymin, int
     P2f expected_edge = lift_warp(s->rect[0], inv_upper);
     double expected_h = p2norm(p2sub(l0, expected_edge));
     double computed_h = p2norm(p2sub(u0, l0));
-    s->h_error = (computed_h < expected_h) ? ddiv(computed_h, expected_h) : ddiv(expected_h, computed_h);
+    s->h_error = (computed_h < expected_h) ? xddiv(computed_h, expected_h) : xddiv(expected_h, computed_h);
     s->orient = orient;
 }
 
@@ -151,7 +151,7 @@ DOFS_D double lift_get_score(float dirx, float diry, int xmin, int ymin, int xma
         LiftSolution s;
         lift_bottom_variants(dirx, diry, xmin, ymin, xmax, ymax, P.hg.persp, P.hg.inv, P.hg.upper[cls], cls,
                              P.cls_size[cls][0], P.cls_size[cls][1], &s);
-        double sc = ddiv(dadd(s.w_error, s.h_error), 2.0);
+        double sc = xddiv(xdadd(s.w_error, s.h_error), 2.0);
         if (s.has_rect && max_score < sc) {
             max_score = sc;
             *best = s;

@@ -106,7 +106,7 @@ k_blur_cols(const float2* __restrict__ src, float2* __restrict__ dst, int W, int
 // key = bit pattern of the f64 weight (non-negative doubles order like unsigned integers).
 // ---------------------------------------------------------------------------------------------
 DOFS_D u64 edge_key(float2 a, float2 b) {
-    float dx = fsub(a.x, b.x), dy = fsub(a.y, b.y);
+    float dx = xfsub(a.x, b.x), dy = xfsub(a.y, b.y);
     return (u64)__double_as_longlong(norm2d(dx, dy));
 }
 
@@ -213,11 +213,11 @@ k_bor_pixel(BorState S, const u32* __restrict__ rank, size_t rank_stride, int W,
             u32 cq = comp[edge_other(p, d, W)];
             if (cq != cp) {
                 mine = min(mine, r[d]);
-                atomicMin(&best[cq], r[d]);
+                if (r[d] < best[cq]) atomicMin(&best[cq], r[d]);  // best only decreases: a stale read is safe
             }
         }
     }
-    if (mine != DOFS_INF32) atomicMin(&best[cp], mine);
+    if (mine != DOFS_INF32 && mine < best[cp]) atomicMin(&best[cp], mine);
 }
 
 // per root: classify its pick (mutual winner / loser), record the loss
@@ -284,12 +284,23 @@ k_bor_finish(BorState S, int N, int levels) {
 
 // ---------------------------------------------------------------------------------------------
 // K9b  winner of every merge event (one event per losing root) and the event sort key
-//      key = lvl[winner] << 56 | winner << 32 | time ; payload = loser
+//      key = lvl[winner] << (tb + wb) | winner << tb | time ; payload = loser
+//      tb = bits of a sorted edge position (< 4N), wb = bits of a pixel id (< N): as few radix
+//      passes as the frame size allows (1080p: 23 + 21 + 5 = 49 bits -> 7 passes instead of 8)
 // ---------------------------------------------------------------------------------------------
 #define EV_KEY_NONE 0xFFFFFFFFFFFFFFFFull
+#define EV_MAX_WAVES 32
+
+struct EvBits {
+    int tb, wb;
+};
+DOFS_D u64 ev_chain(u64 key, EvBits b) { return key >> b.tb; }  // wave | winner
+DOFS_D u32 ev_winner(u64 key, EvBits b) { return (u32)(key >> b.tb) & ((1u << b.wb) - 1u); }
+DOFS_D u32 ev_time(u64 key, EvBits b) { return (u32)key & ((1u << b.tb) - 1u); }
+DOFS_D int ev_wave(u64 key, EvBits b) { return key == EV_KEY_NONE ? EV_MAX_WAVES - 1 : (int)(key >> (b.tb + b.wb)); }
 
 __global__ void __launch_bounds__(SEG_THREADS)
-k_event_keys(BorState S, u32* __restrict__ win, u64* __restrict__ ev_key, int N) {
+k_event_keys(BorState S, u32* __restrict__ win, u64* __restrict__ ev_key, int N, EvBits eb) {
     const int frame = blockIdx.y;
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= N) return;
@@ -303,23 +314,24 @@ k_event_keys(BorState S, u32* __restrict__ win, u64* __restrict__ ev_key, int N)
     u32 cur = S.up[fo + c];
     while (S.loss_time[fo + cur] < t) cur = S.up[fo + cur];
     win[fo + c] = cur;
-    ev_key[fo + c] = ((u64)S.lvl[fo + cur] << 56) | ((u64)cur << 32) | (u64)t;
+    ev_key[fo + c] = ((u64)S.lvl[fo + cur] << (eb.tb + eb.wb)) | ((u64)cur << eb.tb) | (u64)t;
 }
 
-// first event index of every wave (events are sorted by key; wave = key >> 56)
+// first event index of every wave (events are sorted by key)
 __global__ void __launch_bounds__(SEG_THREADS)
-k_wave_starts(const u64* __restrict__ ev_key, int* __restrict__ wave_start /* [F][64] */, int N) {
+k_wave_starts(const u64* __restrict__ ev_key, int* __restrict__ wave_start /* [F][EV_MAX_WAVES+1] */, int N,
+              EvBits eb) {
     const int frame = blockIdx.y;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
     const u64* k = ev_key + (size_t)frame * N;
-    const u64 ki = k[i];
-    const int wi = ki == EV_KEY_NONE ? 63 : (int)(ki >> 56);
-    const int wp = i == 0 ? -1 : (k[i - 1] == EV_KEY_NONE ? 63 : (int)(k[i - 1] >> 56));
+    const int wi = ev_wave(k[i], eb);
+    const int wp = i == 0 ? -1 : ev_wave(k[i - 1], eb);
+    int* ws = wave_start + frame * (EV_MAX_WAVES + 1);
     // waves without events keep the start of the next non-empty wave
-    for (int w = wp + 1; w <= wi; ++w) wave_start[frame * 64 + w] = i;
+    for (int w = wp + 1; w <= wi; ++w) ws[w] = i;
     if (i == N - 1)
-        for (int w = wi + 1; w < 64; ++w) wave_start[frame * 64 + w] = N;
+        for (int w = wi + 1; w <= EV_MAX_WAVES; ++w) ws[w] = N;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -330,7 +342,7 @@ k_wave_starts(const u64* __restrict__ ev_key, int* __restrict__ wave_start /* [F
 struct ReplayArgs {
     const u64* ev_key;     // [F][N] sorted
     const u32* ev_loser;   // [F][N] sorted payload
-    const int* wave_start; // [F][64]
+    const int* wave_start; // [F][EV_MAX_WAVES+1]
     int* rsize;            // [F][N]
     ushort4* rbbox;        // [F][N]
     float2* rflow;         // [F][N]
@@ -340,26 +352,28 @@ struct ReplayArgs {
     int cand_cap;
     int W, H, N;
     int min_size;
+    EvBits eb;
 };
 
 __global__ void __launch_bounds__(SEG_THREADS)
 k_replay_wave(ReplayArgs A, int wave) {
     const int frame = blockIdx.y;
-    const int w0 = A.wave_start[frame * 64 + wave], w1 = A.wave_start[frame * 64 + wave + 1];
+    const int w0 = A.wave_start[frame * (EV_MAX_WAVES + 1) + wave];
+    const int w1 = A.wave_start[frame * (EV_MAX_WAVES + 1) + wave + 1];
     const int i = w0 + blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= w1) return;
     const size_t fo = (size_t)frame * A.N;
     const u64* key = A.ev_key + fo;
     const u64 k0 = key[i];
-    const u32 chain = (u32)(k0 >> 32);  // wave | winner
-    if (i > w0 && (u32)(key[i - 1] >> 32) == chain) return;  // not the head of its chain
-    const u32 r = chain & 0x00FFFFFFu;
+    const u64 chain = ev_chain(k0, A.eb);  // wave | winner
+    if (i > w0 && ev_chain(key[i - 1], A.eb) == chain) return;  // not the head of its chain
+    const u32 r = ev_winner(k0, A.eb);
     int s = A.rsize[fo + r];
     float2 f = A.rflow[fo + r];
     ushort4 bb = A.rbbox[fo + r];
     const int y = (int)r / A.W;
     const bool row_ok = !(y < A.H / 10);                                  // graph.cpp:288
-    const double move_min = ddiv((double)(3 * (y + 1)), (double)A.H);     // graph.cpp:296
+    const double move_min = xddiv((double)(3 * (y + 1)), (double)A.H);     // graph.cpp:296
     int j = i;
     u64 kj = k0;
     for (;;) {
@@ -369,11 +383,11 @@ k_replay_wave(ReplayArgs A, int wave) {
         const ushort4 ba = A.rbbox[fo + a];
         // (flow_a * size_a + flow_b * size_b) / (size_a + size_b) with OpenCV's Vec2f rounding
         const float fsa = (float)sa, fsb = (float)s;
-        const float sx = fadd(fmul(fa.x, fsa), fmul(f.x, fsb));
-        const float sy = fadd(fmul(fa.y, fsa), fmul(f.y, fsb));
-        const double inv = ddiv(1.0, (double)(sa + s));
-        f.x = (float)dmul((double)sx, inv);
-        f.y = (float)dmul((double)sy, inv);
+        const float sx = xfadd(xfmul(fa.x, fsa), xfmul(f.x, fsb));
+        const float sy = xfadd(xfmul(fa.y, fsa), xfmul(f.y, fsb));
+        const double inv = xddiv(1.0, (double)(sa + s));
+        f.x = (float)xdmul((double)sx, inv);
+        f.y = (float)xdmul((double)sy, inv);
         s += sa;
         bb.x = min(bb.x, ba.x);
         bb.y = min(bb.y, ba.y);
@@ -386,7 +400,7 @@ k_replay_wave(ReplayArgs A, int wave) {
                 if (slot < A.cand_cap) {
                     Candidate c;
                     c.root = r;
-                    c.time = (u32)kj;
+                    c.time = ev_time(kj, A.eb);
                     c.size = s;
                     c.fx = f.x;
                     c.fy = f.y;
@@ -402,7 +416,7 @@ k_replay_wave(ReplayArgs A, int wave) {
         ++j;
         if (j >= w1) break;
         kj = key[j];
-        if ((u32)(kj >> 32) != chain) break;
+        if (ev_chain(kj, A.eb) != chain) break;
     }
     A.rsize[fo + r] = s;
     A.rflow[fo + r] = f;
@@ -436,7 +450,7 @@ k_lift_score(SelectArgs A, SegParams P) {
     const Candidate c = A.cand[(size_t)frame * A.cand_cap + i];
     const int xmin = c.bbox[0], ymin = c.bbox[1], xmax = c.bbox[2], ymax = c.bbox[3];
     const double rect_area = (double)((xmax - xmin + 1) * (ymax - ymin + 1));
-    const double convexity = ddiv((double)c.size, rect_area);
+    const double convexity = xddiv((double)c.size, rect_area);
     LiftSolution sol;
     const double score = lift_get_score(c.fx, c.fy, xmin, ymin, xmax, ymax, P, &sol);
     double kept = -1.0;
@@ -605,6 +619,6 @@ k_lift_problems(const float2* __restrict__ dir, const int4* __restrict__ bbox, c
     cd.bbox[2] = (u16)b.z;
     cd.bbox[3] = (u16)b.w;
     cd.pad = 0;
-    fill_box(&out[i], cd, ddiv(dadd(s.w_error, s.h_error), 2.0), s);
+    fill_box(&out[i], cd, xddiv(xdadd(s.w_error, s.h_error), 2.0), s);
     if (!s.has_rect) out[i].cls = c;
 }

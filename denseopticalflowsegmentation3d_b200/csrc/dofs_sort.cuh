@@ -21,8 +21,6 @@
 #define RS_WARPS (RS_THREADS / 32)
 #define RS_BINS 256
 
-#ifndef DOFS_EMUL
-
 // exclusive scan of one value per thread across a 256-thread block; also returns the block total
 DOFS_D u32 rs_block_excl_scan(u32 v, u32* s_warp /* >= 8 */, u32* total) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -176,4 +174,3 @@ k_radix_scatter(const u64* __restrict__ keys_in, const u32* __restrict__ vals_in
     }
 }
 
-#endif  // !DOFS_EMUL

@@ -106,6 +106,7 @@ long long dofs3d_device_bytes(const dofs3d_ctx* ctx);
 
 /* cv::cvtColor(BGR2GRAY) (segment.cpp:97-98) for n frames: bgr [n][H][W][3] -> gray [n][H][W]. */
 int dofs3d_gray(dofs3d_ctx* ctx, const uint8_t* bgr, int n_frames, uint8_t* gray_out);
+int dofs3d_gray_dev(dofs3d_ctx* ctx, const uint8_t* d_bgr, int n_frames, uint8_t* d_gray_out);
 
 /* cv::calcOpticalFlowFarneback(gray0, gray1, flow, pyr_scale, levels, winsize, iters, poly_n,
  * poly_sigma, 0) (segment.cpp:101) for n_pairs independent pairs:
@@ -159,9 +160,10 @@ int dofs3d_synth_frames_dev(dofs3d_ctx* ctx, uint32_t seed, int n_objects, int f
                             uint8_t* d_bgr_out);
 
 /* Per-stage device time (ms, CUDA events on the context's stream) of the last process/segment/flow
- * call when timing was enabled with dofs3d_set_timing(ctx, 1): names/values of up to cap stages. */
+ * call when timing was enabled with dofs3d_set_timing(ctx, 1): name, total ms and number of timed
+ * intervals of up to cap stages (the radix-sort kernels are timed one by one). */
 int dofs3d_set_timing(dofs3d_ctx* ctx, int enabled);
-int dofs3d_get_timing(dofs3d_ctx* ctx, const char** names, float* ms, int cap);
+int dofs3d_get_timing(dofs3d_ctx* ctx, const char** names, float* ms, int* counts, int cap);
 
 #ifdef __cplusplus
 }

