@@ -31,6 +31,30 @@ def build(force=False, verbose=False):
     return OUT
 
 
+HOST_SRC = os.path.join(HERE, "host", "src", "dofs3d_host.cpp")
+HOST_OUT = os.path.join(HERE, "libdofs3d_host.so")
+HOST_INC = os.path.join(HERE, "host", "inc")
+
+
+def build_host(force=False):
+    """The C++ host shim (reference cpp/inc entry points over the C ABI): g++, links against libdofs3d.so."""
+    deps = [HOST_SRC, OUT] + [os.path.join(HOST_INC, f) for f in os.listdir(HOST_INC)]
+    if not force and os.path.exists(HOST_OUT) and all(os.path.getmtime(d) <= os.path.getmtime(HOST_OUT) for d in deps):
+        return HOST_OUT
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-Wall", "-fPIC", "-shared", "-o", HOST_OUT, HOST_SRC,
+                           "-L" + HERE, "-ldofs3d", "-Wl,-rpath,$ORIGIN"])
+    return HOST_OUT
+
+
+def build_host_program(src, out):
+    """Compiles a C++ program against the shim headers and libraries (used by tests/ and the demo driver)."""
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-Wall", "-I" + HOST_INC, src, "-o", out, "-L" + HERE,
+                           "-ldofs3d_host", "-ldofs3d", "-Wl,-rpath," + HERE])
+    return out
+
+
 if __name__ == "__main__":
     build(force="--force" in sys.argv, verbose=True)
+    build_host(force="--force" in sys.argv)
     print(OUT)
+    print(HOST_OUT)

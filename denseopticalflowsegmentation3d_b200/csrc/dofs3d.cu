@@ -123,6 +123,9 @@ struct dofs3d_ctx {
     BorState bor;
     u32* win = nullptr;
     int* wave_start = nullptr;
+    uint2* long_list = nullptr;  // chains longer than REPLAY_SHORT events, per wave
+    int* long_count = nullptr;
+    int list_cap = 0;
     int* rsize = nullptr;
     ushort4* rbbox = nullptr;
     float2* rflow = nullptr;
@@ -132,7 +135,7 @@ struct dofs3d_ctx {
     Candidate* cand = nullptr;
     double* cand_score = nullptr;
     int cand_cap = 0, box_cap = 0;
-    int* counters = nullptr;    // [5][F]: n_cand, longest_chain, n_scored, n_boxes, n_roots
+    int* counters = nullptr;    // [6][F]: n_cand, longest_chain, n_scored, n_boxes, n_roots, final_root
     int* h_counters = nullptr;  // pinned mirror
     dofs3d_box *boxes_tmp = nullptr, *boxes = nullptr;
     int32_t* labels = nullptr;
@@ -262,7 +265,7 @@ int build_sorted_edges(dofs3d_ctx* ctx, int n) {
     return 0;
 }
 
-enum { CNT_CAND = 0, CNT_CHAIN = 1, CNT_SCORED = 2, CNT_BOXES = 3, CNT_ROOTS = 4, CNT_KINDS = 5 };
+enum { CNT_CAND = 0, CNT_CHAIN = 1, CNT_SCORED = 2, CNT_BOXES = 3, CNT_ROOTS = 4, CNT_FINAL = 5, CNT_KINDS = 6 };
 
 // get_segmented_array (segment.cpp:34-72) for n frames whose (unblurred or blurred) flow is at d_flow.
 int segment_dev(dofs3d_ctx* ctx, const float* d_flow, int already_blurred, int n) {
@@ -309,7 +312,7 @@ int segment_dev(dofs3d_ctx* ctx, const float* d_flow, int already_blurred, int n
         }
         if (done) break;
     }
-    LAUNCH(ctx, k_bor_finish, gN, SEG_THREADS, 0, B, N, levels);
+    LAUNCH(ctx, k_bor_finish, gN, SEG_THREADS, 0, B, N, levels, ctx->counters + CNT_FINAL * F);
     mark(ctx, "boruvka");
 
     // K9b events: winner of every loss, sorted by (wave, winner, time); buffers alias the edge keys
@@ -346,7 +349,14 @@ int segment_dev(dofs3d_ctx* ctx, const float* d_flow, int already_blurred, int n
     R.N = N;
     R.min_size = ctx->seg.min_size;
     R.eb = eb;
-    for (int wave = 1; wave <= levels; ++wave) LAUNCH(ctx, k_replay_wave, gN, SEG_THREADS, 0, R, wave);
+    R.long_list = ctx->long_list;
+    R.long_count = ctx->long_count;
+    R.list_cap = ctx->list_cap;
+    CK(cudaMemsetAsync(ctx->long_count, 0, sizeof(int) * (EV_MAX_WAVES + 1), ctx->stream));
+    for (int wave = 1; wave <= levels; ++wave) {
+        LAUNCH(ctx, k_replay_short, gN, SEG_THREADS, 0, R, wave);
+        LAUNCH(ctx, k_replay_long, dim3(148 * 4), 128, 0, R, wave);
+    }
     mark(ctx, "chain_replay");
 
     // K11 + K12 lifting, selection, boxes, labels
@@ -403,6 +413,7 @@ void fill_stats(dofs3d_ctx* ctx, int n, dofs3d_stats* out) {
         s.n_scored = ctx->h_counters[CNT_SCORED * F + f];
         s.n_boxes = ctx->h_counters[CNT_BOXES * F + f];
         s.longest_chain = ctx->h_counters[CNT_CHAIN * F + f];
+        s.final_root = ctx->h_counters[CNT_FINAL * F + f];
         out[f] = s;
     }
 }
@@ -571,6 +582,9 @@ int dofs3d_create(dofs3d_ctx** out, int device, int width, int height, int max_p
     DA(ctx->bor.lvl, F * N);
     DA(ctx->win, F * N);
     DA(ctx->wave_start, F * (EV_MAX_WAVES + 1));
+    ctx->list_cap = (int)std::min<size_t>(F * (N / REPLAY_SHORT + 1), (size_t)1 << 28);
+    DA(ctx->long_list, (size_t)ctx->list_cap);
+    DA(ctx->long_count, EV_MAX_WAVES + 1);
     DA(ctx->rsize, F * N);
     DA(ctx->rbbox, F * N);
     DA(ctx->rflow, F * N);

@@ -274,12 +274,15 @@ k_bor_relabel(BorState S, int N) {
 
 // final root: its level is the number of levels
 __global__ void __launch_bounds__(SEG_THREADS)
-k_bor_finish(BorState S, int N, int levels) {
+k_bor_finish(BorState S, int N, int levels, int* __restrict__ final_root) {
     const int frame = blockIdx.y;
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= N) return;
     const size_t g = (size_t)frame * N + p;
-    if (S.loss_time[g] == DOFS_INF32) S.lvl[g] = (u8)levels;
+    if (S.loss_time[g] == DOFS_INF32) {
+        S.lvl[g] = (u8)levels;
+        final_root[frame] = p;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -335,10 +338,22 @@ k_wave_starts(const u64* __restrict__ ev_key, int* __restrict__ wave_start /* [F
 }
 
 // ---------------------------------------------------------------------------------------------
-// K9c + K10  chain replay of one wave: thread per chain head.  Forest::merge (graph.cpp:170-218)
-// state update per absorbed root, then the size / row / move gates of Forest::new_merge
-// (graph.cpp:280-300); survivors are queued for lifting.
+// K9c + K10  chain replay of one wave.  Forest::merge (graph.cpp:170-218) state update per absorbed
+// root — size, bounding box, and the ORDER-DEPENDENT float mean flow — then the size / row / move
+// gates of Forest::new_merge (graph.cpp:280-300); survivors are queued for lifting.
+//
+// A chain = the events won by one root, in time order.  Chains of one wave are independent (every
+// absorbed root has a lower final rank, so its state is final).  Two kernels per wave:
+//   k_replay_short  one thread per chain of at most REPLAY_SHORT events; longer chains are pushed
+//                   to a work list
+//   k_replay_long   one warp per listed chain, 32 events at a time: the lanes gather the absorbed
+//                   roots' states together (coalesced event reads, 32 gathers in flight, next chunk
+//                   prefetched), sizes and boxes come from warp scans, and only the 3-operation
+//                   float/double recurrence of the mean flow runs serially, fed by shuffles; each
+//                   lane then applies the gates to "its" event.
 // ---------------------------------------------------------------------------------------------
+#define REPLAY_SHORT 32
+
 struct ReplayArgs {
     const u64* ev_key;     // [F][N] sorted
     const u32* ev_loser;   // [F][N] sorted payload
@@ -349,14 +364,40 @@ struct ReplayArgs {
     Candidate* cand;       // [F][cand_cap]
     int* n_cand;           // [F]
     int* longest_chain;    // [F]
+    uint2* long_list;      // [list_cap] (frame, index of the chain's first event)
+    int* long_count;       // [EV_MAX_WAVES + 1]
+    int list_cap;
     int cand_cap;
     int W, H, N;
     int min_size;
     EvBits eb;
 };
 
+// Forest::merge's size-weighted mean (graph.cpp:184-190) with OpenCV's Vec2f rounding:
+// Vec2f * int -> float products, float sum, Vec2f / int -> multiply by the double reciprocal.
+DOFS_D float merge_mean(float fa_times_sa, float f, float sb, double inv) {
+    return (float)xdmul((double)xfadd(fa_times_sa, xfmul(f, sb)), inv);
+}
+
+DOFS_D void push_candidate(const ReplayArgs& A, int frame, u32 root, u32 time, int size, float2 f, ushort4 bb) {
+    const int slot = atomicAdd(&A.n_cand[frame], 1);
+    if (slot >= A.cand_cap) return;
+    Candidate c;
+    c.root = root;
+    c.time = time;
+    c.size = size;
+    c.fx = f.x;
+    c.fy = f.y;
+    c.bbox[0] = bb.x;
+    c.bbox[1] = bb.y;
+    c.bbox[2] = bb.z;
+    c.bbox[3] = bb.w;
+    c.pad = 0;
+    A.cand[(size_t)frame * A.cand_cap + slot] = c;
+}
+
 __global__ void __launch_bounds__(SEG_THREADS)
-k_replay_wave(ReplayArgs A, int wave) {
+k_replay_short(ReplayArgs A, int wave) {
     const int frame = blockIdx.y;
     const int w0 = A.wave_start[frame * (EV_MAX_WAVES + 1) + wave];
     const int w1 = A.wave_start[frame * (EV_MAX_WAVES + 1) + wave + 1];
@@ -367,13 +408,18 @@ k_replay_wave(ReplayArgs A, int wave) {
     const u64 k0 = key[i];
     const u64 chain = ev_chain(k0, A.eb);  // wave | winner
     if (i > w0 && ev_chain(key[i - 1], A.eb) == chain) return;  // not the head of its chain
+    if (i + REPLAY_SHORT < w1 && ev_chain(key[i + REPLAY_SHORT], A.eb) == chain) {  // long chain: a warp takes it
+        const int slot = atomicAdd(&A.long_count[wave], 1);
+        if (slot < A.list_cap) A.long_list[slot] = make_uint2((u32)frame, (u32)i);
+        return;
+    }
     const u32 r = ev_winner(k0, A.eb);
     int s = A.rsize[fo + r];
     float2 f = A.rflow[fo + r];
     ushort4 bb = A.rbbox[fo + r];
     const int y = (int)r / A.W;
     const bool row_ok = !(y < A.H / 10);                                  // graph.cpp:288
-    const double move_min = xddiv((double)(3 * (y + 1)), (double)A.H);     // graph.cpp:296
+    const double move_min = xddiv((double)(3 * (y + 1)), (double)A.H);    // graph.cpp:296
     int j = i;
     u64 kj = k0;
     for (;;) {
@@ -381,13 +427,10 @@ k_replay_wave(ReplayArgs A, int wave) {
         const int sa = A.rsize[fo + a];
         const float2 fa = A.rflow[fo + a];
         const ushort4 ba = A.rbbox[fo + a];
-        // (flow_a * size_a + flow_b * size_b) / (size_a + size_b) with OpenCV's Vec2f rounding
         const float fsa = (float)sa, fsb = (float)s;
-        const float sx = xfadd(xfmul(fa.x, fsa), xfmul(f.x, fsb));
-        const float sy = xfadd(xfmul(fa.y, fsa), xfmul(f.y, fsb));
         const double inv = xddiv(1.0, (double)(sa + s));
-        f.x = (float)xdmul((double)sx, inv);
-        f.y = (float)xdmul((double)sy, inv);
+        f.x = merge_mean(xfmul(fa.x, fsa), f.x, fsb, inv);
+        f.y = merge_mean(xfmul(fa.y, fsa), f.y, fsb, inv);
         s += sa;
         bb.x = min(bb.x, ba.x);
         bb.y = min(bb.y, ba.y);
@@ -395,23 +438,7 @@ k_replay_wave(ReplayArgs A, int wave) {
         bb.w = max(bb.w, ba.w);
         if (s >= A.min_size && row_ok) {
             const double move = norm2d(f.x, f.y);
-            if (!(move < move_min)) {
-                int slot = atomicAdd(&A.n_cand[frame], 1);
-                if (slot < A.cand_cap) {
-                    Candidate c;
-                    c.root = r;
-                    c.time = ev_time(kj, A.eb);
-                    c.size = s;
-                    c.fx = f.x;
-                    c.fy = f.y;
-                    c.bbox[0] = bb.x;
-                    c.bbox[1] = bb.y;
-                    c.bbox[2] = bb.z;
-                    c.bbox[3] = bb.w;
-                    c.pad = 0;
-                    A.cand[(size_t)frame * A.cand_cap + slot] = c;
-                }
-            }
+            if (!(move < move_min)) push_candidate(A, frame, r, ev_time(kj, A.eb), s, f, bb);
         }
         ++j;
         if (j >= w1) break;
@@ -422,6 +449,125 @@ k_replay_wave(ReplayArgs A, int wave) {
     A.rflow[fo + r] = f;
     A.rbbox[fo + r] = bb;
     atomicMax(&A.longest_chain[frame], j - i);
+}
+
+struct ReplayOperand {
+    u64 key;
+    int sa;
+    float2 fa;
+    ushort4 ba;
+    bool valid;
+};
+
+DOFS_D ReplayOperand replay_load(const ReplayArgs& A, size_t fo, int j, int w1, u64 chain) {
+    ReplayOperand o;
+    o.valid = false;
+    o.key = 0;
+    o.sa = 0;
+    o.fa = make_float2(0.f, 0.f);
+    o.ba = make_ushort4(65535, 65535, 0, 0);
+    if (j < w1) {
+        o.key = A.ev_key[fo + j];
+        if (ev_chain(o.key, A.eb) == chain) {
+            const u32 a = A.ev_loser[fo + j];
+            o.valid = true;
+            o.sa = A.rsize[fo + a];
+            o.fa = A.rflow[fo + a];
+            o.ba = A.rbbox[fo + a];
+        }
+    }
+    return o;
+}
+
+__global__ void __launch_bounds__(128)
+k_replay_long(ReplayArgs A, int wave) {
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int n_warps = (gridDim.x * blockDim.x) >> 5;
+    const int n_list = min(A.long_count[wave], A.list_cap);
+    const unsigned FULL = 0xffffffffu;
+    for (int item = warp; item < n_list; item += n_warps) {
+        const uint2 it = A.long_list[item];
+        const int frame = (int)it.x, i0 = (int)it.y;
+        const size_t fo = (size_t)frame * A.N;
+        const int w1 = A.wave_start[frame * (EV_MAX_WAVES + 1) + wave + 1];
+        const u64 k0 = A.ev_key[fo + i0];
+        const u64 chain = ev_chain(k0, A.eb);
+        const u32 r = ev_winner(k0, A.eb);
+        int s = A.rsize[fo + r];
+        float2 f = A.rflow[fo + r];
+        ushort4 bb = A.rbbox[fo + r];
+        const int y = (int)r / A.W;
+        const bool row_ok = !(y < A.H / 10);
+        const double move_min = xddiv((double)(3 * (y + 1)), (double)A.H);
+        int j0 = i0;
+        ReplayOperand nxt = replay_load(A, fo, j0 + lane, w1, chain);
+        for (;;) {
+            const ReplayOperand cur = nxt;
+            nxt = replay_load(A, fo, j0 + 32 + lane, w1, chain);  // prefetch: these gathers overlap the serial part
+            const unsigned vmask = __ballot_sync(FULL, cur.valid);  // valid lanes are a prefix (events are sorted)
+            const int n_valid = __popc(vmask);
+            // sizes: inclusive scan
+            int s_inc = cur.sa;
+            ushort4 b_inc = cur.ba;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(FULL, s_inc, o);
+                const int bx = __shfl_up_sync(FULL, (int)b_inc.x, o), by = __shfl_up_sync(FULL, (int)b_inc.y, o);
+                const int bz = __shfl_up_sync(FULL, (int)b_inc.z, o), bw = __shfl_up_sync(FULL, (int)b_inc.w, o);
+                if (lane >= o) {
+                    s_inc += t;
+                    b_inc.x = min((int)b_inc.x, bx);
+                    b_inc.y = min((int)b_inc.y, by);
+                    b_inc.z = max((int)b_inc.z, bz);
+                    b_inc.w = max((int)b_inc.w, bw);
+                }
+            }
+            const int s_after = s + s_inc, s_before = s_after - cur.sa;
+            ushort4 bb_after;
+            bb_after.x = min(bb.x, b_inc.x);
+            bb_after.y = min(bb.y, b_inc.y);
+            bb_after.z = max(bb.z, b_inc.z);
+            bb_after.w = max(bb.w, b_inc.w);
+            const float fsa = (float)cur.sa;
+            const float ax = xfmul(cur.fa.x, fsa), ay = xfmul(cur.fa.y, fsa);
+            const float sb = (float)s_before;
+            const double inv = xddiv(1.0, (double)max(s_after, 1));
+            // the serial part: mean flow after each event, every lane runs the same recurrence
+            float2 mine = f;
+#pragma unroll 8
+            for (int k = 0; k < 32; ++k) {
+                const float kax = __shfl_sync(FULL, ax, k), kay = __shfl_sync(FULL, ay, k);
+                const float ksb = __shfl_sync(FULL, sb, k);
+                const double kinv = __shfl_sync(FULL, inv, k);
+                if (k < n_valid) {
+                    f.x = merge_mean(kax, f.x, ksb, kinv);
+                    f.y = merge_mean(kay, f.y, ksb, kinv);
+                }
+                if (k == lane) mine = f;
+            }
+            // gates of the event this lane holds
+            if (cur.valid && s_after >= A.min_size && row_ok) {
+                const double move = norm2d(mine.x, mine.y);
+                if (!(move < move_min)) push_candidate(A, frame, r, ev_time(cur.key, A.eb), s_after, mine, bb_after);
+            }
+            // carry to the next chunk = state after the last valid event
+            const int last = max(n_valid - 1, 0);
+            s = __shfl_sync(FULL, s_after, last);
+            bb.x = (u16)__shfl_sync(FULL, (int)bb_after.x, last);
+            bb.y = (u16)__shfl_sync(FULL, (int)bb_after.y, last);
+            bb.z = (u16)__shfl_sync(FULL, (int)bb_after.z, last);
+            bb.w = (u16)__shfl_sync(FULL, (int)bb_after.w, last);
+            j0 += n_valid;
+            if (n_valid < 32) break;
+        }
+        if (lane == 0) {
+            A.rsize[fo + r] = s;
+            A.rflow[fo + r] = f;
+            A.rbbox[fo + r] = bb;
+            atomicMax(&A.longest_chain[frame], j0 - i0);
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -85,7 +85,7 @@ typedef struct {
     int32_t n_scored;      /* ... of those with a valid rectangle that passed convexity and score gates */
     int32_t n_boxes;       /* history entries (roots with a kept snapshot) */
     int32_t longest_chain; /* longest run of merges won by one root (serial depth of the replay) */
-    int32_t pad_;
+    int32_t final_root;    /* root id of the single set the forest ends as (Forest::find of any pixel) */
 } dofs3d_stats;
 
 /* Fills *p with the reference's constants (homographies from get_mat/get_mat_upper, etc.). */

@@ -63,3 +63,16 @@ def test_bad_arguments_rejected():
     assert L.dofs3d_create(ctypes.byref(h), 0, 1, 1, 1, None) == -1  # DOFS3D_ERR_ARG
     assert L.dofs3d_create(None, 0, 64, 64, 1, None) == -1
     assert L.dofs3d_sync(None) == -1
+
+
+def test_host_shim_builds_and_fails_loudly_without_gpu(tmp_path):
+    """The C++ drop-in (reference cpp/inc signatures) compiles against the C ABI; without a GPU it throws."""
+    import subprocess
+    import torch
+    from denseopticalflowsegmentation3d_b200 import build as b
+    b.build_host()
+    exe = b.build_host_program(os.path.join(ROOT, "tests", "cpp", "test_host_shim.cpp"), str(tmp_path / "shim_test"))
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode != 0 and "no CPU fallback" in r.stderr

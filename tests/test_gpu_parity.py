@@ -361,3 +361,35 @@ def test_full_size_1080p_properties_and_oracle(dofs, port):
     res = port.segment(out["flow_blurred"][0], persp, inv, up)
     compare_boxes(boxes, psets, res["entries"], W)
     assert st["n_candidates"] == res["counters"]["get_score"]
+
+
+def test_cpp_host_shim_matches_oracle(dofs, port, golden_pair, tmp_path):
+    """The C++ drop-in headers (graph.hpp / lifting_3d.hpp / segment.hpp of the shim) driven like the reference's
+    main() and gtest: tests/cpp/test_host_shim.cpp prints one line per kept segment; compare with the oracle."""
+    import os
+    import subprocess
+    from denseopticalflowsegmentation3d_b200 import build as b
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    b.build_host()
+    exe = b.build_host_program(os.path.join(root, "tests", "cpp", "test_host_shim.cpp"), str(tmp_path / "shim_test"))
+    flow = golden_pair["flow"]
+    H, W = flow.shape[:2]
+    raw = tmp_path / "flow.bin"
+    flow.tofile(raw)
+    r = subprocess.run([exe, str(raw), str(W), str(H)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr + r.stdout
+    lines = [l for l in r.stdout.splitlines() if l.startswith("segment ")]
+    # oracle on the device-blurred field (the shim blurs on the device, like get_segmented_array blurs with OpenCV)
+    with dofs.Context(W, H) as c:
+        fb = c.blur(flow)[0]
+    persp, inv, up = port.get_mats()
+    ents = port.segment(fb, persp, inv, up)["entries"]
+    assert len(lines) == len(ents) > 0
+    for line, e in zip(lines, ents):
+        kv = dict(t.split("=") for t in line.split()[1:])
+        assert int(kv["root"]) == e["root"] and int(kv["size"]) == e["size"] and int(kv["cls"]) == e["sol"]["cls"]
+        h = 0
+        for px in e["pixels"].tolist():
+            h = (h * 1000003 + px) % 2147483647
+        assert int(kv["hash"]) == h
+        assert abs(float(kv["score"]) - e["score"]) <= TOL_ERR and abs(float(kv["orient"]) - e["sol"]["orient"]) <= TOL_YAW
