@@ -136,11 +136,12 @@ struct dofs3d_ctx {
     double* cand_score = nullptr;
     int cand_cap = 0, box_cap = 0;
     int* counters = nullptr;    // [6][F]: n_cand, longest_chain, n_scored, n_boxes, n_roots, final_root
-    int* h_counters = nullptr;  // pinned mirror
+    dofs3d_stats* h_stats = nullptr;  // pinned copy of the stats of the last call
+    int max_levels = 0;               // guaranteed bound of Boruvka levels for this frame size
+    int pending_pairs = 0, pending_max_boxes = -1;  // last asynchronous call, validated by dofs3d_sync
     dofs3d_box *boxes_tmp = nullptr, *boxes = nullptr;
     int32_t* labels = nullptr;
     dofs3d_stats* stats = nullptr;
-    std::vector<int> levels_of_frame;
 
     // flow buffers
     FlowBuffers fb;
@@ -183,6 +184,12 @@ int dalloc(dofs3d_ctx* ctx, T** p, size_t count) {
     } while (0)
 
 inline dim3 grid1(size_t n, int threads, int frames) { return dim3((unsigned)((n + threads - 1) / threads), frames); }
+// small fixed grid for the grid-stride kernels: about 16 blocks per SM over the whole batch
+inline dim3 grid_stride(const dofs3d_ctx* ctx, int frames) {
+    const unsigned total = 148u * 16u;
+    const unsigned per_frame = std::max(1u, std::min(total / (unsigned)frames, (unsigned)((ctx->N + SEG_THREADS - 1) / SEG_THREADS)));
+    return dim3(per_frame, frames);
+}
 
 void mark(dofs3d_ctx* ctx, const char* name) {
     if (!ctx->timer.enabled) return;
@@ -282,37 +289,20 @@ int segment_dev(dofs3d_ctx* ctx, const float* d_flow, int already_blurred, int n
     int rc = build_sorted_edges(ctx, n);
     if (rc) return rc;
 
-    // K9a Boruvka levels (== union-by-rank ranks)
+    // K9a Boruvka levels (== union-by-rank ranks): the guaranteed bound of levels is enqueued, finished frames skip
     BorState& B = ctx->bor;
-    LAUNCH(ctx, k_bor_init, gN, SEG_THREADS, 0, B, ctx->flow_blur, ctx->rsize, ctx->rbbox, ctx->rflow, ctx->best_score,
+    const dim3 gS = grid_stride(ctx, n);
+    LAUNCH(ctx, k_bor_init, gS, SEG_THREADS, 0, B, ctx->flow_blur, ctx->rsize, ctx->rbbox, ctx->rflow, ctx->best_score,
            ctx->sel_time, ctx->sel_box, W, N);
     CK(cudaMemsetAsync(ctx->counters, 0, sizeof(int) * CNT_KINDS * F, ctx->stream));
-    ctx->levels_of_frame.assign(n, 0);
-    int levels = 0;
-    for (;;) {
-        if (levels >= EV_MAX_WAVES - 2) {
-            ctx->err = "internal: Boruvka did not converge";
-            return DOFS3D_ERR_INTERNAL;
-        }
-        CK(cudaMemsetAsync(ctx->counters + CNT_ROOTS * F, 0, sizeof(int) * F, ctx->stream));
-        LAUNCH(ctx, k_bor_pixel, gN, SEG_THREADS, 0, B, ctx->valsB, ctx->S, W, N);
-        LAUNCH(ctx, k_bor_root, gN, SEG_THREADS, 0, B, ctx->valsA, ctx->S, W, N, levels);
-        LAUNCH(ctx, k_bor_relabel, gN, SEG_THREADS, 0, B, N);
-        ++levels;
-        CK(cudaMemcpyAsync(ctx->h_counters + CNT_ROOTS * F, ctx->counters + CNT_ROOTS * F, sizeof(int) * n,
-                           cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
-        bool done = true;
-        for (int f = 0; f < n; ++f) {
-            if (ctx->h_counters[CNT_ROOTS * F + f] == 1) {
-                if (ctx->levels_of_frame[f] == 0) ctx->levels_of_frame[f] = levels;
-            } else {
-                done = false;
-            }
-        }
-        if (done) break;
+    CK(cudaMemsetAsync(B.n_roots, 0, sizeof(int) * EV_MAX_WAVES * F, ctx->stream));
+    const int levels = ctx->max_levels;
+    for (int level = 0; level < levels; ++level) {
+        LAUNCH(ctx, k_bor_pixel, gS, SEG_THREADS, 0, B, ctx->valsB, ctx->S, W, N, level);
+        LAUNCH(ctx, k_bor_root, gS, SEG_THREADS, 0, B, ctx->valsA, ctx->S, W, N, level);
+        LAUNCH(ctx, k_bor_relabel, gS, SEG_THREADS, 0, B, N, level);
     }
-    LAUNCH(ctx, k_bor_finish, gN, SEG_THREADS, 0, B, N, levels, ctx->counters + CNT_FINAL * F);
+    LAUNCH(ctx, k_bor_finish, gS, SEG_THREADS, 0, B, N, levels);
     mark(ctx, "boruvka");
 
     // K9b events: winner of every loss, sorted by (wave, winner, time); buffers alias the edge keys
@@ -323,13 +313,13 @@ int segment_dev(dofs3d_ctx* ctx, const float* d_flow, int already_blurred, int n
     u64* evB = ctx->keysB;
     u32* evlA = reinterpret_cast<u32*>(ctx->keysA + (size_t)F * N);  // losers, after the F*N keys
     u32* evlB = reinterpret_cast<u32*>(ctx->keysB + (size_t)F * N);
-    LAUNCH(ctx, k_event_keys, gN, SEG_THREADS, 0, B, ctx->win, evA, N, eb);
+    LAUNCH(ctx, k_event_keys, gS, SEG_THREADS, 0, B, ctx->win, evA, N, eb);
     mark(ctx, "event_keys");
     int side = radix_sort(ctx, evA, evlA, evB, evlB, (size_t)N, N, n, eb.tb + eb.wb + 5, true, "event_sort.hist",
                           "event_sort.scan", "event_sort.scatter");
     const u64* ev_key = side ? evB : evA;
     const u32* ev_loser = side ? evlB : evlA;
-    LAUNCH(ctx, k_wave_starts, gN, SEG_THREADS, 0, ev_key, ctx->wave_start, N, eb);
+    LAUNCH(ctx, k_wave_starts, gS, SEG_THREADS, 0, ev_key, ctx->wave_start, N, eb);
     mark(ctx, "event_waves");
 
     // K9c + K10 chain replay, wave by wave
@@ -354,8 +344,8 @@ int segment_dev(dofs3d_ctx* ctx, const float* d_flow, int already_blurred, int n
     R.list_cap = ctx->list_cap;
     CK(cudaMemsetAsync(ctx->long_count, 0, sizeof(int) * (EV_MAX_WAVES + 1), ctx->stream));
     for (int wave = 1; wave <= levels; ++wave) {
-        LAUNCH(ctx, k_replay_short, gN, SEG_THREADS, 0, R, wave);
-        LAUNCH(ctx, k_replay_long, dim3(148 * 4), 128, 0, R, wave);
+        LAUNCH(ctx, k_replay_short, gS, SEG_THREADS, 0, R, wave);
+        LAUNCH(ctx, k_replay_long, dim3(148 * 4), 32 * REPLAY_WARPS, 0, R, wave);
     }
     mark(ctx, "chain_replay");
 
@@ -385,40 +375,35 @@ int segment_dev(dofs3d_ctx* ctx, const float* d_flow, int already_blurred, int n
     LAUNCH(ctx, k_labels, gN, SEG_THREADS, 0, ctx->labels, B.loss_time, ctx->win, ctx->sel_time, ctx->sel_box, N);
     mark(ctx, "labels");
 
-    // counters -> stats (host knows n_levels)
-    CK(cudaMemcpyAsync(ctx->h_counters, ctx->counters, sizeof(int) * CNT_KINDS * F, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    // counters -> stats record, on the device; a copy lands in pinned host memory for the host-pointer entry points
+    LAUNCH(ctx, k_stats<dofs3d_stats>, dim3((n + 63) / 64), 64, 0, ctx->stats, B, ctx->counters + CNT_CAND * F,
+           ctx->counters + CNT_SCORED * F, ctx->counters + CNT_BOXES * F, ctx->counters + CNT_CHAIN * F, n, N,
+           n_edges_of(W, H, ctx->seg.neighbors), levels);
+    CK(cudaMemcpyAsync(ctx->h_stats, ctx->stats, sizeof(dofs3d_stats) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    return 0;
+}
+
+// after a stream synchronisation: did every frame of the last call fit the queues / converge?
+int check_last_call(dofs3d_ctx* ctx, int n, int max_boxes) {
     for (int f = 0; f < n; ++f) {
-        if (ctx->h_counters[CNT_CAND * F + f] > ctx->cand_cap) {
+        const dofs3d_stats& st = ctx->h_stats[f];
+        if (st.final_root < 0) {
+            ctx->err = "internal: Boruvka did not converge";
+            return DOFS3D_ERR_INTERNAL;
+        }
+        if (st.n_candidates > ctx->cand_cap) {
             ctx->err = "candidate queue overflow";
             return DOFS3D_ERR_OVERFLOW;
         }
-        if (ctx->h_counters[CNT_BOXES * F + f] > ctx->box_cap) {
-            ctx->err = "box list overflow";
+        if (st.n_boxes > ctx->box_cap || (max_boxes >= 0 && st.n_boxes > max_boxes)) {
+            ctx->err = "more boxes than max_boxes";
             return DOFS3D_ERR_OVERFLOW;
         }
     }
     return 0;
 }
 
-void fill_stats(dofs3d_ctx* ctx, int n, dofs3d_stats* out) {
-    const int F = ctx->F;
-    for (int f = 0; f < n; ++f) {
-        dofs3d_stats s;
-        memset(&s, 0, sizeof s);
-        s.n_edges = n_edges_of(ctx->W, ctx->H, ctx->seg.neighbors);
-        s.n_merges = ctx->N - ctx->h_counters[CNT_ROOTS * F + f];
-        s.n_levels = ctx->levels_of_frame[f];
-        s.n_candidates = ctx->h_counters[CNT_CAND * F + f];
-        s.n_scored = ctx->h_counters[CNT_SCORED * F + f];
-        s.n_boxes = ctx->h_counters[CNT_BOXES * F + f];
-        s.longest_chain = ctx->h_counters[CNT_CHAIN * F + f];
-        s.final_root = ctx->h_counters[CNT_FINAL * F + f];
-        out[f] = s;
-    }
-}
-
-// copy results of the last segment_dev to caller memory (kind = cudaMemcpyDeviceToHost / DeviceToDevice)
+// copy results of the last segment_dev to caller memory (kind = cudaMemcpyDeviceToHost / DeviceToDevice); asynchronous
 int export_results(dofs3d_ctx* ctx, int n, int32_t* labels_out, dofs3d_box* boxes_out, int32_t* n_boxes_out,
                    int max_boxes, dofs3d_stats* stats_out, cudaMemcpyKind kind) {
     const int F = ctx->F;
@@ -430,30 +415,9 @@ int export_results(dofs3d_ctx* ctx, int n, int32_t* labels_out, dofs3d_box* boxe
                              (size_t)ctx->box_cap * sizeof(dofs3d_box), (size_t)cols * sizeof(dofs3d_box), n, kind,
                              ctx->stream));
     }
-    std::vector<dofs3d_stats> st(n);
-    fill_stats(ctx, n, st.data());
-    if (kind == cudaMemcpyDeviceToHost) {
-        if (n_boxes_out)
-            for (int f = 0; f < n; ++f) n_boxes_out[f] = ctx->h_counters[CNT_BOXES * F + f];
-        if (stats_out) memcpy(stats_out, st.data(), sizeof(dofs3d_stats) * n);
-    } else {
-        if (n_boxes_out)
-            CK(cudaMemcpyAsync(n_boxes_out, ctx->counters + CNT_BOXES * F, sizeof(int) * n, cudaMemcpyDeviceToDevice,
-                               ctx->stream));
-        if (stats_out) {
-            CK(cudaMemcpyAsync(ctx->stats, st.data(), sizeof(dofs3d_stats) * n, cudaMemcpyHostToDevice, ctx->stream));
-            CK(cudaMemcpyAsync(stats_out, ctx->stats, sizeof(dofs3d_stats) * n, cudaMemcpyDeviceToDevice, ctx->stream));
-            CK(cudaStreamSynchronize(ctx->stream));  // st goes out of scope
-        }
-    }
-    if (boxes_out) {
-        for (int f = 0; f < n; ++f)
-            if (ctx->h_counters[CNT_BOXES * F + f] > max_boxes) {
-                CK(cudaStreamSynchronize(ctx->stream));
-                ctx->err = "more boxes than max_boxes";
-                return DOFS3D_ERR_OVERFLOW;
-            }
-    }
+    if (n_boxes_out)
+        CK(cudaMemcpyAsync(n_boxes_out, ctx->counters + CNT_BOXES * F, sizeof(int) * n, kind, ctx->stream));
+    if (stats_out) CK(cudaMemcpyAsync(stats_out, ctx->stats, sizeof(dofs3d_stats) * n, kind, ctx->stream));
     return 0;
 }
 
@@ -596,8 +560,12 @@ int dofs3d_create(dofs3d_ctx** out, int device, int width, int height, int max_p
     DA(ctx->cand, F * ctx->cand_cap);
     DA(ctx->cand_score, F * ctx->cand_cap);
     DA(ctx->counters, (size_t)CNT_KINDS * F);
-    ctx->bor.n_roots = ctx->counters + CNT_ROOTS * F;
-    CK(cudaMallocHost(&ctx->h_counters, sizeof(int) * CNT_KINDS * F));
+    DA(ctx->bor.n_roots, (size_t)EV_MAX_WAVES * F);
+    DA(ctx->bor.levels, F);
+    ctx->bor.final_root = ctx->counters + CNT_FINAL * F;
+    ctx->bor.F = (int)F;
+    ctx->max_levels = std::min(EV_MAX_WAVES - 2, ceil_log2((unsigned long long)N) + 1);  // components at least halve per level
+    CK(cudaMallocHost(&ctx->h_stats, sizeof(dofs3d_stats) * F));
     DA(ctx->boxes_tmp, F * ctx->box_cap);
     DA(ctx->boxes, F * ctx->box_cap);
     DA(ctx->labels, F * N);
@@ -640,7 +608,7 @@ void dofs3d_destroy(dofs3d_ctx* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (void* p : ctx->allocs) cudaFree(p);
     farneback_free(&ctx->fb);
-    if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
+    if (ctx->h_stats) cudaFreeHost(ctx->h_stats);
     for (auto& m : ctx->timer.marks) cudaEventDestroy(m.second);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -649,6 +617,11 @@ void dofs3d_destroy(dofs3d_ctx* ctx) {
 int dofs3d_sync(dofs3d_ctx* ctx) {
     if (!ctx) return DOFS3D_ERR_ARG;
     CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->pending_pairs > 0) {  // an asynchronous segment/process call has finished: report overflow / non-convergence
+        const int n = ctx->pending_pairs;
+        ctx->pending_pairs = 0;
+        return check_last_call(ctx, n, ctx->pending_max_boxes);
+    }
     return 0;
 }
 
@@ -766,6 +739,8 @@ int dofs3d_segment_dev(dofs3d_ctx* ctx, const float* d_flow, int already_blurred
     rc = export_results(ctx, n_pairs, d_labels_out, d_boxes_out, d_n_boxes_out, max_boxes, d_stats_out,
                         cudaMemcpyDeviceToDevice);
     CK(cudaGetLastError());
+    ctx->pending_pairs = n_pairs;
+    ctx->pending_max_boxes = d_boxes_out ? max_boxes : -1;
     timer_collect(ctx);
     return rc;
 }
@@ -788,7 +763,7 @@ int dofs3d_segment(dofs3d_ctx* ctx, const float* flow, int already_blurred, int 
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaGetLastError());
     timer_collect(ctx);
-    return rc;
+    return check_last_call(ctx, n_pairs, boxes_out ? max_boxes : -1);
 }
 
 // ------------------------------------------------------------------------------------- lift
@@ -874,6 +849,8 @@ int dofs3d_process_dev(dofs3d_ctx* ctx, const uint8_t* d_bgr_frames, int n_frame
     if (rc) return rc;
     rc = export_results(ctx, n, d_labels_out, d_boxes_out, d_n_boxes_out, max_boxes, d_stats_out, cudaMemcpyDeviceToDevice);
     CK(cudaGetLastError());
+    ctx->pending_pairs = n;
+    ctx->pending_max_boxes = d_boxes_out ? max_boxes : -1;
     timer_collect(ctx);
     return rc;
 }
@@ -896,10 +873,11 @@ int dofs3d_process(dofs3d_ctx* ctx, const uint8_t* bgr_frames, int n_frames, int
     rc = segment_dev(ctx, reinterpret_cast<const float*>(ctx->flow_raw), 0, n);
     if (rc) return rc;
     rc = export_results(ctx, n, labels_out, boxes_out, n_boxes_out, max_boxes, stats_out, cudaMemcpyDeviceToHost);
+    if (rc) return rc;
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaGetLastError());
     timer_collect(ctx);
-    return rc;
+    return check_last_call(ctx, n, boxes_out ? max_boxes : -1);
 }
 
 // ------------------------------------------------------------------------------------- synthetic video

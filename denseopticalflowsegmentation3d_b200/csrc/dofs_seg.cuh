@@ -159,7 +159,10 @@ k_edges_decode(const u32* __restrict__ sorted_seq, int* __restrict__ start, int*
 }
 
 // ---------------------------------------------------------------------------------------------
-// K9a  Boruvka levels
+// K9a  Boruvka levels.  No host round trip: the host enqueues the guaranteed bound of levels
+// (components at least halve per level) and every kernel of a level returns at once for a frame that
+// is already one component.  Kernels are grid-stride with a small fixed grid, so a level that has
+// nothing left to do costs a few microseconds.
 // ---------------------------------------------------------------------------------------------
 struct BorState {
     u32* comp;       // [F][N] current component root of each pixel
@@ -168,120 +171,148 @@ struct BorState {
     u32* loss_time;  // [F][N] per root id: sorted position of the edge at which it loses (INF: never)
     u32* up;         // [F][N] per root id: root of the next-level component it is contracted into
     u8* lvl;         // [F][N] per root id: level at which it loses == its final union-find rank
-    int* n_roots;    // [F] number of roots after the current level
+    int* n_roots;    // [EV_MAX_WAVES][F] number of roots after each level (zeroed per call)
+    int* levels;     // [F] number of levels the frame needed (written by k_bor_finish)
+    int* final_root; // [F]
+    int F;
 };
+
+#define EV_MAX_WAVES 32
+
+DOFS_D bool bor_done(const BorState& S, int level, int frame) {
+    return level > 0 && S.n_roots[(level - 1) * S.F + frame] == 1;
+}
+
+#define GRID_STRIDE(p, N) for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < (N); p += gridDim.x * blockDim.x)
 
 __global__ void __launch_bounds__(SEG_THREADS)
 k_bor_init(BorState S, const float2* __restrict__ flow, int* __restrict__ rsize, ushort4* __restrict__ rbbox,
            float2* __restrict__ rflow, u64* __restrict__ best_score, u32* __restrict__ sel_time,
            int* __restrict__ sel_box, int W, int N) {
     const int frame = blockIdx.y;
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= N) return;
-    const size_t g = (size_t)frame * N + p;
-    S.comp[g] = (u32)p;
-    S.best[g] = DOFS_INF32;
-    S.newp[g] = (u32)p;
-    S.loss_time[g] = DOFS_INF32;
-    S.up[g] = (u32)p;
-    S.lvl[g] = 0;
-    // Forest::Forest (graph.cpp:129-148): singleton sets
-    rsize[g] = 1;
-    const int y = p / W, x = p - y * W;
-    rbbox[g] = make_ushort4((u16)x, (u16)y, (u16)x, (u16)y);
-    rflow[g] = flow[g];
-    best_score[g] = 0ull;
-    sel_time[g] = DOFS_INF32;
-    sel_box[g] = -1;
+    GRID_STRIDE(p, N) {
+        const size_t g = (size_t)frame * N + p;
+        S.comp[g] = (u32)p;
+        S.best[g] = DOFS_INF32;
+        S.newp[g] = (u32)p;
+        S.loss_time[g] = DOFS_INF32;
+        S.up[g] = (u32)p;
+        S.lvl[g] = 0;
+        // Forest::Forest (graph.cpp:129-148): singleton sets
+        rsize[g] = 1;
+        const int y = p / W, x = p - y * W;
+        rbbox[g] = make_ushort4((u16)x, (u16)y, (u16)x, (u16)y);
+        rflow[g] = flow[g];
+        best_score[g] = 0ull;
+        sel_time[g] = DOFS_INF32;
+        sel_box[g] = -1;
+    }
 }
 
 // every edge whose endpoints are in different components offers its rank to both components
 __global__ void __launch_bounds__(SEG_THREADS)
-k_bor_pixel(BorState S, const u32* __restrict__ rank, size_t rank_stride, int W, int N) {
+k_bor_pixel(BorState S, const u32* __restrict__ rank, size_t rank_stride, int W, int N, int level) {
     const int frame = blockIdx.y;
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= N) return;
+    if (bor_done(S, level, frame)) return;
     const u32* comp = S.comp + (size_t)frame * N;
     u32* best = S.best + (size_t)frame * N;
-    const uint4 r4 = *reinterpret_cast<const uint4*>(rank + (size_t)frame * rank_stride + 4 * (size_t)p);
-    const u32 r[4] = {r4.x, r4.y, r4.z, r4.w};
-    const u32 cp = comp[p];
-    u32 mine = DOFS_INF32;
+    GRID_STRIDE(p, N) {
+        const uint4 r4 = *reinterpret_cast<const uint4*>(rank + (size_t)frame * rank_stride + 4 * (size_t)p);
+        const u32 r[4] = {r4.x, r4.y, r4.z, r4.w};
+        const u32 cp = comp[p];
+        u32 mine = DOFS_INF32;
 #pragma unroll
-    for (int d = 0; d < 4; ++d) {
-        if (r[d] != DOFS_INF32) {
-            u32 cq = comp[edge_other(p, d, W)];
-            if (cq != cp) {
-                mine = min(mine, r[d]);
-                if (r[d] < best[cq]) atomicMin(&best[cq], r[d]);  // best only decreases: a stale read is safe
+        for (int d = 0; d < 4; ++d) {
+            if (r[d] != DOFS_INF32) {
+                u32 cq = comp[edge_other(p, d, W)];
+                if (cq != cp) {
+                    mine = min(mine, r[d]);
+                    if (r[d] < best[cq]) atomicMin(&best[cq], r[d]);  // best only decreases: a stale read is safe
+                }
             }
         }
+        if (mine != DOFS_INF32 && mine < best[cp]) atomicMin(&best[cp], mine);
     }
-    if (mine != DOFS_INF32 && mine < best[cp]) atomicMin(&best[cp], mine);
 }
 
 // per root: classify its pick (mutual winner / loser), record the loss
 __global__ void __launch_bounds__(SEG_THREADS)
 k_bor_root(BorState S, const u32* __restrict__ sorted_seq, size_t seq_stride, int W, int N, int level) {
     const int frame = blockIdx.y;
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= N) return;
+    if (bor_done(S, level, frame)) return;
     const size_t fo = (size_t)frame * N;
     const u32* comp = S.comp + fo;
-    if (comp[c] != (u32)c) return;
-    const u32 t = S.best[fo + c];
-    if (t == DOFS_INF32) {  // the last component
-        S.newp[fo + c] = (u32)c;
-        return;
-    }
-    const u32 seq = sorted_seq[(size_t)frame * seq_stride + t];
-    const int s = (int)(seq >> 2);
-    const int e = edge_other(s, (int)(seq & 3u), W);
-    const u32 cs = comp[s], ce = comp[e];
-    const u32 other = (cs == (u32)c) ? ce : cs;
-    const bool mutual = S.best[fo + other] == t;
-    if (mutual && ce == (u32)c) {
-        S.newp[fo + c] = (u32)c;  // rank tie: the `end` side survives (graph.cpp:177-182, 210-213)
-    } else {
-        S.newp[fo + c] = other;
-        S.loss_time[fo + c] = t;
-        S.lvl[fo + c] = (u8)level;
+    GRID_STRIDE(c, N) {
+        if (comp[c] != (u32)c) continue;
+        const u32 t = S.best[fo + c];
+        if (t == DOFS_INF32) {  // the last component
+            S.newp[fo + c] = (u32)c;
+            continue;
+        }
+        const u32 seq = sorted_seq[(size_t)frame * seq_stride + t];
+        const int s = (int)(seq >> 2);
+        const int e = edge_other(s, (int)(seq & 3u), W);
+        const u32 cs = comp[s], ce = comp[e];
+        const u32 other = (cs == (u32)c) ? ce : cs;
+        const bool mutual = S.best[fo + other] == t;
+        if (mutual && ce == (u32)c) {
+            S.newp[fo + c] = (u32)c;  // rank tie: the `end` side survives (graph.cpp:177-182, 210-213)
+        } else {
+            S.newp[fo + c] = other;
+            S.loss_time[fo + c] = t;
+            S.lvl[fo + c] = (u8)level;
+        }
     }
 }
 
 // contract: every pixel follows the hooks to the group root; losers remember it in `up`
 __global__ void __launch_bounds__(SEG_THREADS)
-k_bor_relabel(BorState S, int N) {
+k_bor_relabel(BorState S, int N, int level) {
     const int frame = blockIdx.y;
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= N) return;
+    if (bor_done(S, level, frame)) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) S.n_roots[level * S.F + frame] = 1;
+        return;
+    }
     const size_t fo = (size_t)frame * N;
-    const u32 c = S.comp[fo + p];
     const volatile u32* newp = S.newp + fo;
-    u32 g = c;
-    for (;;) {
-        u32 nx = newp[g];
-        if (nx == g) break;
-        g = nx;
+    int roots = 0;
+    GRID_STRIDE(p, N) {
+        const u32 c = S.comp[fo + p];
+        u32 g = c;
+        for (;;) {
+            u32 nx = newp[g];
+            if (nx == g) break;
+            g = nx;
+        }
+        if (c == (u32)p) {  // p was a root in this level
+            S.best[fo + p] = DOFS_INF32;
+            if (g != (u32)p) S.up[fo + p] = g;
+            else ++roots;
+        }
+        if (g != c) S.comp[fo + p] = g;
     }
-    if (c == (u32)p) {  // p was a root in this level
-        S.best[fo + p] = DOFS_INF32;
-        if (g != (u32)p) S.up[fo + p] = g;
-        else atomicAdd(&S.n_roots[frame], 1);
-    }
-    if (g != c) S.comp[fo + p] = g;
+    // one atomic per warp
+    for (int o = 16; o > 0; o >>= 1) roots += __shfl_down_sync(0xffffffffu, roots, o);
+    if ((threadIdx.x & 31) == 0 && roots) atomicAdd(&S.n_roots[level * S.F + frame], roots);
 }
 
-// final root: its level is the number of levels
+// final root: it loses never; its chain is replayed in the last wave
 __global__ void __launch_bounds__(SEG_THREADS)
-k_bor_finish(BorState S, int N, int levels, int* __restrict__ final_root) {
+k_bor_finish(BorState S, int N, int max_levels) {
     const int frame = blockIdx.y;
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= N) return;
-    const size_t g = (size_t)frame * N + p;
-    if (S.loss_time[g] == DOFS_INF32) {
-        S.lvl[g] = (u8)levels;
-        final_root[frame] = p;
+    int levels = max_levels;
+    for (int l = 0; l < max_levels; ++l)
+        if (S.n_roots[l * S.F + frame] == 1) {
+            levels = l + 1;
+            break;
+        }
+    GRID_STRIDE(p, N) {
+        const size_t g = (size_t)frame * N + p;
+        if (S.loss_time[g] == DOFS_INF32) {
+            S.lvl[g] = (u8)max_levels;  // every frame's last chain runs in the same (last) wave, side by side
+            S.final_root[frame] = p;  // if the frame did not converge several pixels land here; n_roots says so
+            S.levels[frame] = levels;
+        }
     }
 }
 
@@ -292,7 +323,6 @@ k_bor_finish(BorState S, int N, int levels, int* __restrict__ final_root) {
 //      passes as the frame size allows (1080p: 23 + 21 + 5 = 49 bits -> 7 passes instead of 8)
 // ---------------------------------------------------------------------------------------------
 #define EV_KEY_NONE 0xFFFFFFFFFFFFFFFFull
-#define EV_MAX_WAVES 32
 
 struct EvBits {
     int tb, wb;
@@ -305,19 +335,19 @@ DOFS_D int ev_wave(u64 key, EvBits b) { return key == EV_KEY_NONE ? EV_MAX_WAVES
 __global__ void __launch_bounds__(SEG_THREADS)
 k_event_keys(BorState S, u32* __restrict__ win, u64* __restrict__ ev_key, int N, EvBits eb) {
     const int frame = blockIdx.y;
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= N) return;
     const size_t fo = (size_t)frame * N;
-    const u32 t = S.loss_time[fo + c];
-    if (t == DOFS_INF32) {
-        win[fo + c] = (u32)c;
-        ev_key[fo + c] = EV_KEY_NONE;
-        return;
+    GRID_STRIDE(c, N) {
+        const u32 t = S.loss_time[fo + c];
+        if (t == DOFS_INF32) {
+            win[fo + c] = (u32)c;
+            ev_key[fo + c] = EV_KEY_NONE;
+            continue;
+        }
+        u32 cur = S.up[fo + c];
+        while (S.loss_time[fo + cur] < t) cur = S.up[fo + cur];
+        win[fo + c] = cur;
+        ev_key[fo + c] = ((u64)S.lvl[fo + cur] << (eb.tb + eb.wb)) | ((u64)cur << eb.tb) | (u64)t;
     }
-    u32 cur = S.up[fo + c];
-    while (S.loss_time[fo + cur] < t) cur = S.up[fo + cur];
-    win[fo + c] = cur;
-    ev_key[fo + c] = ((u64)S.lvl[fo + cur] << (eb.tb + eb.wb)) | ((u64)cur << eb.tb) | (u64)t;
 }
 
 // first event index of every wave (events are sorted by key)
@@ -325,16 +355,16 @@ __global__ void __launch_bounds__(SEG_THREADS)
 k_wave_starts(const u64* __restrict__ ev_key, int* __restrict__ wave_start /* [F][EV_MAX_WAVES+1] */, int N,
               EvBits eb) {
     const int frame = blockIdx.y;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= N) return;
     const u64* k = ev_key + (size_t)frame * N;
-    const int wi = ev_wave(k[i], eb);
-    const int wp = i == 0 ? -1 : ev_wave(k[i - 1], eb);
     int* ws = wave_start + frame * (EV_MAX_WAVES + 1);
-    // waves without events keep the start of the next non-empty wave
-    for (int w = wp + 1; w <= wi; ++w) ws[w] = i;
-    if (i == N - 1)
-        for (int w = wi + 1; w <= EV_MAX_WAVES; ++w) ws[w] = N;
+    GRID_STRIDE(i, N) {
+        const int wi = ev_wave(k[i], eb);
+        const int wp = i == 0 ? -1 : ev_wave(k[i - 1], eb);
+        // waves without events keep the start of the next non-empty wave
+        for (int w = wp + 1; w <= wi; ++w) ws[w] = i;
+        if (i == N - 1)
+            for (int w = wi + 1; w <= EV_MAX_WAVES; ++w) ws[w] = N;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -401,87 +431,100 @@ k_replay_short(ReplayArgs A, int wave) {
     const int frame = blockIdx.y;
     const int w0 = A.wave_start[frame * (EV_MAX_WAVES + 1) + wave];
     const int w1 = A.wave_start[frame * (EV_MAX_WAVES + 1) + wave + 1];
-    const int i = w0 + blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= w1) return;
     const size_t fo = (size_t)frame * A.N;
     const u64* key = A.ev_key + fo;
-    const u64 k0 = key[i];
-    const u64 chain = ev_chain(k0, A.eb);  // wave | winner
-    if (i > w0 && ev_chain(key[i - 1], A.eb) == chain) return;  // not the head of its chain
-    if (i + REPLAY_SHORT < w1 && ev_chain(key[i + REPLAY_SHORT], A.eb) == chain) {  // long chain: a warp takes it
-        const int slot = atomicAdd(&A.long_count[wave], 1);
-        if (slot < A.list_cap) A.long_list[slot] = make_uint2((u32)frame, (u32)i);
-        return;
-    }
-    const u32 r = ev_winner(k0, A.eb);
-    int s = A.rsize[fo + r];
-    float2 f = A.rflow[fo + r];
-    ushort4 bb = A.rbbox[fo + r];
-    const int y = (int)r / A.W;
-    const bool row_ok = !(y < A.H / 10);                                  // graph.cpp:288
-    const double move_min = xddiv((double)(3 * (y + 1)), (double)A.H);    // graph.cpp:296
-    int j = i;
-    u64 kj = k0;
-    for (;;) {
-        const u32 a = A.ev_loser[fo + j];
-        const int sa = A.rsize[fo + a];
-        const float2 fa = A.rflow[fo + a];
-        const ushort4 ba = A.rbbox[fo + a];
-        const float fsa = (float)sa, fsb = (float)s;
-        const double inv = xddiv(1.0, (double)(sa + s));
-        f.x = merge_mean(xfmul(fa.x, fsa), f.x, fsb, inv);
-        f.y = merge_mean(xfmul(fa.y, fsa), f.y, fsb, inv);
-        s += sa;
-        bb.x = min(bb.x, ba.x);
-        bb.y = min(bb.y, ba.y);
-        bb.z = max(bb.z, ba.z);
-        bb.w = max(bb.w, ba.w);
-        if (s >= A.min_size && row_ok) {
-            const double move = norm2d(f.x, f.y);
-            if (!(move < move_min)) push_candidate(A, frame, r, ev_time(kj, A.eb), s, f, bb);
+    int longest = 0;
+    for (int i = w0 + blockIdx.x * blockDim.x + threadIdx.x; i < w1; i += gridDim.x * blockDim.x) {
+        const u64 k0 = key[i];
+        const u64 chain = ev_chain(k0, A.eb);  // wave | winner
+        if (i > w0 && ev_chain(key[i - 1], A.eb) == chain) continue;  // not the head of its chain
+        if (i + REPLAY_SHORT < w1 && ev_chain(key[i + REPLAY_SHORT], A.eb) == chain) {  // long chain: a warp takes it
+            const int slot = atomicAdd(&A.long_count[wave], 1);
+            if (slot < A.list_cap) A.long_list[slot] = make_uint2((u32)frame, (u32)i);
+            continue;
         }
-        ++j;
-        if (j >= w1) break;
-        kj = key[j];
-        if (ev_chain(kj, A.eb) != chain) break;
+        const u32 r = ev_winner(k0, A.eb);
+        int s = A.rsize[fo + r];
+        float2 f = A.rflow[fo + r];
+        ushort4 bb = A.rbbox[fo + r];
+        const int y = (int)r / A.W;
+        const bool row_ok = !(y < A.H / 10);                                  // graph.cpp:288
+        const double move_min = xddiv((double)(3 * (y + 1)), (double)A.H);    // graph.cpp:296
+        int j = i;
+        u64 kj = k0;
+        for (;;) {
+            const u32 a = A.ev_loser[fo + j];
+            const int sa = A.rsize[fo + a];
+            const float2 fa = A.rflow[fo + a];
+            const ushort4 ba = A.rbbox[fo + a];
+            const float fsa = (float)sa, fsb = (float)s;
+            const double inv = xddiv(1.0, (double)(sa + s));
+            f.x = merge_mean(xfmul(fa.x, fsa), f.x, fsb, inv);
+            f.y = merge_mean(xfmul(fa.y, fsa), f.y, fsb, inv);
+            s += sa;
+            bb.x = min(bb.x, ba.x);
+            bb.y = min(bb.y, ba.y);
+            bb.z = max(bb.z, ba.z);
+            bb.w = max(bb.w, ba.w);
+            if (s >= A.min_size && row_ok) {
+                const double move = norm2d(f.x, f.y);
+                if (!(move < move_min)) push_candidate(A, frame, r, ev_time(kj, A.eb), s, f, bb);
+            }
+            ++j;
+            if (j >= w1) break;
+            kj = key[j];
+            if (ev_chain(kj, A.eb) != chain) break;
+        }
+        A.rsize[fo + r] = s;
+        A.rflow[fo + r] = f;
+        A.rbbox[fo + r] = bb;
+        longest = max(longest, j - i);
     }
-    A.rsize[fo + r] = s;
-    A.rflow[fo + r] = f;
-    A.rbbox[fo + r] = bb;
-    atomicMax(&A.longest_chain[frame], j - i);
+    if (longest) atomicMax(&A.longest_chain[frame], longest);
 }
 
-struct ReplayOperand {
+// REPLAY_Q chunks of 32 events form one software-pipeline stage: while stage t is replayed, the gathers
+// of stage t+1 and the event reads of stage t+2 are in flight (nothing is unpacked or tested before
+// its use, so the warp never waits at the issue point of a load).
+#define REPLAY_Q 4
+#define REPLAY_WARPS 4
+#define REPLAY_G 8
+
+struct ReplayEvent {  // stage 0: straight reads of the sorted event arrays
     u64 key;
+    u32 a;
+};
+struct ReplayOperand {  // stage 1: state of the absorbed root, raw
     int sa;
     float2 fa;
-    ushort4 ba;
-    bool valid;
+    uint2 ba;  // ushort4 bounding box, still packed
 };
 
-DOFS_D ReplayOperand replay_load(const ReplayArgs& A, size_t fo, int j, int w1, u64 chain) {
-    ReplayOperand o;
-    o.valid = false;
-    o.key = 0;
-    o.sa = 0;
-    o.fa = make_float2(0.f, 0.f);
-    o.ba = make_ushort4(65535, 65535, 0, 0);
+DOFS_D ReplayEvent replay_read(const ReplayArgs& A, size_t fo, int j, int w1, u32 r) {
+    ReplayEvent e;
+    e.key = EV_KEY_NONE;
+    e.a = r;  // any valid index
     if (j < w1) {
-        o.key = A.ev_key[fo + j];
-        if (ev_chain(o.key, A.eb) == chain) {
-            const u32 a = A.ev_loser[fo + j];
-            o.valid = true;
-            o.sa = A.rsize[fo + a];
-            o.fa = A.rflow[fo + a];
-            o.ba = A.rbbox[fo + a];
-        }
+        e.key = A.ev_key[fo + j];
+        e.a = A.ev_loser[fo + j];
     }
+    return e;
+}
+
+DOFS_D ReplayOperand replay_gather(const ReplayArgs& A, size_t fo, u32 a) {
+    ReplayOperand o;
+    o.sa = A.rsize[fo + a];
+    o.fa = A.rflow[fo + a];
+    o.ba = *reinterpret_cast<const uint2*>(&A.rbbox[fo + a]);
     return o;
 }
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(32 * REPLAY_WARPS, 1)
 k_replay_long(ReplayArgs A, int wave) {
-    const int lane = threadIdx.x & 31;
+    __shared__ float4 s_op[REPLAY_WARPS][32];   // (loser mean * loser size).xy, size before the event, unused
+    __shared__ double s_inv[REPLAY_WARPS][32];  // 1 / size after the event
+    __shared__ float2 s_f[REPLAY_WARPS][32];    // mean flow after the event
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int n_warps = (gridDim.x * blockDim.x) >> 5;
     const int n_list = min(A.long_count[wave], A.list_cap);
@@ -501,65 +544,135 @@ k_replay_long(ReplayArgs A, int wave) {
         const bool row_ok = !(y < A.H / 10);
         const double move_min = xddiv((double)(3 * (y + 1)), (double)A.H);
         int j0 = i0;
-        ReplayOperand nxt = replay_load(A, fo, j0 + lane, w1, chain);
-        for (;;) {
-            const ReplayOperand cur = nxt;
-            nxt = replay_load(A, fo, j0 + 32 + lane, w1, chain);  // prefetch: these gathers overlap the serial part
-            const unsigned vmask = __ballot_sync(FULL, cur.valid);  // valid lanes are a prefix (events are sorted)
-            const int n_valid = __popc(vmask);
-            // sizes: inclusive scan
-            int s_inc = cur.sa;
-            ushort4 b_inc = cur.ba;
+        bool more = true;
+        ReplayEvent ev_cur[REPLAY_Q], ev_nxt[REPLAY_Q], ev_far[REPLAY_Q];
+        ReplayOperand op_cur[REPLAY_Q], op_nxt[REPLAY_Q];
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int t = __shfl_up_sync(FULL, s_inc, o);
-                const int bx = __shfl_up_sync(FULL, (int)b_inc.x, o), by = __shfl_up_sync(FULL, (int)b_inc.y, o);
-                const int bz = __shfl_up_sync(FULL, (int)b_inc.z, o), bw = __shfl_up_sync(FULL, (int)b_inc.w, o);
-                if (lane >= o) {
-                    s_inc += t;
-                    b_inc.x = min((int)b_inc.x, bx);
-                    b_inc.y = min((int)b_inc.y, by);
-                    b_inc.z = max((int)b_inc.z, bz);
-                    b_inc.w = max((int)b_inc.w, bw);
+        for (int q = 0; q < REPLAY_Q; ++q) ev_nxt[q] = replay_read(A, fo, j0 + 32 * q + lane, w1, r);
+#pragma unroll
+        for (int q = 0; q < REPLAY_Q; ++q) ev_far[q] = replay_read(A, fo, j0 + 32 * (REPLAY_Q + q) + lane, w1, r);
+#pragma unroll
+        for (int q = 0; q < REPLAY_Q; ++q) op_nxt[q] = replay_gather(A, fo, ev_nxt[q].a);
+        while (more) {
+#pragma unroll
+            for (int q = 0; q < REPLAY_Q; ++q) {
+                ev_cur[q] = ev_nxt[q];
+                op_cur[q] = op_nxt[q];
+                ev_nxt[q] = ev_far[q];
+            }
+#pragma unroll
+            for (int q = 0; q < REPLAY_Q; ++q) op_nxt[q] = replay_gather(A, fo, ev_nxt[q].a);
+#pragma unroll
+            for (int q = 0; q < REPLAY_Q; ++q) ev_far[q] = replay_read(A, fo, j0 + 32 * (2 * REPLAY_Q + q) + lane, w1, r);
+#pragma unroll
+            for (int q = 0; q < REPLAY_Q; ++q) {
+                const bool valid = ev_cur[q].key != EV_KEY_NONE && ev_chain(ev_cur[q].key, A.eb) == chain;
+                const unsigned vmask = __ballot_sync(FULL, valid);  // valid lanes are a prefix (events are sorted)
+                const int n_valid = __popc(vmask);
+                if (n_valid == 0) {
+                    more = false;
+                    break;
+                }
+                const int sa = valid ? op_cur[q].sa : 0;
+                const float2 fa = op_cur[q].fa;
+                // sizes and boxes after every event: inclusive warp scans
+                int s_inc = sa;
+                int bx0 = valid ? (int)(op_cur[q].ba.x & 0xffffu) : 65535, by0 = valid ? (int)(op_cur[q].ba.x >> 16) : 65535;
+                int bx1 = valid ? (int)(op_cur[q].ba.y & 0xffffu) : 0, by1 = valid ? (int)(op_cur[q].ba.y >> 16) : 0;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int t = __shfl_up_sync(FULL, s_inc, o);
+                    const int t0 = __shfl_up_sync(FULL, bx0, o), t1 = __shfl_up_sync(FULL, by0, o);
+                    const int t2 = __shfl_up_sync(FULL, bx1, o), t3 = __shfl_up_sync(FULL, by1, o);
+                    if (lane >= o) {
+                        s_inc += t;
+                        bx0 = min(bx0, t0);
+                        by0 = min(by0, t1);
+                        bx1 = max(bx1, t2);
+                        by1 = max(by1, t3);
+                    }
+                }
+                const int s_after = s + s_inc, s_before = s_after - sa;
+                ushort4 bb_after;
+                bb_after.x = (u16)min((int)bb.x, bx0);
+                bb_after.y = (u16)min((int)bb.y, by0);
+                bb_after.z = (u16)max((int)bb.z, bx1);
+                bb_after.w = (u16)max((int)bb.w, by1);
+                const float fsa = (float)sa;
+                // operands of the recurrence, broadcast through shared memory
+                s_op[wib][lane] = make_float4(xfmul(fa.x, fsa), xfmul(fa.y, fsa), (float)s_before, 0.f);
+                s_inv[wib][lane] = xddiv(1.0, (double)max(s_after, 1));
+                __syncwarp();
+                // the serial part: mean flow after each event; every lane runs the same recurrence
+                if (n_valid == 32) {
+                    // groups of REPLAY_G events: operands of the next group are read from shared memory before the
+                    // results of this group are stored, so no step waits for a shared-memory round trip
+                    float4 o4[REPLAY_G];
+                    double kv[REPLAY_G];
+#pragma unroll
+                    for (int k = 0; k < REPLAY_G; ++k) {
+                        o4[k] = s_op[wib][k];
+                        kv[k] = s_inv[wib][k];
+                    }
+#pragma unroll
+                    for (int g = 0; g < 32 / REPLAY_G; ++g) {
+                        float4 n4[REPLAY_G];
+                        double nv[REPLAY_G];
+                        if (g + 1 < 32 / REPLAY_G) {
+#pragma unroll
+                            for (int k = 0; k < REPLAY_G; ++k) {
+                                n4[k] = s_op[wib][(g + 1) * REPLAY_G + k];
+                                nv[k] = s_inv[wib][(g + 1) * REPLAY_G + k];
+                            }
+                        }
+                        float2 fh[REPLAY_G];
+#pragma unroll
+                        for (int k = 0; k < REPLAY_G; ++k) {
+                            f.x = merge_mean(o4[k].x, f.x, o4[k].z, kv[k]);
+                            f.y = merge_mean(o4[k].y, f.y, o4[k].z, kv[k]);
+                            fh[k] = f;
+                        }
+#pragma unroll
+                        for (int k = 0; k < REPLAY_G; ++k) s_f[wib][g * REPLAY_G + k] = fh[k];
+                        if (g + 1 < 32 / REPLAY_G) {
+#pragma unroll
+                            for (int k = 0; k < REPLAY_G; ++k) {
+                                o4[k] = n4[k];
+                                kv[k] = nv[k];
+                            }
+                        }
+                    }
+                } else {
+                    for (int k = 0; k < n_valid; ++k) {
+                        const float4 o4 = s_op[wib][k];
+                        const double kinv = s_inv[wib][k];
+                        f.x = merge_mean(o4.x, f.x, o4.z, kinv);
+                        f.y = merge_mean(o4.y, f.y, o4.z, kinv);
+                        s_f[wib][k] = f;
+                    }
+                }
+                __syncwarp();
+                // gates of the event this lane holds
+                if (valid && s_after >= A.min_size && row_ok) {
+                    const float2 mine = s_f[wib][lane];
+                    const double move = norm2d(mine.x, mine.y);
+                    if (!(move < move_min))
+                        push_candidate(A, frame, r, ev_time(ev_cur[q].key, A.eb), s_after, mine, bb_after);
+                }
+                __syncwarp();
+                // carry = state after the last valid event
+                const int last = n_valid - 1;
+                s = __shfl_sync(FULL, s_after, last);
+                bb.x = (u16)__shfl_sync(FULL, (int)bb_after.x, last);
+                bb.y = (u16)__shfl_sync(FULL, (int)bb_after.y, last);
+                bb.z = (u16)__shfl_sync(FULL, (int)bb_after.z, last);
+                bb.w = (u16)__shfl_sync(FULL, (int)bb_after.w, last);
+                j0 += n_valid;
+                if (n_valid < 32) {
+                    more = false;
+                    break;
                 }
             }
-            const int s_after = s + s_inc, s_before = s_after - cur.sa;
-            ushort4 bb_after;
-            bb_after.x = min(bb.x, b_inc.x);
-            bb_after.y = min(bb.y, b_inc.y);
-            bb_after.z = max(bb.z, b_inc.z);
-            bb_after.w = max(bb.w, b_inc.w);
-            const float fsa = (float)cur.sa;
-            const float ax = xfmul(cur.fa.x, fsa), ay = xfmul(cur.fa.y, fsa);
-            const float sb = (float)s_before;
-            const double inv = xddiv(1.0, (double)max(s_after, 1));
-            // the serial part: mean flow after each event, every lane runs the same recurrence
-            float2 mine = f;
-#pragma unroll 8
-            for (int k = 0; k < 32; ++k) {
-                const float kax = __shfl_sync(FULL, ax, k), kay = __shfl_sync(FULL, ay, k);
-                const float ksb = __shfl_sync(FULL, sb, k);
-                const double kinv = __shfl_sync(FULL, inv, k);
-                if (k < n_valid) {
-                    f.x = merge_mean(kax, f.x, ksb, kinv);
-                    f.y = merge_mean(kay, f.y, ksb, kinv);
-                }
-                if (k == lane) mine = f;
-            }
-            // gates of the event this lane holds
-            if (cur.valid && s_after >= A.min_size && row_ok) {
-                const double move = norm2d(mine.x, mine.y);
-                if (!(move < move_min)) push_candidate(A, frame, r, ev_time(cur.key, A.eb), s_after, mine, bb_after);
-            }
-            // carry to the next chunk = state after the last valid event
-            const int last = max(n_valid - 1, 0);
-            s = __shfl_sync(FULL, s_after, last);
-            bb.x = (u16)__shfl_sync(FULL, (int)bb_after.x, last);
-            bb.y = (u16)__shfl_sync(FULL, (int)bb_after.y, last);
-            bb.z = (u16)__shfl_sync(FULL, (int)bb_after.z, last);
-            bb.w = (u16)__shfl_sync(FULL, (int)bb_after.w, last);
-            j0 += n_valid;
-            if (n_valid < 32) break;
         }
         if (lane == 0) {
             A.rsize[fo + r] = s;
@@ -767,4 +880,26 @@ k_lift_problems(const float2* __restrict__ dir, const int4* __restrict__ bbox, c
     cd.pad = 0;
     fill_box(&out[i], cd, xddiv(xdadd(s.w_error, s.h_error), 2.0), s);
     if (!s.has_rect) out[i].cls = c;
+}
+
+// per-frame work counters -> the public stats record (include/dofs3d.h), on the device so that the
+// whole call stays asynchronous
+template <typename StatsT>
+__global__ void k_stats(StatsT* __restrict__ out, BorState S, const int* __restrict__ n_cand, const int* __restrict__ n_scored,
+                        const int* __restrict__ n_boxes, const int* __restrict__ longest_chain, int n_frames, int N,
+                        int n_edges, int max_levels) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= n_frames) return;
+    const int levels = S.levels[f];
+    StatsT st;
+    st.n_edges = n_edges;
+    st.n_levels = levels;
+    const int roots = S.n_roots[(min(max(levels, 1), max_levels) - 1) * S.F + f];
+    st.n_merges = N - roots;
+    st.n_candidates = n_cand[f];
+    st.n_scored = n_scored[f];
+    st.n_boxes = n_boxes[f];
+    st.longest_chain = longest_chain[f];
+    st.final_root = roots == 1 ? S.final_root[f] : -1;
+    out[f] = st;
 }
