@@ -274,15 +274,23 @@ k_bor_relabel(BorState S, int N, int level) {
         return;
     }
     const size_t fo = (size_t)frame * N;
-    const volatile u32* newp = S.newp + fo;
+    volatile u32* newp = S.newp + fo;
     int roots = 0;
     GRID_STRIDE(p, N) {
         const u32 c = S.comp[fo + p];
+        // follow the hooks to the group root with path halving: concurrent writers only ever replace a
+        // pointer by one of its ancestors, so any interleaving still ends at the same root
         u32 g = c;
         for (;;) {
-            u32 nx = newp[g];
+            const u32 nx = newp[g];
             if (nx == g) break;
-            g = nx;
+            const u32 nn = newp[nx];
+            if (nn == nx) {
+                g = nx;
+                break;
+            }
+            newp[g] = nn;
+            g = nn;
         }
         if (c == (u32)p) {  // p was a root in this level
             S.best[fo + p] = DOFS_INF32;
