@@ -125,6 +125,7 @@ struct dofs3d_ctx {
     int* wave_start = nullptr;
     uint2* long_list = nullptr;  // chains longer than REPLAY_SHORT events, per wave
     int* long_count = nullptr;
+    int* repair_flags = nullptr;  // [0] number of long prefix runs, [1] need the full 64-bit edge sort
     int list_cap = 0;
     int* rsize = nullptr;
     ushort4* rbbox = nullptr;
@@ -228,21 +229,24 @@ void timer_collect(dofs3d_ctx* ctx) {
 // [0, key_bits).  Input in (kA, vA) (payload = index when iota), ping-pong with (kB, vB).
 // Returns 0 if the result is in A, 1 if in B.
 // ---------------------------------------------------------------------------------------------
-int radix_sort(dofs3d_ctx* ctx, u64* kA, u32* vA, u64* kB, u32* vB, size_t stride, int n, int frames, int key_bits,
-               bool iota, const char* tag_hist, const char* tag_scan, const char* tag_scatter) {
+template <typename K>
+int radix_sort(dofs3d_ctx* ctx, K* kA, u32* vA, K* kB, u32* vB, size_t stride, int n, int frames, int key_bits, bool iota,
+               const char* tag_hist, const char* tag_scan, const char* tag_scatter, const int* enable = nullptr) {
     const int tiles = (n + RS_TILE - 1) / RS_TILE;
+    // a conditional sort is enqueued with a small persistent grid: it costs next to nothing when disabled
+    const int gx = enable ? std::min(tiles, std::max(1, 148 * 2 / frames)) : tiles;
     int side = 0;
     for (int shift = 0; shift < key_bits; shift += 8) {
-        const u64* kin = side ? kB : kA;
+        const K* kin = side ? kB : kA;
         const u32* vin = side ? vB : vA;
-        u64* kout = side ? kA : kB;
+        K* kout = side ? kA : kB;
         u32* vout = side ? vA : vB;
-        LAUNCH(ctx, k_radix_hist, dim3(tiles, frames), RS_THREADS, 0, kin, stride, ctx->tile_hist, n, shift, tiles);
+        LAUNCH(ctx, k_radix_hist<K>, dim3(gx, frames), RS_THREADS, 0, kin, stride, ctx->tile_hist, n, shift, tiles, enable);
         mark(ctx, tag_hist);
-        LAUNCH(ctx, k_radix_scan, dim3(RS_BINS, frames), RS_THREADS, 0, ctx->tile_hist, ctx->digit_tot, tiles);
+        LAUNCH(ctx, k_radix_scan, dim3(RS_BINS, frames), RS_THREADS, 0, ctx->tile_hist, ctx->digit_tot, tiles, enable);
         mark(ctx, tag_scan);
-        LAUNCH(ctx, k_radix_scatter, dim3(tiles, frames), RS_THREADS, RS_SMEM_BYTES, kin, vin, kout, vout, stride,
-               ctx->tile_hist, ctx->digit_tot, n, shift, tiles, (iota && shift == 0) ? 1 : 0);
+        LAUNCH(ctx, k_radix_scatter<K>, dim3(gx, frames), RS_THREADS, rs_smem_bytes<K>(), kin, vin, kout, vout, stride,
+               ctx->tile_hist, ctx->digit_tot, n, shift, tiles, (iota && shift == 0) ? 1 : 0, enable);
         mark(ctx, tag_scatter);
         side ^= 1;
     }
@@ -253,22 +257,45 @@ int n_edges_of(int W, int H, int neighbors) {
     return neighbors == 8 ? 4 * W * H - 3 * W - 3 * H + 2 : 2 * W * H - W - H;
 }
 
-// K7 + K8: blurred flow (ctx->flow_blur) -> sorted keys in keysA, sorted sequence numbers in valsA,
-// rank of every slot in valsB.
+// K7 + K8: blurred flow (ctx->flow_blur) -> weights by slot in keysA, sorted sequence numbers in valsA, rank of every
+// slot in valsB.  4 radix passes on a 32-bit order-preserving prefix of the weight, exact repair of the runs that share
+// a prefix, and — only if a frame has a long run the repair kernels cannot order — the full 64-bit sort.
 int build_sorted_edges(dofs3d_ctx* ctx, int n) {
     const int N = ctx->N;
-    LAUNCH(ctx, k_edge_keys, grid1(N, SEG_THREADS, n), SEG_THREADS, 0, ctx->flow_blur, ctx->keysA, ctx->S, ctx->W,
+    const int S = (int)ctx->S;
+    u32* preA = reinterpret_cast<u32*>(ctx->keysB);  // the prefix buffers live in keysB, which only the fallback needs
+    u32* preB = preA + (size_t)ctx->F * ctx->S;
+    LAUNCH(ctx, k_edge_keys, grid1(N, SEG_THREADS, n), SEG_THREADS, 0, ctx->flow_blur, ctx->keysA, preA, ctx->S, ctx->W,
            ctx->H, ctx->seg.neighbors == 8 ? 1 : 0);
     mark(ctx, "edge_keys");
-    int side = radix_sort(ctx, ctx->keysA, ctx->valsA, ctx->keysB, ctx->valsB, ctx->S, (int)ctx->S, n, 64, true,
-                          "edge_sort.hist", "edge_sort.scan", "edge_sort.scatter");
+    int side = radix_sort<u32>(ctx, preA, ctx->valsA, preB, ctx->valsB, ctx->S, S, n, 32, true, "edge_sort.hist",
+                               "edge_sort.scan", "edge_sort.scatter");
     if (side != 0) {
         ctx->err = "internal: odd number of sort passes";
         return DOFS3D_ERR_INTERNAL;
     }
-    LAUNCH(ctx, k_rank_scatter, grid1(ctx->S, SEG_THREADS, n), SEG_THREADS, 0, ctx->valsA, ctx->valsB, ctx->S,
-           (int)ctx->S, n_edges_of(ctx->W, ctx->H, ctx->seg.neighbors));
-    mark(ctx, "edge_rank");
+    CK(cudaMemsetAsync(ctx->repair_flags, 0, 2 * sizeof(int), ctx->stream));
+    RepairArgs R;
+    R.prefix = preA;
+    R.seq = ctx->valsA;
+    R.keys = ctx->keysA;
+    R.rank = ctx->valsB;
+    R.long_list = ctx->long_list;
+    R.long_count = ctx->repair_flags;
+    R.need_full = ctx->repair_flags + 1;
+    R.list_cap = ctx->list_cap;
+    R.stride = ctx->S;
+    R.n_slots = S;
+    LAUNCH(ctx, k_prefix_repair_short, grid1(ctx->S, SEG_THREADS, n), SEG_THREADS, 0, R);
+    LAUNCH(ctx, k_prefix_repair_long, dim3(148 * 2), 256, 0, R);
+    mark(ctx, "edge_repair");
+    // fallback, enabled on the device by *need_full
+    const int* enable = ctx->repair_flags + 1;
+    side = radix_sort<u64>(ctx, ctx->keysA, ctx->valsA, ctx->keysB, ctx->valsB, ctx->S, S, n, 64, true, "edge_fallback",
+                           "edge_fallback", "edge_fallback", enable);
+    LAUNCH(ctx, k_rank_scatter, dim3(std::max(1, 148 * 4 / n), n), SEG_THREADS, 0, ctx->valsA, ctx->valsB, ctx->S, S,
+           n_edges_of(ctx->W, ctx->H, ctx->seg.neighbors), enable);
+    mark(ctx, "edge_fallback");
     return 0;
 }
 
@@ -315,7 +342,7 @@ int segment_dev(dofs3d_ctx* ctx, const float* d_flow, int already_blurred, int n
     u32* evlB = reinterpret_cast<u32*>(ctx->keysB + (size_t)F * N);
     LAUNCH(ctx, k_event_keys, gS, SEG_THREADS, 0, B, ctx->win, evA, N, eb);
     mark(ctx, "event_keys");
-    int side = radix_sort(ctx, evA, evlA, evB, evlB, (size_t)N, N, n, eb.tb + eb.wb + 5, true, "event_sort.hist",
+    int side = radix_sort<u64>(ctx, evA, evlA, evB, evlB, (size_t)N, N, n, eb.tb + eb.wb + 5, true, "event_sort.hist",
                           "event_sort.scan", "event_sort.scatter");
     const u64* ev_key = side ? evB : evA;
     const u32* ev_loser = side ? evlB : evlA;
@@ -378,7 +405,7 @@ int segment_dev(dofs3d_ctx* ctx, const float* d_flow, int already_blurred, int n
     // counters -> stats record, on the device; a copy lands in pinned host memory for the host-pointer entry points
     LAUNCH(ctx, k_stats<dofs3d_stats>, dim3((n + 63) / 64), 64, 0, ctx->stats, B, ctx->counters + CNT_CAND * F,
            ctx->counters + CNT_SCORED * F, ctx->counters + CNT_BOXES * F, ctx->counters + CNT_CHAIN * F, n, N,
-           n_edges_of(W, H, ctx->seg.neighbors), levels);
+           n_edges_of(W, H, ctx->seg.neighbors), levels, ctx->repair_flags + 1);
     CK(cudaMemcpyAsync(ctx->h_stats, ctx->stats, sizeof(dofs3d_stats) * n, cudaMemcpyDeviceToHost, ctx->stream));
     return 0;
 }
@@ -525,7 +552,8 @@ int dofs3d_create(dofs3d_ctx** out, int device, int width, int height, int max_p
     }
     CK(cudaSetDevice(device));
     CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-    CK(cudaFuncSetAttribute(k_radix_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, RS_SMEM_BYTES));
+    CK(cudaFuncSetAttribute(k_radix_scatter<u64>, cudaFuncAttributeMaxDynamicSharedMemorySize, rs_smem_bytes<u64>()));
+    CK(cudaFuncSetAttribute(k_radix_scatter<u32>, cudaFuncAttributeMaxDynamicSharedMemorySize, rs_smem_bytes<u32>()));
 
     const size_t F = ctx->F, N = ctx->N, S = ctx->S;
     DA(ctx->flow_in, F * N);
@@ -549,6 +577,7 @@ int dofs3d_create(dofs3d_ctx** out, int device, int width, int height, int max_p
     ctx->list_cap = (int)std::min<size_t>(F * (N / REPLAY_SHORT + 1), (size_t)1 << 28);
     DA(ctx->long_list, (size_t)ctx->list_cap);
     DA(ctx->long_count, EV_MAX_WAVES + 1);
+    DA(ctx->repair_flags, 2);
     DA(ctx->rsize, F * N);
     DA(ctx->rbbox, F * N);
     DA(ctx->rflow, F * N);
@@ -817,15 +846,16 @@ long long dofs3d_edges_sorted(dofs3d_ctx* ctx, const float* flow_blurred, int32_
     CK(cudaMemcpyAsync(ctx->flow_blur, flow_blurred, (size_t)N * sizeof(float2), cudaMemcpyHostToDevice, ctx->stream));
     int rc = build_sorted_edges(ctx, 1);
     if (rc) return rc;
-    // decode (start, end) into the dead B buffers
+    // decode (start, end, weight) into the dead B buffers
     int* d_start = reinterpret_cast<int*>(ctx->keysB);
     int* d_end = d_start + ctx->S;
-    LAUNCH(ctx, k_edges_decode, grid1(E, SEG_THREADS, 1), SEG_THREADS, 0, ctx->valsA, d_start, d_end, ctx->W, E);
+    u64* d_w = ctx->keysA;  // the weights by slot are no longer needed
+    LAUNCH(ctx, k_edges_decode, grid1(E, SEG_THREADS, 1), SEG_THREADS, 0, ctx->valsA, ctx->flow_blur, d_start, d_end, d_w,
+           ctx->W, E);
     CK(cudaGetLastError());
     if (start) CK(cudaMemcpyAsync(start, d_start, sizeof(int) * (size_t)E, cudaMemcpyDeviceToHost, ctx->stream));
     if (end) CK(cudaMemcpyAsync(end, d_end, sizeof(int) * (size_t)E, cudaMemcpyDeviceToHost, ctx->stream));
-    if (weight_bits)
-        CK(cudaMemcpyAsync(weight_bits, ctx->keysA, sizeof(u64) * (size_t)E, cudaMemcpyDeviceToHost, ctx->stream));
+    if (weight_bits) CK(cudaMemcpyAsync(weight_bits, d_w, sizeof(u64) * (size_t)E, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return E;
 }

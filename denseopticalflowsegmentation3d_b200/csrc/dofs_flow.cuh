@@ -480,65 +480,80 @@ k_update_matrices(const float* __restrict__ R, const float2* __restrict__ flow, 
 // vertical window sums are formed once per column and reused by the horizontal window.
 // ---------------------------------------------------------------------------------------------
 #define BX_TW 32
-#define BX_TH 8
+#define BX_TH 16
+#define BX_THREADS 256
+#define BX_GROUP 8  // consecutive outputs one thread produces with a sliding window
 
-__global__ void __launch_bounds__(BX_TW * BX_TH)
+// Window sums are formed with sliding windows in double (first window summed directly, then
+// + entering - leaving), vertically per (column, channel) and horizontally per (row, channel, group
+// of BX_GROUP columns): ~3 shared-memory reads per output and channel instead of 15.
+__global__ void __launch_bounds__(BX_THREADS)
 k_box_solve(const float* __restrict__ M, float2* __restrict__ flow, int Wk, int Hk, int m /* winsize/2 */) {
     extern __shared__ __align__(16) unsigned char bx_smem[];
     const int cols = BX_TW + 2 * m, rows = BX_TH + 2 * m;
-    float* s_m = reinterpret_cast<float*>(bx_smem);                         // [rows][cols][5]
-    double* s_v = reinterpret_cast<double*>(bx_smem + (((size_t)rows * cols * 5 * 4 + 15) & ~(size_t)15));  // [TH][cols][5]
+    const int cw = cols * 5;                                               // floats / doubles per tile row
+    float* s_m = reinterpret_cast<float*>(bx_smem);                        // [rows][cols][5] M tile with halo
+    double* s_h = reinterpret_cast<double*>(bx_smem);                      // [TH][TW][5] window sums (aliases s_m)
+    const size_t tile_bytes = ((size_t)rows * cw * 4 + 15) & ~(size_t)15, sum_bytes = (size_t)BX_TH * BX_TW * 5 * 8;
+    double* s_v = reinterpret_cast<double*>(bx_smem + (tile_bytes > sum_bytes ? tile_bytes : sum_bytes));  // [TH][cols][5]
     const int pair = blockIdx.z;
     const int x0 = blockIdx.x * BX_TW, y0 = blockIdx.y * BX_TH;
     const float* src = M + (size_t)pair * Wk * Hk * 5;
-    for (int idx = threadIdx.x; idx < rows * cols; idx += BX_TW * BX_TH) {
-        const int ry = idx / cols, cx = idx - ry * cols;
+    // stage the tile: consecutive threads read consecutive floats of a row (replicated borders by clamping)
+    for (int idx = threadIdx.x; idx < rows * cw; idx += BX_THREADS) {
+        const int ry = idx / cw, rem = idx - ry * cw;
+        const int cx = rem / 5, c = rem - cx * 5;
         const int yy = min(max(y0 + ry - m, 0), Hk - 1);
         const int xx = min(max(x0 + cx - m, 0), Wk - 1);
-        const float* p = src + ((size_t)yy * Wk + xx) * 5;
-        float* d = s_m + (size_t)idx * 5;
-        d[0] = p[0];
-        d[1] = p[1];
-        d[2] = p[2];
-        d[3] = p[3];
-        d[4] = p[4];
+        s_m[idx] = src[((size_t)yy * Wk + xx) * 5 + c];
     }
     __syncthreads();
-    for (int idx = threadIdx.x; idx < BX_TH * cols * 5; idx += BX_TW * BX_TH) {
-        const int ty = idx / (cols * 5), rem = idx - ty * cols * 5;  // rem = cx*5 + c
+    // vertical windows: one thread per (column, channel), sliding down the BX_TH rows
+    for (int e = threadIdx.x; e < cw; e += BX_THREADS) {
         double s = 0;
-        for (int j = 0; j <= 2 * m; ++j) s += (double)s_m[(size_t)(ty + j) * cols * 5 + rem];
-        s_v[idx] = s;
+        for (int j = 0; j <= 2 * m; ++j) s += (double)s_m[j * cw + e];
+        s_v[e] = s;
+        for (int ty = 1; ty < BX_TH; ++ty) {
+            s += (double)s_m[(ty + 2 * m) * cw + e] - (double)s_m[(ty - 1) * cw + e];
+            s_v[ty * cw + e] = s;
+        }
     }
     __syncthreads();
-    const int tx = threadIdx.x & (BX_TW - 1), ty = threadIdx.x / BX_TW;
-    const int x = x0 + tx, y = y0 + ty;
-    if (x >= Wk || y >= Hk) return;
-    double g11 = 0, g12 = 0, g22 = 0, h1 = 0, h2 = 0;
-    const double* v = s_v + ((size_t)ty * cols + tx) * 5;
-    for (int i = 0; i <= 2 * m; ++i) {
-        g11 += v[i * 5];
-        g12 += v[i * 5 + 1];
-        g22 += v[i * 5 + 2];
-        h1 += v[i * 5 + 3];
-        h2 += v[i * 5 + 4];
+    // horizontal windows: one thread per (row, channel, group of columns); results over the dead M tile
+    for (int w = threadIdx.x; w < BX_TH * 5 * (BX_TW / BX_GROUP); w += BX_THREADS) {
+        const int c = w % 5, g = (w / 5) % (BX_TW / BX_GROUP), ty = w / (5 * (BX_TW / BX_GROUP));
+        const double* v = s_v + ty * cw + c;  // element of column cx at v[cx * 5]
+        const int xs = g * BX_GROUP;
+        double s = 0;
+        for (int i = 0; i <= 2 * m; ++i) s += v[(xs + i) * 5];
+        s_h[(ty * BX_TW + xs) * 5 + c] = s;
+        for (int k = 1; k < BX_GROUP; ++k) {
+            s += v[(xs + k + 2 * m) * 5] - v[(xs + k - 1) * 5];
+            s_h[(ty * BX_TW + xs + k) * 5 + c] = s;
+        }
     }
+    __syncthreads();
     const int bs = 2 * m + 1;
     const double scale = 1.0 / (double)(bs * bs);
-    g11 = xdmul(g11, scale);
-    g12 = xdmul(g12, scale);
-    g22 = xdmul(g22, scale);
-    h1 = xdmul(h1, scale);
-    h2 = xdmul(h2, scale);
-    const double idet = xddiv(1.0, xdadd(xdsub(xdmul(g11, g22), xdmul(g12, g12)), 1e-3));
-    const float u = (float)xdmul(xdsub(xdmul(g11, h2), xdmul(g12, h1)), idet);
-    const float w = (float)xdmul(xdsub(xdmul(g22, h1), xdmul(g12, h2)), idet);
-    flow[((size_t)pair * Hk + y) * Wk + x] = make_float2(u, w);
+    for (int o = threadIdx.x; o < BX_TW * BX_TH; o += BX_THREADS) {
+        const int tx = o % BX_TW, ty = o / BX_TW;
+        const int x = x0 + tx, y = y0 + ty;
+        if (x >= Wk || y >= Hk) continue;
+        const double* h = s_h + (size_t)o * 5;
+        const double g11 = xdmul(h[0], scale), g12 = xdmul(h[1], scale), g22 = xdmul(h[2], scale);
+        const double h1 = xdmul(h[3], scale), h2 = xdmul(h[4], scale);
+        const double idet = xddiv(1.0, xdadd(xdsub(xdmul(g11, g22), xdmul(g12, g12)), 1e-3));
+        const float u = (float)xdmul(xdsub(xdmul(g11, h2), xdmul(g12, h1)), idet);
+        const float w = (float)xdmul(xdsub(xdmul(g22, h1), xdmul(g12, h2)), idet);
+        flow[((size_t)pair * Hk + y) * Wk + x] = make_float2(u, w);
+    }
 }
 
 inline size_t box_solve_smem(int m) {
     const size_t cols = BX_TW + 2 * m, rows = BX_TH + 2 * m;
-    return ((rows * cols * 5 * 4 + 15) & ~(size_t)15) + (size_t)BX_TH * cols * 5 * 8;
+    const size_t tile = (rows * cols * 5 * 4 + 15) & ~(size_t)15;
+    const size_t sums = (size_t)BX_TH * BX_TW * 5 * 8;
+    return (tile > sums ? tile : sums) + (size_t)BX_TH * cols * 5 * 8;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -574,6 +589,7 @@ inline int farneback_run(FlowBuffers& fb, const u8* d_gray0, const u8* d_gray1, 
         const dim3 blk(256);
         const dim3 g_img((L.w + 31) / 32, (L.h + 7) / 8, imgs.count);
         const dim3 g_pair((L.w + 31) / 32, (L.h + 7) / 8, n);
+        const dim3 g_box((L.w + BX_TW - 1) / BX_TW, (L.h + BX_TH - 1) / BX_TH, n);
         cur = (k == 0) ? d_flow_out : (prev == fb.flowA ? fb.flowB : fb.flowA);
         if (!prev) {
             if (cudaMemsetAsync(cur, 0, (size_t)n * L.w * L.h * sizeof(float2), stream) != cudaSuccess) return 3;
@@ -586,7 +602,7 @@ inline int farneback_run(FlowBuffers& fb, const u8* d_gray0, const u8* d_gray1, 
         k_update_matrices<<<g_pair, blk, 0, stream>>>(fb.R, cur, fb.M, L.w, L.h, ps);
         st->launches += 3;
         for (int it = 0; it < fb.cfg.iters; ++it) {
-            k_box_solve<<<g_pair, blk, bx_smem, stream>>>(fb.M, cur, L.w, L.h, m);
+            k_box_solve<<<g_box, BX_THREADS, bx_smem, stream>>>(fb.M, cur, L.w, L.h, m);
             st->launches++;
             if (it < fb.cfg.iters - 1) {
                 k_update_matrices<<<g_pair, blk, 0, stream>>>(fb.R, cur, fb.M, L.w, L.h, ps);

@@ -111,9 +111,21 @@ DOFS_D u64 edge_key(float2 a, float2 b) {
 }
 
 #define EDGE_KEY_INVALID 0x7FF0000000000000ull
+#define EDGE_PREFIX_INVALID 0xFFFFFFFFu
+
+// Order-preserving 32-bit prefix of a weight: exponent rebased to 2^-200 (9 bits cover every weight a
+// float flow field can produce) followed by the top 23 mantissa bits.  Monotone in the weight; weights
+// that share a prefix are put in exact order afterwards (k_prefix_repair_*).
+DOFS_D u32 edge_prefix(u64 key) {
+    const u64 base = (u64)(1023 - 200) << 52;
+    if (key >= EDGE_KEY_INVALID) return EDGE_PREFIX_INVALID;
+    const u64 k = key > base ? key - base : 0ull;
+    return (u32)min(k >> 29, (u64)0xFFFFFFFEu);
+}
 
 __global__ void __launch_bounds__(SEG_THREADS)
-k_edge_keys(const float2* __restrict__ flow, u64* __restrict__ keys, size_t key_stride, int W, int H, int neighbors8) {
+k_edge_keys(const float2* __restrict__ flow, u64* __restrict__ keys, u32* __restrict__ prefix, size_t key_stride, int W,
+            int H, int neighbors8) {
     const int frame = blockIdx.y;
     const int N = W * H;
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -131,31 +143,184 @@ k_edge_keys(const float2* __restrict__ flow, u64* __restrict__ keys, size_t key_
     ulonglong2* out = reinterpret_cast<ulonglong2*>(keys + (size_t)frame * key_stride + 4 * (size_t)p);
     out[0] = make_ulonglong2(k0, k1);
     out[1] = make_ulonglong2(k2, k3);
+    *reinterpret_cast<uint4*>(prefix + (size_t)frame * key_stride + 4 * (size_t)p) =
+        make_uint4(edge_prefix(k0), edge_prefix(k1), edge_prefix(k2), edge_prefix(k3));
 }
 
 DOFS_D int edge_other(int s, int d, int W) {
     return d == 0 ? s - 1 : d == 1 ? s - W : d == 2 ? s - W - 1 : s + W - 1;
 }
 
-// rank[seq] = position in the sorted list (INF for the non-existent slots, which sort last)
+// rank[seq] = position in the sorted list (INF for the non-existent slots, which sort last); only used
+// after the full 64-bit fallback sort
 __global__ void __launch_bounds__(SEG_THREADS)
-k_rank_scatter(const u32* __restrict__ sorted_seq, u32* __restrict__ rank, size_t stride, int n_slots, int n_edges) {
+k_rank_scatter(const u32* __restrict__ sorted_seq, u32* __restrict__ rank, size_t stride, int n_slots, int n_edges,
+               const int* __restrict__ enable) {
+    if (enable && *enable == 0) return;
     const int frame = blockIdx.y;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_slots) return;
-    u32 seq = sorted_seq[(size_t)frame * stride + i];
-    rank[(size_t)frame * stride + seq] = i < n_edges ? (u32)i : DOFS_INF32;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_slots; i += gridDim.x * blockDim.x) {
+        u32 seq = sorted_seq[(size_t)frame * stride + i];
+        rank[(size_t)frame * stride + seq] = i < n_edges ? (u32)i : DOFS_INF32;
+    }
 }
 
-// parity hook: sorted (start, end) from the sorted sequence numbers
+// parity hook: sorted (start, end, weight) from the sorted sequence numbers
 __global__ void __launch_bounds__(SEG_THREADS)
-k_edges_decode(const u32* __restrict__ sorted_seq, int* __restrict__ start, int* __restrict__ end, int W, int n_edges) {
+k_edges_decode(const u32* __restrict__ sorted_seq, const float2* __restrict__ flow, int* __restrict__ start,
+               int* __restrict__ end, u64* __restrict__ weight, int W, int n_edges) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_edges) return;
     u32 seq = sorted_seq[i];
     int s = (int)(seq >> 2);
+    int e = edge_other(s, (int)(seq & 3u), W);
     start[i] = s;
-    end[i] = edge_other(s, (int)(seq & 3u), W);
+    end[i] = e;
+    weight[i] = edge_key(flow[s], flow[e]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K8b  exact order inside runs of equal 32-bit prefix.  After the 4-pass sort on the prefix the
+// sequence numbers are in (prefix, insertion) order; the reference order is (weight, insertion).
+// Runs are short (a handful of edges: two weights must agree to 2^-23 relative to share a prefix):
+//   k_prefix_repair_short  every run of at most REPAIR_SHORT edges is insertion-sorted by its head
+//                          thread on the 64-bit weights; also writes rank[seq] = final position.
+//                          Longer runs are pushed to a list.
+//   k_prefix_repair_long   one block per listed run: a run of identical weights (zero-weight ties of a
+//                          static scene, flat ramps) is already in order; otherwise it is sorted in
+//                          shared memory (<= REPAIR_SMEM edges) or, beyond that, *need_full is raised
+//                          and the full 64-bit radix sort that is enqueued behind runs instead.
+// ---------------------------------------------------------------------------------------------
+#define REPAIR_SHORT 16
+#define REPAIR_SMEM 2048
+
+struct RepairArgs {
+    const u32* prefix;   // [F][S] sorted prefixes
+    u32* seq;            // [F][S] sequence numbers in (prefix, insertion) order -> repaired in place
+    const u64* keys;     // [F][S] weights by slot (= by sequence number)
+    u32* rank;           // [F][S] out: rank[seq] = position, INF for non-existent slots
+    uint2* long_list;    // (frame, start)
+    int* long_count;
+    int* need_full;
+    int list_cap;
+    size_t stride;
+    int n_slots;
+};
+
+__global__ void __launch_bounds__(SEG_THREADS)
+k_prefix_repair_short(RepairArgs A) {
+    const int frame = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= A.n_slots) return;
+    const size_t fo = (size_t)frame * A.stride;
+    const u32* pre = A.prefix + fo;
+    const u32 k = pre[i];
+    if (k == EDGE_PREFIX_INVALID) {  // non-existent border slot
+        A.rank[fo + A.seq[fo + i]] = DOFS_INF32;
+        return;
+    }
+    const bool prev_same = i > 0 && pre[i - 1] == k;
+    const bool next_same = i + 1 < A.n_slots && pre[i + 1] == k;
+    if (!prev_same && !next_same) {  // a run of one
+        A.rank[fo + A.seq[fo + i]] = (u32)i;
+        return;
+    }
+    if (prev_same) return;  // the head of the run does the work
+    int len = 2;
+    while (len <= REPAIR_SHORT && i + len < A.n_slots && pre[i + len] == k) ++len;
+    if (len > REPAIR_SHORT) {
+        const int slot = atomicAdd(A.long_count, 1);
+        if (slot < A.list_cap) A.long_list[slot] = make_uint2((u32)frame, (u32)i);
+        else atomicExch(A.need_full, 1);
+        return;
+    }
+    u32 sq[REPAIR_SHORT];
+    u64 kk[REPAIR_SHORT];
+    for (int j = 0; j < len; ++j) {
+        sq[j] = A.seq[fo + i + j];
+        kk[j] = A.keys[fo + sq[j]];
+    }
+    for (int j = 1; j < len; ++j) {  // stable insertion sort by weight
+        const u32 s = sq[j];
+        const u64 w = kk[j];
+        int m = j - 1;
+        while (m >= 0 && kk[m] > w) {
+            sq[m + 1] = sq[m];
+            kk[m + 1] = kk[m];
+            --m;
+        }
+        sq[m + 1] = s;
+        kk[m + 1] = w;
+    }
+    for (int j = 0; j < len; ++j) {
+        A.seq[fo + i + j] = sq[j];
+        A.rank[fo + sq[j]] = (u32)(i + j);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_prefix_repair_long(RepairArgs A) {
+    __shared__ u64 s_key[REPAIR_SMEM];
+    __shared__ u32 s_seq[REPAIR_SMEM];
+    __shared__ int s_flag, s_len;
+    const int n_list = min(*A.long_count, A.list_cap);
+    for (int item = blockIdx.x; item < n_list; item += gridDim.x) {
+        const uint2 it = A.long_list[item];
+        const size_t fo = (size_t)it.x * A.stride;
+        const int i0 = (int)it.y;
+        const u32* pre = A.prefix + fo;
+        const u32 k = pre[i0];
+        // length of the run
+        if (threadIdx.x == 0) s_len = A.n_slots - i0;
+        __syncthreads();
+        for (int base = 0; base < A.n_slots - i0; base += 256) {
+            const int j = base + threadIdx.x;
+            if (j < A.n_slots - i0 && pre[i0 + j] != k) atomicMin(&s_len, j);
+            __syncthreads();
+            const int seen = s_len;
+            __syncthreads();
+            if (seen <= base + 256) break;
+        }
+        const int len = s_len;
+        // identical weights?
+        const u64 w0 = A.keys[fo + A.seq[fo + i0]];
+        if (threadIdx.x == 0) s_flag = 0;
+        __syncthreads();
+        int differs = 0;
+        for (int j = threadIdx.x; j < len; j += 256) differs |= A.keys[fo + A.seq[fo + i0 + j]] != w0;
+        if (differs) s_flag = 1;
+        __syncthreads();
+        const bool trivial = s_flag == 0;
+        __syncthreads();
+        if (!trivial && len > REPAIR_SMEM) {
+            if (threadIdx.x == 0) atomicExch(A.need_full, 1);
+            continue;  // block-uniform
+        }
+        if (!trivial) {
+            // odd-even transposition sort in shared memory: stable, len rounds of disjoint compare-exchanges
+            for (int j = threadIdx.x; j < len; j += 256) {
+                s_seq[j] = A.seq[fo + i0 + j];
+                s_key[j] = A.keys[fo + s_seq[j]];
+            }
+            __syncthreads();
+            for (int round = 0; round < len; ++round) {
+                for (int j = 2 * threadIdx.x + (round & 1); j + 1 < len; j += 512) {
+                    if (s_key[j] > s_key[j + 1]) {
+                        const u64 tk = s_key[j];
+                        s_key[j] = s_key[j + 1];
+                        s_key[j + 1] = tk;
+                        const u32 ts = s_seq[j];
+                        s_seq[j] = s_seq[j + 1];
+                        s_seq[j + 1] = ts;
+                    }
+                }
+                __syncthreads();
+            }
+            for (int j = threadIdx.x; j < len; j += 256) A.seq[fo + i0 + j] = s_seq[j];
+            __syncthreads();
+        }
+        for (int j = threadIdx.x; j < len; j += 256) A.rank[fo + A.seq[fo + i0 + j]] = (u32)(i0 + j);
+        __syncthreads();
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -895,7 +1060,7 @@ k_lift_problems(const float2* __restrict__ dir, const int4* __restrict__ bbox, c
 template <typename StatsT>
 __global__ void k_stats(StatsT* __restrict__ out, BorState S, const int* __restrict__ n_cand, const int* __restrict__ n_scored,
                         const int* __restrict__ n_boxes, const int* __restrict__ longest_chain, int n_frames, int N,
-                        int n_edges, int max_levels) {
+                        int n_edges, int max_levels, const int* __restrict__ need_full) {
     const int f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= n_frames) return;
     const int levels = S.levels[f];
@@ -909,5 +1074,7 @@ __global__ void k_stats(StatsT* __restrict__ out, BorState S, const int* __restr
     st.n_boxes = n_boxes[f];
     st.longest_chain = longest_chain[f];
     st.final_root = roots == 1 ? S.final_root[f] : -1;
+    st.sort_fallback = *need_full;
+    st.pad_ = 0;
     out[f] = st;
 }

@@ -1,17 +1,22 @@
-// Stable LSD radix sort of (u64 key, u32 payload) pairs, batched over frames (blockIdx.y = frame).
+// Stable LSD radix sort of (key, u32 payload) pairs, batched over frames (blockIdx.y = frame), for
+// 32-bit and 64-bit keys.
 //
 // Reproduces the order of the reference's std::multiset edge container (graph.cpp:55-60): ascending
 // f64 weight (non-negative doubles order like their bit patterns), equal weights in insertion order —
-// i.e. a STABLE sort of the insertion sequence by weight.  Also used to order merge events by
-// (wave, winner root, time).
+// i.e. a STABLE sort of the insertion sequence by weight.  The edge list is ordered in two steps
+// (dofs_seg.cuh: 4 passes on an order-preserving 32-bit prefix of the weight, then an exact in-place
+// repair of the short runs that share a prefix); the full 64-bit sort is the fallback of that scheme and
+// the sort of the merge events by (wave, winner root, time).
 //
 // One 8-bit digit per pass, three kernels per pass:
-//   k_radix_hist     per-tile digit histogram            reads keys (8 B/elem)
-//   k_radix_scan     per-digit exclusive scan over tiles  (tiny)
+//   k_radix_hist     per-tile digit histogram             reads keys
+//   k_radix_scan     per-digit exclusive scan over tiles   (tiny)
 //   k_radix_scatter  stable in-tile ranking (warp match-any), reorder through shared memory so that
-//                    each digit run leaves the block as one coalesced segment
-//                    reads keys+payload (12 B/elem), writes keys+payload (12 B/elem)
-// HBM-bound: 32 B per element per pass.
+//                    each digit run leaves the block as one coalesced segment; reads and writes
+//                    keys + payload
+// HBM-bound: (2 * sizeof(key) + 8) + sizeof(key) bytes per element per pass.
+// Every kernel loops over its tiles with stride gridDim.x and returns at once when *enable == 0, so a
+// conditional sort can be enqueued with a small grid at the cost of a few empty launches.
 #pragma once
 #include "dofs_common.cuh"
 
@@ -45,27 +50,33 @@ DOFS_D u32 rs_block_excl_scan(u32 v, u32* s_warp /* >= 8 */, u32* total) {
 }
 
 // tile_hist layout: [frame][digit][tile]
+template <typename K>
 __global__ void __launch_bounds__(RS_THREADS)
-k_radix_hist(const u64* __restrict__ keys, size_t frame_stride, u32* __restrict__ tile_hist, int n, int shift,
-             int num_tiles) {
+k_radix_hist(const K* __restrict__ keys, size_t frame_stride, u32* __restrict__ tile_hist, int n, int shift,
+             int num_tiles, const int* __restrict__ enable) {
+    if (enable && *enable == 0) return;
     __shared__ u32 s_hist[RS_BINS];
-    const int tile = blockIdx.x, frame = blockIdx.y;
+    const int frame = blockIdx.y;
     keys += (size_t)frame * frame_stride;
-    s_hist[threadIdx.x] = 0;
-    __syncthreads();
-    const int base = tile * RS_TILE;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        s_hist[threadIdx.x] = 0;
+        __syncthreads();
+        const int base = tile * RS_TILE;
 #pragma unroll
-    for (int i = 0; i < RS_ITEMS; ++i) {
-        int idx = base + i * RS_THREADS + threadIdx.x;
-        if (idx < n) atomicAdd(&s_hist[(u32)(keys[idx] >> shift) & 255u], 1u);
+        for (int i = 0; i < RS_ITEMS; ++i) {
+            int idx = base + i * RS_THREADS + threadIdx.x;
+            if (idx < n) atomicAdd(&s_hist[(u32)(keys[idx] >> shift) & 255u], 1u);
+        }
+        __syncthreads();
+        tile_hist[((size_t)frame * RS_BINS + threadIdx.x) * num_tiles + tile] = s_hist[threadIdx.x];
+        __syncthreads();
     }
-    __syncthreads();
-    tile_hist[((size_t)frame * RS_BINS + threadIdx.x) * num_tiles + tile] = s_hist[threadIdx.x];
 }
 
 // grid (256 digits, frames): exclusive scan of row [digit][0..num_tiles) in place; digit_tot[frame][digit]
 __global__ void __launch_bounds__(RS_THREADS)
-k_radix_scan(u32* __restrict__ tile_hist, u32* __restrict__ digit_tot, int num_tiles) {
+k_radix_scan(u32* __restrict__ tile_hist, u32* __restrict__ digit_tot, int num_tiles, const int* __restrict__ enable) {
+    if (enable && *enable == 0) return;
     __shared__ u32 s_warp[RS_WARPS];
     const int digit = blockIdx.x, frame = blockIdx.y;
     u32* row = tile_hist + ((size_t)frame * RS_BINS + digit) * num_tiles;
@@ -81,96 +92,105 @@ k_radix_scan(u32* __restrict__ tile_hist, u32* __restrict__ digit_tot, int num_t
     if (threadIdx.x == 0) digit_tot[frame * RS_BINS + digit] = carry;
 }
 
-// dynamic shared memory: keys[RS_TILE] u64 | vals[RS_TILE] u32 | whist[RS_WARPS][256] | dlocal[256] | dbase[256] | warp[8]
-#define RS_SMEM_BYTES (RS_TILE * 8 + RS_TILE * 4 + RS_WARPS * RS_BINS * 4 + RS_BINS * 4 * 2 + 64)
+// dynamic shared memory: keys[RS_TILE] | vals[RS_TILE] u32 | whist[RS_WARPS][256] | dlocal[256] | dbase[256] | warp[8]
+template <typename K>
+constexpr int rs_smem_bytes() {
+    return RS_TILE * (int)sizeof(K) + RS_TILE * 4 + RS_WARPS * RS_BINS * 4 + RS_BINS * 4 * 2 + 64;
+}
 
+template <typename K>
 __global__ void __launch_bounds__(RS_THREADS)
-k_radix_scatter(const u64* __restrict__ keys_in, const u32* __restrict__ vals_in, u64* __restrict__ keys_out,
+k_radix_scatter(const K* __restrict__ keys_in, const u32* __restrict__ vals_in, K* __restrict__ keys_out,
                 u32* __restrict__ vals_out, size_t frame_stride, const u32* __restrict__ tile_offs,
-                const u32* __restrict__ digit_tot, int n, int shift, int num_tiles, int iota_vals) {
+                const u32* __restrict__ digit_tot, int n, int shift, int num_tiles, int iota_vals,
+                const int* __restrict__ enable) {
+    if (enable && *enable == 0) return;
     extern __shared__ __align__(16) unsigned char rs_smem[];
-    u64* s_keys = reinterpret_cast<u64*>(rs_smem);
-    u32* s_vals = reinterpret_cast<u32*>(rs_smem + RS_TILE * 8);
+    K* s_keys = reinterpret_cast<K*>(rs_smem);
+    u32* s_vals = reinterpret_cast<u32*>(rs_smem + RS_TILE * sizeof(K));
     u32* s_whist = s_vals + RS_TILE;           // [warp][digit]
     u32* s_dlocal = s_whist + RS_WARPS * RS_BINS;  // exclusive prefix of the digit inside this tile
     u32* s_dbase = s_dlocal + RS_BINS;             // global position of the tile's first element of the digit
     u32* s_warp = s_dbase + RS_BINS;
 
-    const int tile = blockIdx.x, frame = blockIdx.y, tid = threadIdx.x;
+    const int frame = blockIdx.y, tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
     keys_in += (size_t)frame * frame_stride;
     vals_in += (size_t)frame * frame_stride;
     keys_out += (size_t)frame * frame_stride;
     vals_out += (size_t)frame * frame_stride;
+    // global base of every digit (exclusive scan of the digit totals), the same for all tiles
+    const u32 gtot = digit_tot[frame * RS_BINS + tid];
+    const u32 gbase = rs_block_excl_scan(gtot, s_warp, nullptr);
 
-    for (int i = tid; i < RS_WARPS * RS_BINS; i += RS_THREADS) s_whist[i] = 0;
-    __syncthreads();
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int i = tid; i < RS_WARPS * RS_BINS; i += RS_THREADS) s_whist[i] = 0;
+        __syncthreads();
 
-    // warp-striped load: element order inside the tile is (warp, item, lane) == memory order
-    const int wbase = tile * RS_TILE + warp * (32 * RS_ITEMS);
-    u64 key[RS_ITEMS];
-    u32 val[RS_ITEMS];
-    u32 rnk[RS_ITEMS];
+        // warp-striped load: element order inside the tile is (warp, item, lane) == memory order
+        const int wbase = tile * RS_TILE + warp * (32 * RS_ITEMS);
+        K key[RS_ITEMS];
+        u32 val[RS_ITEMS];
+        u32 rnk[RS_ITEMS];
 #pragma unroll
-    for (int i = 0; i < RS_ITEMS; ++i) {
-        int idx = wbase + i * 32 + lane;
-        bool ok = idx < n;
-        key[i] = ok ? keys_in[idx] : ~0ull;
-        val[i] = ok ? (iota_vals ? (u32)idx : vals_in[idx]) : 0u;
-    }
-    u32* my_hist = s_whist + warp * RS_BINS;
-#pragma unroll
-    for (int i = 0; i < RS_ITEMS; ++i) {
-        int idx = wbase + i * 32 + lane;
-        bool ok = idx < n;
-        u32 d = ok ? ((u32)(key[i] >> shift) & 255u) : 256u;  // out-of-range lanes form their own group
-        u32 peers = __match_any_sync(0xffffffffu, d);
-        u32 below = __popc(peers & ((1u << lane) - 1u));
-        int leader = __ffs(peers) - 1;
-        u32 pre = 0;
-        if (lane == leader && ok) {
-            pre = my_hist[d];
-            my_hist[d] = pre + __popc(peers);
+        for (int i = 0; i < RS_ITEMS; ++i) {
+            int idx = wbase + i * 32 + lane;
+            bool ok = idx < n;
+            key[i] = ok ? keys_in[idx] : (K)~(K)0;
+            val[i] = ok ? (iota_vals ? (u32)idx : vals_in[idx]) : 0u;
         }
-        pre = __shfl_sync(0xffffffffu, pre, leader);
-        rnk[i] = pre + below;
-        __syncwarp();
-    }
-    __syncthreads();
-
-    // digit = tid: exclusive scan over the warps of this digit, tile total of the digit
-    u32 run = 0;
+        u32* my_hist = s_whist + warp * RS_BINS;
 #pragma unroll
-    for (int w = 0; w < RS_WARPS; ++w) {
-        u32 c = s_whist[w * RS_BINS + tid];
-        s_whist[w * RS_BINS + tid] = run;
-        run += c;
-    }
-    u32 tile_total;
-    u32 dl = rs_block_excl_scan(run, s_warp, &tile_total);
-    s_dlocal[tid] = dl;
-    u32 gtot = digit_tot[frame * RS_BINS + tid];
-    u32 gbase = rs_block_excl_scan(gtot, s_warp, nullptr);
-    s_dbase[tid] = gbase + tile_offs[((size_t)frame * RS_BINS + tid) * num_tiles + tile];
-    __syncthreads();
-
-#pragma unroll
-    for (int i = 0; i < RS_ITEMS; ++i) {
-        int idx = wbase + i * 32 + lane;
-        if (idx < n) {
-            u32 d = (u32)(key[i] >> shift) & 255u;
-            u32 pos = s_dlocal[d] + my_hist[d] + rnk[i];
-            s_keys[pos] = key[i];
-            s_vals[pos] = val[i];
+        for (int i = 0; i < RS_ITEMS; ++i) {
+            int idx = wbase + i * 32 + lane;
+            bool ok = idx < n;
+            u32 d = ok ? ((u32)(key[i] >> shift) & 255u) : 256u;  // out-of-range lanes form their own group
+            u32 peers = __match_any_sync(0xffffffffu, d);
+            u32 below = __popc(peers & ((1u << lane) - 1u));
+            int leader = __ffs(peers) - 1;
+            u32 pre = 0;
+            if (lane == leader && ok) {
+                pre = my_hist[d];
+                my_hist[d] = pre + __popc(peers);
+            }
+            pre = __shfl_sync(0xffffffffu, pre, leader);
+            rnk[i] = pre + below;
+            __syncwarp();
         }
-    }
-    __syncthreads();
-    for (u32 j = tid; j < tile_total; j += RS_THREADS) {
-        u64 k = s_keys[j];
-        u32 d = (u32)(k >> shift) & 255u;
-        u32 dst = s_dbase[d] + (j - s_dlocal[d]);
-        keys_out[dst] = k;
-        vals_out[dst] = s_vals[j];
+        __syncthreads();
+
+        // digit = tid: exclusive scan over the warps of this digit, tile total of the digit
+        u32 run = 0;
+#pragma unroll
+        for (int w = 0; w < RS_WARPS; ++w) {
+            u32 c = s_whist[w * RS_BINS + tid];
+            s_whist[w * RS_BINS + tid] = run;
+            run += c;
+        }
+        u32 tile_total;
+        u32 dl = rs_block_excl_scan(run, s_warp, &tile_total);
+        s_dlocal[tid] = dl;
+        s_dbase[tid] = gbase + tile_offs[((size_t)frame * RS_BINS + tid) * num_tiles + tile];
+        __syncthreads();
+
+#pragma unroll
+        for (int i = 0; i < RS_ITEMS; ++i) {
+            int idx = wbase + i * 32 + lane;
+            if (idx < n) {
+                u32 d = (u32)(key[i] >> shift) & 255u;
+                u32 pos = s_dlocal[d] + my_hist[d] + rnk[i];
+                s_keys[pos] = key[i];
+                s_vals[pos] = val[i];
+            }
+        }
+        __syncthreads();
+        for (u32 j = tid; j < tile_total; j += RS_THREADS) {
+            K k = s_keys[j];
+            u32 d = (u32)(k >> shift) & 255u;
+            u32 dst = s_dbase[d] + (j - s_dlocal[d]);
+            keys_out[dst] = k;
+            vals_out[dst] = s_vals[j];
+        }
+        __syncthreads();
     }
 }
-

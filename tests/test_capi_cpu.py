@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_layouts_match_header():
     assert ctypes.sizeof(capi.Box) == capi.BOX_DTYPE.itemsize == 216
-    assert ctypes.sizeof(capi.Stats) == capi.STATS_DTYPE.itemsize == 32
+    assert ctypes.sizeof(capi.Stats) == capi.STATS_DTYPE.itemsize == 40
     for name, _ in capi.Box._fields_:
         if name in capi.BOX_DTYPE.names:
             assert getattr(capi.Box, name).offset == capi.BOX_DTYPE.fields[name][1], name

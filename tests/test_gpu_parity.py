@@ -162,6 +162,30 @@ def test_sorted_edges_bitwise(dofs, port, seed, W, H, nb):
     assert np.array_equal(gs, s) and np.array_equal(ge, e)
 
 
+def near_tie_field(W, H, seed=0):
+    """Vertical neighbours differ by exactly 1 in y and by a tiny random amount in x: thousands of weights
+    1 + O(1e-8) that share their 32-bit prefix and differ only in the low mantissa bits."""
+    rng = np.random.default_rng(seed)
+    f = np.zeros((H, W, 2), np.float32)
+    f[..., 1] = np.arange(H, dtype=np.float32)[:, None]
+    f[..., 0] = (rng.random((H, W)) * 3e-4).astype(np.float32)
+    return f
+
+
+@pytest.mark.parametrize("W,H,fallback", [(24, 20, 0), (300, 200, 1)])
+def test_sorted_edges_long_prefix_runs(dofs, port, W, H, fallback):
+    """Runs of equal prefix longer than a thread repairs: shared-memory sort (<= 2048 edges) or, beyond that, the
+    full 64-bit radix sort enabled on the device."""
+    fb = near_tie_field(W, H)
+    s, e, w = port.build_graph(fb, True)
+    with dofs.Context(W, H) as c:
+        gs, ge, gw = c.edges_sorted(fb)
+        st = c.segment(fb, already_blurred=True)["stats"][0]
+    assert np.array_equal(gw.view(np.uint64), w.view(np.uint64))
+    assert np.array_equal(gs, s) and np.array_equal(ge, e)
+    assert st["sort_fallback"] == fallback
+
+
 def test_sorted_edges_reference_golden(dofs, golden_pair):
     g = golden_pair
     fb = g["flow_blurred"]
@@ -226,7 +250,7 @@ def test_segments_degenerate_fields(dofs, port):
     const = np.full((H, W, 2), 2.5, np.float32)                  # moving everywhere, still all ties
     ramp = np.zeros((H, W, 2), np.float32)
     ramp[..., 1] = np.linspace(0, 6, H, dtype=np.float32)[:, None]  # strictly ordered rows
-    run_and_compare(dofs, port, [zero, const, ramp], min_size=50)
+    run_and_compare(dofs, port, [zero, const, ramp, near_tie_field(W, H)], min_size=50)
 
 
 @pytest.mark.parametrize("name", ["golden_pair", "golden_synth"])
