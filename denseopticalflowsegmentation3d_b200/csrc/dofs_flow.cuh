@@ -479,82 +479,95 @@ k_update_matrices(const float* __restrict__ R, const float2* __restrict__ flow, 
 // solve, in double.  Block = 32x8 pixels; the M tile with its halo is staged in shared memory, the
 // vertical window sums are formed once per column and reused by the horizontal window.
 // ---------------------------------------------------------------------------------------------
-#define BX_TW 32
-#define BX_TH 16
-#define BX_THREADS 256
-#define BX_GROUP 8  // consecutive outputs one thread produces with a sliding window
+#define BS_COLS 64   // output columns per block
+#define BS_ROWS 64   // rows per block (one marching segment)
+#define BS_BATCH 8   // rows of vertical sums staged per horizontal phase
+#define BS_GROUP 8   // consecutive outputs one thread produces with a sliding horizontal window
 
-// Window sums are formed with sliding windows in double (first window summed directly, then
-// + entering - leaving), vertically per (column, channel) and horizontally per (row, channel, group
-// of BX_GROUP columns): ~3 shared-memory reads per output and channel instead of 15.
-__global__ void __launch_bounds__(BX_THREADS)
+// Each thread owns one (column, channel) of a strip of BS_COLS + 2m columns and marches down BS_ROWS
+// rows keeping the vertical window sum in a register (first window summed directly, then + entering
+// row - leaving row, in double): every M element is read straight from global memory / L1, coalesced
+// across the strip, with all the loads of a batch of rows in flight together — no halo rows are
+// re-staged.  Every BS_BATCH rows the vertical sums go through shared memory to the horizontal
+// sliding windows and the solve.
+__global__ void __launch_bounds__(640)
 k_box_solve(const float* __restrict__ M, float2* __restrict__ flow, int Wk, int Hk, int m /* winsize/2 */) {
     extern __shared__ __align__(16) unsigned char bx_smem[];
-    const int cols = BX_TW + 2 * m, rows = BX_TH + 2 * m;
-    const int cw = cols * 5;                                               // floats / doubles per tile row
-    float* s_m = reinterpret_cast<float*>(bx_smem);                        // [rows][cols][5] M tile with halo
-    double* s_h = reinterpret_cast<double*>(bx_smem);                      // [TH][TW][5] window sums (aliases s_m)
-    const size_t tile_bytes = ((size_t)rows * cw * 4 + 15) & ~(size_t)15, sum_bytes = (size_t)BX_TH * BX_TW * 5 * 8;
-    double* s_v = reinterpret_cast<double*>(bx_smem + (tile_bytes > sum_bytes ? tile_bytes : sum_bytes));  // [TH][cols][5]
+    const int cols = BS_COLS + 2 * m;
+    const int cw = cols * 5;
+    double* s_v = reinterpret_cast<double*>(bx_smem);   // [BS_BATCH][cols][5] vertical window sums
+    double* s_h = s_v + (size_t)BS_BATCH * cw;           // [BS_BATCH][BS_COLS][5] full window sums
     const int pair = blockIdx.z;
-    const int x0 = blockIdx.x * BX_TW, y0 = blockIdx.y * BX_TH;
+    const int x0 = blockIdx.x * BS_COLS;
+    const int y_begin = blockIdx.y * BS_ROWS, y_end = min(y_begin + BS_ROWS, Hk);
     const float* src = M + (size_t)pair * Wk * Hk * 5;
-    // stage the tile: consecutive threads read consecutive floats of a row (replicated borders by clamping)
-    for (int idx = threadIdx.x; idx < rows * cw; idx += BX_THREADS) {
-        const int ry = idx / cw, rem = idx - ry * cw;
-        const int cx = rem / 5, c = rem - cx * 5;
-        const int yy = min(max(y0 + ry - m, 0), Hk - 1);
-        const int xx = min(max(x0 + cx - m, 0), Wk - 1);
-        s_m[idx] = src[((size_t)yy * Wk + xx) * 5 + c];
+    const size_t pitch = (size_t)Wk * 5;
+    const int e = threadIdx.x;
+    const bool owner = e < cw;
+    const float* col = src;
+    if (owner) {
+        const int cx = e / 5, c = e - cx * 5;
+        col = src + (size_t)min(max(x0 + cx - m, 0), Wk - 1) * 5 + c;  // replicated border columns
     }
-    __syncthreads();
-    // vertical windows: one thread per (column, channel), sliding down the BX_TH rows
-    for (int e = threadIdx.x; e < cw; e += BX_THREADS) {
-        double s = 0;
-        for (int j = 0; j <= 2 * m; ++j) s += (double)s_m[j * cw + e];
-        s_v[e] = s;
-        for (int ty = 1; ty < BX_TH; ++ty) {
-            s += (double)s_m[(ty + 2 * m) * cw + e] - (double)s_m[(ty - 1) * cw + e];
-            s_v[ty * cw + e] = s;
-        }
-    }
-    __syncthreads();
-    // horizontal windows: one thread per (row, channel, group of columns); results over the dead M tile
-    for (int w = threadIdx.x; w < BX_TH * 5 * (BX_TW / BX_GROUP); w += BX_THREADS) {
-        const int c = w % 5, g = (w / 5) % (BX_TW / BX_GROUP), ty = w / (5 * (BX_TW / BX_GROUP));
-        const double* v = s_v + ty * cw + c;  // element of column cx at v[cx * 5]
-        const int xs = g * BX_GROUP;
-        double s = 0;
-        for (int i = 0; i <= 2 * m; ++i) s += v[(xs + i) * 5];
-        s_h[(ty * BX_TW + xs) * 5 + c] = s;
-        for (int k = 1; k < BX_GROUP; ++k) {
-            s += v[(xs + k + 2 * m) * 5] - v[(xs + k - 1) * 5];
-            s_h[(ty * BX_TW + xs + k) * 5 + c] = s;
-        }
-    }
-    __syncthreads();
+    double s = 0;
+    if (owner)
+        for (int j = -m; j <= m; ++j) s += (double)col[(size_t)min(max(y_begin + j, 0), Hk - 1) * pitch];
     const int bs = 2 * m + 1;
     const double scale = 1.0 / (double)(bs * bs);
-    for (int o = threadIdx.x; o < BX_TW * BX_TH; o += BX_THREADS) {
-        const int tx = o % BX_TW, ty = o / BX_TW;
-        const int x = x0 + tx, y = y0 + ty;
-        if (x >= Wk || y >= Hk) continue;
-        const double* h = s_h + (size_t)o * 5;
-        const double g11 = xdmul(h[0], scale), g12 = xdmul(h[1], scale), g22 = xdmul(h[2], scale);
-        const double h1 = xdmul(h[3], scale), h2 = xdmul(h[4], scale);
-        const double idet = xddiv(1.0, xdadd(xdsub(xdmul(g11, g22), xdmul(g12, g12)), 1e-3));
-        const float u = (float)xdmul(xdsub(xdmul(g11, h2), xdmul(g12, h1)), idet);
-        const float w = (float)xdmul(xdsub(xdmul(g22, h1), xdmul(g12, h2)), idet);
-        flow[((size_t)pair * Hk + y) * Wk + x] = make_float2(u, w);
+    for (int yb = y_begin; yb < y_end; yb += BS_BATCH) {
+        const int nb = min(BS_BATCH, y_end - yb);
+        if (owner) {
+            float vin[BS_BATCH], vout[BS_BATCH];
+#pragma unroll
+            for (int r = 0; r < BS_BATCH; ++r) {
+                const int y = yb + r;
+                vin[r] = col[(size_t)min(y + m, Hk - 1) * pitch];
+                vout[r] = col[(size_t)max(y - m - 1, 0) * pitch];
+            }
+#pragma unroll
+            for (int r = 0; r < BS_BATCH; ++r) {
+                if (r < nb) {
+                    if (yb + r != y_begin) s += (double)vin[r] - (double)vout[r];
+                    s_v[r * cw + e] = s;
+                }
+            }
+        }
+        __syncthreads();
+        for (int w = threadIdx.x; w < nb * 5 * (BS_COLS / BS_GROUP); w += blockDim.x) {
+            const int c = w % 5, g = (w / 5) % (BS_COLS / BS_GROUP), r = w / (5 * (BS_COLS / BS_GROUP));
+            const double* v = s_v + r * cw + c;  // column cx of the strip at v[cx * 5]
+            const int xs = g * BS_GROUP;
+            double t = 0;
+            for (int i = 0; i <= 2 * m; ++i) t += v[(xs + i) * 5];
+            s_h[(r * BS_COLS + xs) * 5 + c] = t;
+#pragma unroll
+            for (int k = 1; k < BS_GROUP; ++k) {
+                t += v[(xs + k + 2 * m) * 5] - v[(xs + k - 1) * 5];
+                s_h[(r * BS_COLS + xs + k) * 5 + c] = t;
+            }
+        }
+        __syncthreads();
+        for (int o = threadIdx.x; o < nb * BS_COLS; o += blockDim.x) {
+            const int tx = o % BS_COLS, r = o / BS_COLS;
+            const int x = x0 + tx, y = yb + r;
+            if (x >= Wk) continue;
+            const double* h = s_h + (size_t)o * 5;
+            const double g11 = xdmul(h[0], scale), g12 = xdmul(h[1], scale), g22 = xdmul(h[2], scale);
+            const double h1 = xdmul(h[3], scale), h2 = xdmul(h[4], scale);
+            const double idet = xddiv(1.0, xdadd(xdsub(xdmul(g11, g22), xdmul(g12, g12)), 1e-3));
+            const float u = (float)xdmul(xdsub(xdmul(g11, h2), xdmul(g12, h1)), idet);
+            const float w = (float)xdmul(xdsub(xdmul(g22, h1), xdmul(g12, h2)), idet);
+            flow[((size_t)pair * Hk + y) * Wk + x] = make_float2(u, w);
+        }
+        __syncthreads();
     }
 }
 
 inline size_t box_solve_smem(int m) {
-    const size_t cols = BX_TW + 2 * m, rows = BX_TH + 2 * m;
-    const size_t tile = (rows * cols * 5 * 4 + 15) & ~(size_t)15;
-    const size_t sums = (size_t)BX_TH * BX_TW * 5 * 8;
-    return (tile > sums ? tile : sums) + (size_t)BX_TH * cols * 5 * 8;
+    const size_t cols = BS_COLS + 2 * m;
+    return (size_t)BS_BATCH * cols * 5 * 8 + (size_t)BS_BATCH * BS_COLS * 5 * 8;
 }
+inline int box_solve_threads(int m) { return (((BS_COLS + 2 * m) * 5 + 31) / 32) * 32; }
 
 // ---------------------------------------------------------------------------------------------
 // driver: n pairs; images of pair p are gray0 + p*N and gray1 + p*N.  When gray1 == gray0 + N the
@@ -589,7 +602,7 @@ inline int farneback_run(FlowBuffers& fb, const u8* d_gray0, const u8* d_gray1, 
         const dim3 blk(256);
         const dim3 g_img((L.w + 31) / 32, (L.h + 7) / 8, imgs.count);
         const dim3 g_pair((L.w + 31) / 32, (L.h + 7) / 8, n);
-        const dim3 g_box((L.w + BX_TW - 1) / BX_TW, (L.h + BX_TH - 1) / BX_TH, n);
+        const dim3 g_box((L.w + BS_COLS - 1) / BS_COLS, (L.h + BS_ROWS - 1) / BS_ROWS, n);
         cur = (k == 0) ? d_flow_out : (prev == fb.flowA ? fb.flowB : fb.flowA);
         if (!prev) {
             if (cudaMemsetAsync(cur, 0, (size_t)n * L.w * L.h * sizeof(float2), stream) != cudaSuccess) return 3;
@@ -602,7 +615,7 @@ inline int farneback_run(FlowBuffers& fb, const u8* d_gray0, const u8* d_gray1, 
         k_update_matrices<<<g_pair, blk, 0, stream>>>(fb.R, cur, fb.M, L.w, L.h, ps);
         st->launches += 3;
         for (int it = 0; it < fb.cfg.iters; ++it) {
-            k_box_solve<<<g_box, BX_THREADS, bx_smem, stream>>>(fb.M, cur, L.w, L.h, m);
+            k_box_solve<<<g_box, box_solve_threads(m), bx_smem, stream>>>(fb.M, cur, L.w, L.h, m);
             st->launches++;
             if (it < fb.cfg.iters - 1) {
                 k_update_matrices<<<g_pair, blk, 0, stream>>>(fb.R, cur, fb.M, L.w, L.h, ps);
