@@ -36,7 +36,8 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=32, help="frame pairs per step per GPU")
+    ap.add_argument("--batch", type=int, default=64, help="frame pairs per step per GPU")
+    ap.add_argument("--contexts", type=int, default=2, help="contexts (streams) per GPU; each takes batch/contexts pairs of a step")
     ap.add_argument("--width", type=int, default=1920)
     ap.add_argument("--height", type=int, default=1080)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -236,6 +237,8 @@ def ncu_traffic_bytes(kernel):
 
 
 def ours(args):
+    import ctypes as C
+    import threading as th
     import torch
     import denseopticalflowsegmentation3d_b200 as dofs
     from denseopticalflowsegmentation3d_b200.capi import BOX_DTYPE, STATS_DTYPE
@@ -247,22 +250,32 @@ def ours(args):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
-    W, H, B, K, Wm = args.width, args.height, args.batch, args.steps, args.warmup
+    W, H, B, K, Wm, NC = args.width, args.height, args.batch, args.steps, args.warmup, args.contexts
+    assert B % NC == 0, "--batch must be a multiple of --contexts"
+    Bc = B // NC  # pairs per context per step
     N = W * H
     MAXB = 256
-    ctx = dofs.Context(W, H, max_pairs=B, device=local)
-    stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    # NC contexts = NC streams: the latency-bound phases of one sub-batch (merge-chain replay, late Boruvka levels)
+    # overlap the bandwidth-bound phases of the other.  Each context is driven through the plain C ABI.
+    ctxs = [dofs.Context(W, H, max_pairs=Bc, device=local) for _ in range(NC)]
+    streams = [torch.cuda.ExternalStream(c.stream, device=dev) for c in ctxs]
 
-    # this rank's block of the video: frames [rank*T, rank*T + T], T = B pairs per step; a few distinct steps, cycled
-    n_inputs = min(K + Wm, 4)
-    frames = [torch.empty((B + 1, H, W, 3), dtype=torch.uint8, device="cuda") for _ in range(n_inputs)]
-    for i, f in enumerate(frames):
-        ctx.synth_frames_dev(SEED, N_OBJECTS, (rank * (K + Wm) + i) * B, B + 1, f.data_ptr())
-    d_labels = torch.empty((B, H, W), dtype=torch.int32, device="cuda")
-    d_boxes = torch.empty((B, MAXB * BOX_DTYPE.itemsize), dtype=torch.uint8, device="cuda")
-    d_nbox = torch.empty((B,), dtype=torch.int32, device="cuda")
-    d_stats = torch.empty((B, STATS_DTYPE.itemsize), dtype=torch.uint8, device="cuda")
-    ctx.sync()
+    # this rank's block of the video, cut into steps of B pairs; context c takes pairs [c*Bc, (c+1)*Bc) of the step
+    n_inputs = min(K + Wm, 3)
+    frames, outs = [], []
+    for c, ctx in enumerate(ctxs):
+        fl = []
+        for i in range(n_inputs):
+            f = torch.empty((Bc + 1, H, W, 3), dtype=torch.uint8, device=dev)
+            ctx.synth_frames_dev(SEED, N_OBJECTS, (rank * (K + Wm) + i) * B + c * Bc, Bc + 1, f.data_ptr())
+            fl.append(f)
+        frames.append(fl)
+        outs.append(dict(labels=torch.empty((Bc, H, W), dtype=torch.int32, device=dev),
+                         boxes=torch.empty((Bc, MAXB * BOX_DTYPE.itemsize), dtype=torch.uint8, device=dev),
+                         nbox=torch.empty((Bc,), dtype=torch.int32, device=dev),
+                         stats=torch.empty((Bc, STATS_DTYPE.itemsize), dtype=torch.uint8, device=dev)))
+        ctx.sync()
 
     def barrier():
         torch.cuda.synchronize()
@@ -270,71 +283,120 @@ def ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step_dev(i):
-        ctx.process_dev(frames[i % n_inputs].data_ptr(), B + 1, d_labels.data_ptr(), d_boxes.data_ptr(), d_nbox.data_ptr(),
-                        MAXB, d_stats.data_ptr())
+    def step_dev(i):  # asynchronous: enqueue every context, no host wait
+        for c, ctx in enumerate(ctxs):
+            o = outs[c]
+            ctx.process_dev(frames[c][i % n_inputs].data_ptr(), Bc + 1, o["labels"].data_ptr(), o["boxes"].data_ptr(),
+                            o["nbox"].data_ptr(), MAXB, o["stats"].data_ptr())
 
-    ctx.set_timing(True)
+    def sync_all():
+        for ctx in ctxs:
+            ctx.sync()  # also validates the finished call (overflow / convergence)
+
     for i in range(Wm):
         step_dev(i)
-    stage_ms = {}
+        sync_all()
+
+    def enqueue(c, i):
+        o = outs[c]
+        ctxs[c].process_dev(frames[c][i % n_inputs].data_ptr(), Bc + 1, o["labels"].data_ptr(), o["boxes"].data_ptr(),
+                            o["nbox"].data_ptr(), MAXB, o["stats"].data_ptr())
+
+    # stagger the contexts by 1/NC of a step (once, untimed) so that the latency-bound tail of one sub-batch runs
+    # under the bandwidth-bound head of the next; nothing couples the streams afterwards, so the phase persists
+    torch.cuda.synchronize()
+    t_probe = time.perf_counter()
+    enqueue(0, Wm)
+    ctxs[0].sync()
+    alone_ms = 1e3 * (time.perf_counter() - t_probe)
     clocks = ClockSampler(local)
     barrier()
     clocks.start()
-    launches0 = ctx.launch_count
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record(stream)
-    for i in range(K):
-        step_dev(Wm + i)
-        for k, (ms, cnt) in ctx.timing().items():
-            a = stage_ms.setdefault(k, [0.0, 0])
+    launches0 = sum(c.launch_count for c in ctxs)
+    ev0 = [torch.cuda.Event(enable_timing=True) for _ in ctxs]
+    ev1 = [torch.cuda.Event(enable_timing=True) for _ in ctxs]
+    ctxs[0].set_timing(True)  # per-kernel CUDA events on context 0's stream, live in the timed region
+    for c in range(NC):
+        if c > 0:
+            with torch.cuda.stream(streams[c]):
+                torch.cuda._sleep(int(alone_ms * 1e-3 * c / NC * 1.9e9))
+        ev0[c].record(streams[c])
+    for i in range(K):  # every step of every context is enqueued without a host wait in between
+        for c in range(NC):
+            enqueue(c, Wm + 1 + i)
+            if i == K - 1:
+                ev1[c].record(streams[c])
+    sync_all()
+    stage_ms = {}
+    for k, (ms, cnt) in ctxs[0].timing().items():  # the marks of context 0's last step
+        stage_ms[k] = [ms * K, cnt * K]
+    barrier()
+    ctxs[0].set_timing(False)
+    clk = clocks.stop()
+    launches = sum(c.launch_count for c in ctxs) - launches0
+    ms_total = max(ev0[0].elapsed_time(e) for e in ev1)  # first start to last end (context 0 starts first)
+    n_boxes_dev = int(sum(int(o["nbox"].sum().item()) for o in outs))
+
+    # ---- the same kernels alone on the GPU (one context, nothing overlapping): the per-kernel roofline numbers
+    iso_ms = {}
+    ctxs[0].set_timing(True)
+    for i in range(max(2, min(K, 3))):
+        o = outs[0]
+        ctxs[0].process_dev(frames[0][i % n_inputs].data_ptr(), Bc + 1, o["labels"].data_ptr(), o["boxes"].data_ptr(),
+                            o["nbox"].data_ptr(), MAXB, o["stats"].data_ptr())
+        ctxs[0].sync()
+        for k, (ms, cnt) in ctxs[0].timing().items():
+            a = iso_ms.setdefault(k, [0.0, 0])
             a[0] += ms
             a[1] += cnt
-    ev1.record(stream)
+    ctxs[0].set_timing(False)
+
+    # ---- end to end through the host-pointer entry point: pinned frames in, labels + boxes out; one host thread per context
+    host = []
+    for c in range(NC):
+        hf = torch.empty((Bc + 1, H, W, 3), dtype=torch.uint8).pin_memory()
+        hf.copy_(frames[c][0])
+        host.append(dict(frames=hf, labels=torch.empty((Bc, H, W), dtype=torch.int32).pin_memory(),
+                         boxes=torch.empty((Bc, MAXB * BOX_DTYPE.itemsize), dtype=torch.uint8).pin_memory(),
+                         nbox=torch.empty((Bc,), dtype=torch.int32).pin_memory(),
+                         stats=torch.empty((Bc, STATS_DTYPE.itemsize), dtype=torch.uint8).pin_memory()))
+    errors = []
+
+    def host_calls(c, n_calls):
+        ctx, h = ctxs[c], host[c]
+        for _ in range(n_calls):
+            rc = ctx.L.dofs3d_process(ctx.h, C.c_void_p(h["frames"].data_ptr()), Bc + 1, C.c_void_p(h["labels"].data_ptr()),
+                                      C.c_void_p(h["boxes"].data_ptr()), C.c_void_p(h["nbox"].data_ptr()), MAXB,
+                                      C.c_void_p(h["stats"].data_ptr()))
+            if rc != 0:
+                errors.append((rc, ctx.L.dofs3d_last_error(ctx.h).decode()))
+                return
+
+    def host_steps(n_calls):
+        ts = [th.Thread(target=host_calls, args=(c, n_calls)) for c in range(NC)]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+        if errors:
+            raise dofs.DofsError(*errors[0])
+
+    host_steps(min(Wm, 2))
     barrier()
-    clk = clocks.stop()
-    launches = ctx.launch_count - launches0
-    ms_total = ev0.elapsed_time(ev1)
-    n_boxes_dev = int(d_nbox.sum().item())
-
-    # ---- end to end through the host-pointer entry point: pinned frames in, labels + boxes out
-    h_frames = torch.empty((B + 1, H, W, 3), dtype=torch.uint8).pin_memory()
-    h_frames.copy_(frames[0])
-    h_labels = torch.empty((B, H, W), dtype=torch.int32).pin_memory()
-    h_boxes = torch.empty((B, MAXB * BOX_DTYPE.itemsize), dtype=torch.uint8).pin_memory()
-    h_nbox = torch.empty((B,), dtype=torch.int32).pin_memory()
-    h_stats = torch.empty((B, STATS_DTYPE.itemsize), dtype=torch.uint8).pin_memory()
-    import ctypes as C
-
-    def step_host():
-        rc = ctx.L.dofs3d_process(ctx.h, C.c_void_p(h_frames.data_ptr()), B + 1, C.c_void_p(h_labels.data_ptr()),
-                                  C.c_void_p(h_boxes.data_ptr()), C.c_void_p(h_nbox.data_ptr()), MAXB,
-                                  C.c_void_p(h_stats.data_ptr()))
-        if rc != 0:
-            raise dofs.DofsError(rc, ctx.L.dofs3d_last_error(ctx.h).decode())
-
-    ctx.set_timing(False)
-    for _ in range(min(Wm, 2)):
-        step_host()
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
     t0 = time.perf_counter()
-    for _ in range(K):
-        step_host()
-    e1.record(stream)
+    host_steps(K)
+    torch.cuda.synchronize()
+    e2e_ms = 1e3 * (time.perf_counter() - t0)
     barrier()
-    e2e_wall_ms = 1e3 * (time.perf_counter() - t0)
-    e2e_ms = max(e0.elapsed_time(e1), e2e_wall_ms if world == 1 else e0.elapsed_time(e1))
-    n_boxes_host = int(h_nbox.sum().item())
-    h2d = (B + 1) * N * 3
+    n_boxes_host = int(sum(int(h["nbox"].sum().item()) for h in host))
+    h2d = NC * (Bc + 1) * N * 3
     d2h = B * N * 4 + B * MAXB * BOX_DTYPE.itemsize + B * 4 + B * STATS_DTYPE.itemsize
 
     # ---- max over ranks
-    t = torch.tensor([ms_total, e2e_ms, float(launches)], dtype=torch.float64, device="cuda")
+    t = torch.tensor([ms_total, e2e_ms, float(launches)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        counts = torch.tensor([n_boxes_dev], dtype=torch.int64, device="cuda")
+        counts = torch.tensor([n_boxes_dev], dtype=torch.int64, device=dev)
         gathered = [torch.zeros_like(counts) for _ in range(world)]
         dist.all_gather(gathered, counts)  # per-rank box counts to every rank over NCCL/NVLink (results, not data path)
         total_boxes = int(sum(int(g.item()) for g in gathered))
@@ -346,35 +408,51 @@ def ours(args):
         value = world * B * K / (ms_total / 1e3)
         e2e_value = world * B * K / (e2e_ms / 1e3)
         peak, peak_src = measured_peak_gbs()
-        # dominant kernel: the radix-sort scatter pass over the 4N edge slots of all B frames
-        # algorithmic bytes per launch: read (8 B key + 4 B payload) + write (8 + 4) per slot
-        slots = 4 * N * B
-        sc = stage_ms.get("edge_sort.scatter", [0.0, 0])
-        roof = None
-        if sc[1] > 0:
+        # dominant kernel: one radix pass (scatter) over the 4N edge slots of a sub-batch, 32-bit prefix key + 32-bit
+        # sequence number: algorithmic bytes per launch = read (4 + 4) + write (4 + 4) per slot
+        slots = 4 * N * Bc
+
+        def roof_of(stages):
+            sc = stages.get("edge_sort.scatter", [0.0, 0])
+            if sc[1] == 0:
+                return None
             ms_launch = sc[0] / sc[1]
-            achieved = slots * 24 / (ms_launch / 1e3) / 1e9
-            roof = {"bound": "hbm", "kernel": "k_radix_scatter (edge sort pass)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": ncu_traffic_bytes("k_radix_scatter"), "peak_source": peak_src,
-                    "algorithmic_bytes_per_launch": slots * 24, "ms_per_launch": ms_launch, "launches_timed": sc[1]}
+            achieved = slots * 16 / (ms_launch / 1e3) / 1e9
+            return {"achieved": achieved, "frac": achieved / peak, "ms_per_launch": ms_launch, "launches_timed": sc[1]}
+
+        live, iso = roof_of(stage_ms), roof_of(iso_ms)
+        roof = None
+        if live:
+            roof = {"bound": "hbm", "kernel": "k_radix_scatter<u32> (one 8-bit pass of the edge sort)", "achieved": live["achieved"],
+                    "peak": peak, "unit": "GB/s", "frac": live["frac"], "traffic": ncu_traffic_bytes("k_radix_scatter<u32>"),
+                    "peak_source": peak_src, "algorithmic_bytes_per_launch": slots * 16, "ms_per_launch": live["ms_per_launch"],
+                    "launches_timed": live["launches_timed"],
+                    "note": f"timed live in the timed region on context 0 while {NC - 1} other context(s) share the GPU",
+                    "alone_on_gpu": iso}
         stages = {k: round(v[0] / K, 4) for k, v in sorted(stage_ms.items(), key=lambda kv: -kv[1][0])}
+        n_iso = max(2, min(K, 3))
+        stages_iso = {k: round(v[0] / n_iso, 4) for k, v in sorted(iso_ms.items(), key=lambda kv: -kv[1][0])}
         whole_bytes = 1476 * N * B  # algorithmic HBM bytes per pixel per pair, whole path
+        cfg = workload_config(args, world)
+        cfg["contexts_per_gpu"] = NC
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32 flow / f64 edge weights / u64 keys", "data": "synthetic", "config": workload_config(args, world),
+            "dtype": "f32 flow / f64 edge weights / u32+u64 keys", "data": "synthetic", "config": cfg,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_ms / K, "api": "dofs3d_process (host pointers, pinned)"},
+                    "ms_per_step": e2e_ms / K, "api": f"dofs3d_process (host pointers, pinned), {NC} host thread(s), one per context"},
             "gpu_launches": int(t[2].item()), "clocks": clk, "roofline": roof,
             "whole_path": {"algorithmic_GBps": whole_bytes / (ms_total / K / 1e3) / 1e9,
                            "frac_of_peak": whole_bytes / (ms_total / K / 1e3) / 1e9 / peak,
                            "bytes_per_pixel_per_pair": 1476},
-            "stage_ms_per_step": stages, "boxes_found": total_boxes, "boxes_found_e2e_rank0": n_boxes_host,
-            "device_bytes": ctx.device_bytes,
+            "stage_ms_per_step_context0_live": stages, "stage_ms_per_call_alone": stages_iso,
+            "boxes_found": total_boxes, "boxes_found_e2e_rank0": n_boxes_host,
+            "device_bytes": sum(c.device_bytes for c in ctxs),
         }
         if world == 1 and not args.no_cpu_baseline:
             rows = cpu_sample_rows(H, 20.0)
-            ctx.close()
+            for c in ctxs:
+                c.close()
             r = run_cpu_reference(args, 1, rows, 1, 0)
             line["cpu_baseline"] = {
                 "value": r["pairs_per_s"], "unit": UNIT, "cores": 1, "kind": r["kind"],

@@ -667,6 +667,7 @@ int dofs3d_set_timing(dofs3d_ctx* ctx, int enabled) {
 
 int dofs3d_get_timing(dofs3d_ctx* ctx, const char** names, float* ms, int* counts, int cap) {
     if (!ctx) return DOFS3D_ERR_ARG;
+    timer_collect(ctx);  // waits for the stream; the timed call itself stays asynchronous
     int n = 0;
     for (auto& r : ctx->timer.result) {
         if (n >= cap) break;
@@ -717,7 +718,6 @@ int dofs3d_flow_dev(dofs3d_ctx* ctx, const uint8_t* d_gray0, const uint8_t* d_gr
     rc = flow_dev(ctx, d_gray0, d_gray1, 0, n_pairs, reinterpret_cast<float2*>(d_flow_out));
     if (rc) return rc;
     CK(cudaGetLastError());
-    timer_collect(ctx);
     return 0;
 }
 
@@ -770,7 +770,6 @@ int dofs3d_segment_dev(dofs3d_ctx* ctx, const float* d_flow, int already_blurred
     CK(cudaGetLastError());
     ctx->pending_pairs = n_pairs;
     ctx->pending_max_boxes = d_boxes_out ? max_boxes : -1;
-    timer_collect(ctx);
     return rc;
 }
 
@@ -791,7 +790,6 @@ int dofs3d_segment(dofs3d_ctx* ctx, const float* flow, int already_blurred, int 
         CK(cudaMemcpyAsync(flow_blurred_out, ctx->flow_blur, px * sizeof(float2), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaGetLastError());
-    timer_collect(ctx);
     return check_last_call(ctx, n_pairs, boxes_out ? max_boxes : -1);
 }
 
@@ -881,7 +879,6 @@ int dofs3d_process_dev(dofs3d_ctx* ctx, const uint8_t* d_bgr_frames, int n_frame
     CK(cudaGetLastError());
     ctx->pending_pairs = n;
     ctx->pending_max_boxes = d_boxes_out ? max_boxes : -1;
-    timer_collect(ctx);
     return rc;
 }
 
@@ -906,7 +903,6 @@ int dofs3d_process(dofs3d_ctx* ctx, const uint8_t* bgr_frames, int n_frames, int
     if (rc) return rc;
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaGetLastError());
-    timer_collect(ctx);
     return check_last_call(ctx, n, boxes_out ? max_boxes : -1);
 }
 
