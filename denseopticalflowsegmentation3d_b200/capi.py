@@ -48,11 +48,11 @@ assert BOX_DTYPE.itemsize == C.sizeof(Box) == 216, (BOX_DTYPE.itemsize, C.sizeof
 
 class Stats(C.Structure):
     _fields_ = [(k, C.c_int32) for k in ("n_edges", "n_merges", "n_levels", "n_candidates", "n_scored", "n_boxes",
-                                         "longest_chain", "final_root", "sort_fallback", "pad_")]
+                                         "longest_chain", "final_root", "sort_fallback", "replay_exact_chunks")]
 
 
 STATS_DTYPE = np.dtype([(k, "<i4") for k in ("n_edges", "n_merges", "n_levels", "n_candidates", "n_scored",
-                                             "n_boxes", "longest_chain", "final_root", "sort_fallback", "pad_")])
+                                             "n_boxes", "longest_chain", "final_root", "sort_fallback", "replay_exact_chunks")])
 
 # every symbol include/dofs3d.h declares
 SYMBOLS = [

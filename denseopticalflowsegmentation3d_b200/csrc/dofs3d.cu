@@ -126,6 +126,14 @@ struct dofs3d_ctx {
     uint2* long_list = nullptr;  // chains longer than REPLAY_SHORT events, per wave
     int* long_count = nullptr;
     int* repair_flags = nullptr;  // [0] number of long prefix runs, [1] need the full 64-bit edge sort
+    // per merge event (chain replay)
+    float4* ev_op = nullptr;
+    double* ev_inv = nullptr;
+    int *ev_size = nullptr, *ev_sa = nullptr;
+    ushort4* ev_bbox = nullptr;
+    float2 *ev_prod = nullptr, *ev_flow = nullptr;
+    TileAgg *tile_agg = nullptr, *tile_carry = nullptr;
+    int tiles_cap = 0;
     int list_cap = 0;
     int* rsize = nullptr;
     ushort4* rbbox = nullptr;
@@ -370,9 +378,23 @@ int segment_dev(dofs3d_ctx* ctx, const float* d_flow, int already_blurred, int n
     R.long_count = ctx->long_count;
     R.list_cap = ctx->list_cap;
     CK(cudaMemsetAsync(ctx->long_count, 0, sizeof(int) * (EV_MAX_WAVES + 1), ctx->stream));
+    R.ev_op = ctx->ev_op;
+    R.ev_inv = ctx->ev_inv;
+    R.ev_size = ctx->ev_size;
+    R.ev_bbox = ctx->ev_bbox;
+    R.ev_prod = ctx->ev_prod;
+    R.ev_sa = ctx->ev_sa;
+    R.ev_flow = ctx->ev_flow;
+    R.tile_agg = ctx->tile_agg;
+    R.tile_carry = ctx->tile_carry;
+    R.tiles_cap = ctx->tiles_cap;
     for (int wave = 1; wave <= levels; ++wave) {
-        LAUNCH(ctx, k_replay_short, gS, SEG_THREADS, 0, R, wave);
-        LAUNCH(ctx, k_replay_long, dim3(148 * 4), 32 * REPLAY_WARPS, 0, R, wave);
+        LAUNCH(ctx, k_replay_scan, gS, REPLAY_TILE, 0, R, wave);
+        LAUNCH(ctx, k_replay_carry, dim3(n), 32, 0, R, wave);
+        LAUNCH(ctx, k_replay_operands, gS, SEG_THREADS, 0, R, wave);
+        LAUNCH(ctx, k_replay_serial_short, gS, SEG_THREADS, 0, R, wave);
+        LAUNCH(ctx, k_replay_serial_long, dim3(148 * 4), 32 * REPLAY_WARPS, 0, R, wave);
+        LAUNCH(ctx, k_replay_gates, gS, SEG_THREADS, 0, R, wave);
     }
     mark(ctx, "chain_replay");
 
@@ -405,7 +427,7 @@ int segment_dev(dofs3d_ctx* ctx, const float* d_flow, int already_blurred, int n
     // counters -> stats record, on the device; a copy lands in pinned host memory for the host-pointer entry points
     LAUNCH(ctx, k_stats<dofs3d_stats>, dim3((n + 63) / 64), 64, 0, ctx->stats, B, ctx->counters + CNT_CAND * F,
            ctx->counters + CNT_SCORED * F, ctx->counters + CNT_BOXES * F, ctx->counters + CNT_CHAIN * F, n, N,
-           n_edges_of(W, H, ctx->seg.neighbors), levels, ctx->repair_flags + 1);
+           n_edges_of(W, H, ctx->seg.neighbors), levels, ctx->repair_flags + 1, ctx->long_count);
     CK(cudaMemcpyAsync(ctx->h_stats, ctx->stats, sizeof(dofs3d_stats) * n, cudaMemcpyDeviceToHost, ctx->stream));
     return 0;
 }
@@ -578,6 +600,16 @@ int dofs3d_create(dofs3d_ctx** out, int device, int width, int height, int max_p
     DA(ctx->long_list, (size_t)ctx->list_cap);
     DA(ctx->long_count, EV_MAX_WAVES + 1);
     DA(ctx->repair_flags, 2);
+    DA(ctx->ev_op, F * N);
+    DA(ctx->ev_inv, F * N);
+    DA(ctx->ev_size, F * N);
+    DA(ctx->ev_sa, F * N);
+    DA(ctx->ev_bbox, F * N);
+    DA(ctx->ev_prod, F * N);
+    DA(ctx->ev_flow, F * N);
+    ctx->tiles_cap = (int)((N + REPLAY_TILE - 1) / REPLAY_TILE + 1);
+    DA(ctx->tile_agg, F * ctx->tiles_cap);
+    DA(ctx->tile_carry, F * ctx->tiles_cap);
     DA(ctx->rsize, F * N);
     DA(ctx->rbbox, F * N);
     DA(ctx->rflow, F * N);

@@ -545,17 +545,61 @@ k_wave_starts(const u64* __restrict__ ev_key, int* __restrict__ wave_start /* [F
 // root — size, bounding box, and the ORDER-DEPENDENT float mean flow — then the size / row / move
 // gates of Forest::new_merge (graph.cpp:280-300); survivors are queued for lifting.
 //
-// A chain = the events won by one root, in time order.  Chains of one wave are independent (every
-// absorbed root has a lower final rank, so its state is final).  Two kernels per wave:
-//   k_replay_short  one thread per chain of at most REPLAY_SHORT events; longer chains are pushed
-//                   to a work list
-//   k_replay_long   one warp per listed chain, 32 events at a time: the lanes gather the absorbed
-//                   roots' states together (coalesced event reads, 32 gathers in flight, next chunk
-//                   prefetched), sizes and boxes come from warp scans, and only the 3-operation
-//                   float/double recurrence of the mean flow runs serially, fed by shuffles; each
-//                   lane then applies the gates to "its" event.
+// A chain = the events won by one root, in time order (contiguous in the sorted event array).  Chains
+// of one wave are independent (every absorbed root has a lower final rank, so its state is final).
+// Only the mean flow is a true recurrence; sizes and boxes are prefix sums / prefix min-max along the
+// chain.  So a wave is five steps:
+//   k_replay_scan      per event: gather the absorbed root's state; segmented scan (segments = chains)
+//                      of (size, box) inside tiles of 256 events; one aggregate per tile
+//   k_replay_carry     per frame: running (size, box) across the tiles of the wave
+//   k_replay_operands  per event: size before / after, box after, the operands of the recurrence
+//                      (loser_mean*loser_size, float(size_before), 1.0/size_after); chain heads are
+//                      classified short (<= REPLAY_SHORT events) or long (work list)
+//   k_replay_serial_*  the recurrence itself, nothing else: a thread per short chain, a warp per long
+//                      chain (operands stream in coalesced, prefetched, broadcast through shared memory)
+//   k_replay_gates     per event: gates, candidate queue; the last event of a chain stores the root's state
+// The only serial work left is ~10 instructions per event of the longest chain.
 // ---------------------------------------------------------------------------------------------
 #define REPLAY_SHORT 32
+#define REPLAY_TILE 256
+
+struct ScanTuple {  // absorbed size and bounding box since the start of the chain (or of the tile)
+    int s;
+    int x0, y0, x1, y1;
+};
+DOFS_D ScanTuple scan_combine(const ScanTuple& a, const ScanTuple& b) {  // a then b
+    ScanTuple r;
+    r.s = a.s + b.s;
+    r.x0 = min(a.x0, b.x0);
+    r.y0 = min(a.y0, b.y0);
+    r.x1 = max(a.x1, b.x1);
+    r.y1 = max(a.y1, b.y1);
+    return r;
+}
+DOFS_D ScanTuple scan_identity() {
+    ScanTuple r;
+    r.s = 0;
+    r.x0 = 65535;
+    r.y0 = 65535;
+    r.x1 = 0;
+    r.y1 = 0;
+    return r;
+}
+DOFS_D ScanTuple scan_shfl_up(const ScanTuple& t, int o) {
+    ScanTuple r;
+    r.s = __shfl_up_sync(0xffffffffu, t.s, o);
+    r.x0 = __shfl_up_sync(0xffffffffu, t.x0, o);
+    r.y0 = __shfl_up_sync(0xffffffffu, t.y0, o);
+    r.x1 = __shfl_up_sync(0xffffffffu, t.x1, o);
+    r.y1 = __shfl_up_sync(0xffffffffu, t.y1, o);
+    return r;
+}
+
+struct TileAgg {  // what a tile passes on: the scan value of its last event, and whether a chain started inside it
+    int s;
+    ushort4 bb;
+    int has_head;
+};
 
 struct ReplayArgs {
     const u64* ev_key;     // [F][N] sorted
@@ -564,6 +608,17 @@ struct ReplayArgs {
     int* rsize;            // [F][N]
     ushort4* rbbox;        // [F][N]
     float2* rflow;         // [F][N]
+    // per event (index = position in the sorted event array)
+    float4* ev_op;         // [F][N] (loser mean * loser size).xy, float(size before), float(size after)
+    double* ev_inv;        // [F][N] 1.0 / size after
+    int* ev_size;          // [F][N] k_replay_scan: tile-local scan | flag bit 31; k_replay_operands: size after
+    ushort4* ev_bbox;      // [F][N] tile-local scan, then box after
+    float2* ev_prod;       // [F][N] loser mean * loser size
+    int* ev_sa;            // [F][N] loser size
+    float2* ev_flow;       // [F][N] mean flow after the event
+    TileAgg* tile_agg;     // [F][tiles]
+    TileAgg* tile_carry;   // [F][tiles] state carried into the tile
+    int tiles_cap;
     Candidate* cand;       // [F][cand_cap]
     int* n_cand;           // [F]
     int* longest_chain;    // [F]
@@ -599,109 +654,231 @@ DOFS_D void push_candidate(const ReplayArgs& A, int frame, u32 root, u32 time, i
     A.cand[(size_t)frame * A.cand_cap + slot] = c;
 }
 
+#define EV_FLAG_STARTED 0x80000000u  // in ev_size after k_replay_scan: the event's chain started inside its tile
+
+__global__ void __launch_bounds__(REPLAY_TILE)
+k_replay_scan(ReplayArgs A, int wave) {
+    __shared__ ScanTuple s_tot[REPLAY_TILE / 32];
+    __shared__ int s_head[REPLAY_TILE / 32];
+    const int frame = blockIdx.y;
+    const int w0 = A.wave_start[frame * (EV_MAX_WAVES + 1) + wave];
+    const int w1 = A.wave_start[frame * (EV_MAX_WAVES + 1) + wave + 1];
+    const size_t fo = (size_t)frame * A.N;
+    const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+    const int n_tiles = (w1 - w0 + REPLAY_TILE - 1) / REPLAY_TILE;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int j = w0 + tile * REPLAY_TILE + threadIdx.x;
+        const bool valid = j < w1;
+        ScanTuple t = scan_identity();
+        bool head = false;
+        if (valid) {
+            const u64 key = A.ev_key[fo + j];
+            const u32 a = A.ev_loser[fo + j];
+            head = j == w0 || ev_chain(A.ev_key[fo + j - 1], A.eb) != ev_chain(key, A.eb);
+            const int sa = A.rsize[fo + a];
+            const float2 fa = A.rflow[fo + a];
+            const ushort4 ba = A.rbbox[fo + a];
+            const float fsa = (float)sa;
+            A.ev_prod[fo + j] = make_float2(xfmul(fa.x, fsa), xfmul(fa.y, fsa));
+            A.ev_sa[fo + j] = sa;
+            t.s = sa;
+            t.x0 = ba.x;
+            t.y0 = ba.y;
+            t.x1 = ba.z;
+            t.y1 = ba.w;
+        }
+        // segmented inclusive scan in the warp: `started` = a head at or before this lane (within the warp)
+        int started = head ? 1 : 0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const ScanTuple u = scan_shfl_up(t, o);
+            const int us = __shfl_up_sync(0xffffffffu, started, o);
+            if (lane >= o) {
+                if (!started) t = scan_combine(u, t);
+                started |= us;
+            }
+        }
+        if (lane == 31) {
+            s_tot[wrp] = t;
+            s_head[wrp] = started;
+        }
+        __syncthreads();
+        // carry from the previous warps of the tile
+        ScanTuple c = scan_identity();
+        int c_started = 0;
+        for (int w = 0; w < wrp; ++w) {
+            if (s_head[w]) {
+                c = s_tot[w];
+                c_started = 1;
+            } else {
+                c = scan_combine(c, s_tot[w]);
+            }
+        }
+        if (!started) t = scan_combine(c, t);
+        started |= c_started;
+        if (valid) {
+            A.ev_size[fo + j] = (int)((u32)t.s | (started ? EV_FLAG_STARTED : 0u));
+            A.ev_bbox[fo + j] = make_ushort4((u16)t.x0, (u16)t.y0, (u16)t.x1, (u16)t.y1);
+        }
+        if (threadIdx.x == REPLAY_TILE - 1) {  // padding lanes carry the identity, so this is the last valid event's value
+            TileAgg g;
+            g.s = t.s;
+            g.bb = make_ushort4((u16)t.x0, (u16)t.y0, (u16)t.x1, (u16)t.y1);
+            g.has_head = started;
+            A.tile_agg[(size_t)frame * A.tiles_cap + tile] = g;
+        }
+        __syncthreads();
+    }
+}
+
+// one warp per frame: the state carried into every tile of the wave (segmented exclusive scan of the tile aggregates)
+__global__ void __launch_bounds__(32)
+k_replay_carry(ReplayArgs A, int wave) {
+    const int frame = blockIdx.x, lane = threadIdx.x;
+    const int w0 = A.wave_start[frame * (EV_MAX_WAVES + 1) + wave];
+    const int w1 = A.wave_start[frame * (EV_MAX_WAVES + 1) + wave + 1];
+    const int n_tiles = (w1 - w0 + REPLAY_TILE - 1) / REPLAY_TILE;
+    ScanTuple carry = scan_identity();  // state after all tiles before this round
+    for (int base = 0; base < n_tiles; base += 32) {
+        const int t = base + lane;
+        ScanTuple v = scan_identity();
+        int started = 0;
+        if (t < n_tiles) {
+            const TileAgg g = A.tile_agg[(size_t)frame * A.tiles_cap + t];
+            v.s = g.s;
+            v.x0 = g.bb.x;
+            v.y0 = g.bb.y;
+            v.x1 = g.bb.z;
+            v.y1 = g.bb.w;
+            started = g.has_head;
+        }
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const ScanTuple u = scan_shfl_up(v, o);
+            const int us = __shfl_up_sync(0xffffffffu, started, o);
+            if (lane >= o) {
+                if (!started) v = scan_combine(u, v);
+                started |= us;
+            }
+        }
+        if (!started) v = scan_combine(carry, v);  // inclusive value after tile t
+        // exclusive: what enters tile t is the inclusive value after tile t-1
+        ScanTuple in = scan_shfl_up(v, 1);
+        if (lane == 0) in = carry;
+        if (t < n_tiles) {
+            TileAgg c;
+            c.s = in.s;
+            c.bb = make_ushort4((u16)in.x0, (u16)in.y0, (u16)in.x1, (u16)in.y1);
+            c.has_head = 0;
+            A.tile_carry[(size_t)frame * A.tiles_cap + t] = c;
+        }
+        carry.s = __shfl_sync(0xffffffffu, v.s, 31);
+        carry.x0 = __shfl_sync(0xffffffffu, v.x0, 31);
+        carry.y0 = __shfl_sync(0xffffffffu, v.y0, 31);
+        carry.x1 = __shfl_sync(0xffffffffu, v.x1, 31);
+        carry.y1 = __shfl_sync(0xffffffffu, v.y1, 31);
+    }
+}
+
 __global__ void __launch_bounds__(SEG_THREADS)
-k_replay_short(ReplayArgs A, int wave) {
+k_replay_operands(ReplayArgs A, int wave) {
+    const int frame = blockIdx.y;
+    const int w0 = A.wave_start[frame * (EV_MAX_WAVES + 1) + wave];
+    const int w1 = A.wave_start[frame * (EV_MAX_WAVES + 1) + wave + 1];
+    const size_t fo = (size_t)frame * A.N;
+    for (int j = w0 + blockIdx.x * blockDim.x + threadIdx.x; j < w1; j += gridDim.x * blockDim.x) {
+        const u64 key = A.ev_key[fo + j];
+        const u64 chain = ev_chain(key, A.eb);
+        const u32 r = ev_winner(key, A.eb);
+        const u32 raw = (u32)A.ev_size[fo + j];
+        int s = (int)(raw & ~EV_FLAG_STARTED);
+        ushort4 bb = A.ev_bbox[fo + j];
+        if (!(raw & EV_FLAG_STARTED)) {  // the chain started in an earlier tile
+            const TileAgg c = A.tile_carry[(size_t)frame * A.tiles_cap + (j - w0) / REPLAY_TILE];
+            s += c.s;
+            bb.x = min(bb.x, c.bb.x);
+            bb.y = min(bb.y, c.bb.y);
+            bb.z = max(bb.z, c.bb.z);
+            bb.w = max(bb.w, c.bb.w);
+        }
+        // the root's own state before this wave
+        const int s_after = s + A.rsize[fo + r];
+        const ushort4 rb = A.rbbox[fo + r];
+        bb.x = min(bb.x, rb.x);
+        bb.y = min(bb.y, rb.y);
+        bb.z = max(bb.z, rb.z);
+        bb.w = max(bb.w, rb.w);
+        const int sa = A.ev_sa[fo + j];
+        const float2 pr = A.ev_prod[fo + j];
+        A.ev_op[fo + j] = make_float4(pr.x, pr.y, (float)(s_after - sa), (float)s_after);
+        A.ev_inv[fo + j] = xddiv(1.0, (double)s_after);
+        A.ev_size[fo + j] = s_after;
+        A.ev_bbox[fo + j] = bb;
+        // long chains go to the warp kernel
+        const bool head = j == w0 || ev_chain(A.ev_key[fo + j - 1], A.eb) != chain;
+        if (head && j + REPLAY_SHORT < w1 && ev_chain(A.ev_key[fo + j + REPLAY_SHORT], A.eb) == chain) {
+            const int slot = atomicAdd(&A.long_count[wave], 1);
+            if (slot < A.list_cap) A.long_list[slot] = make_uint2((u32)frame, (u32)j);
+        }
+    }
+}
+
+// the recurrence of every chain of at most REPLAY_SHORT events: one thread per chain head
+__global__ void __launch_bounds__(SEG_THREADS)
+k_replay_serial_short(ReplayArgs A, int wave) {
     const int frame = blockIdx.y;
     const int w0 = A.wave_start[frame * (EV_MAX_WAVES + 1) + wave];
     const int w1 = A.wave_start[frame * (EV_MAX_WAVES + 1) + wave + 1];
     const size_t fo = (size_t)frame * A.N;
     const u64* key = A.ev_key + fo;
-    int longest = 0;
     for (int i = w0 + blockIdx.x * blockDim.x + threadIdx.x; i < w1; i += gridDim.x * blockDim.x) {
-        const u64 k0 = key[i];
-        const u64 chain = ev_chain(k0, A.eb);  // wave | winner
-        if (i > w0 && ev_chain(key[i - 1], A.eb) == chain) continue;  // not the head of its chain
-        if (i + REPLAY_SHORT < w1 && ev_chain(key[i + REPLAY_SHORT], A.eb) == chain) {  // long chain: a warp takes it
-            const int slot = atomicAdd(&A.long_count[wave], 1);
-            if (slot < A.list_cap) A.long_list[slot] = make_uint2((u32)frame, (u32)i);
-            continue;
-        }
-        const u32 r = ev_winner(k0, A.eb);
-        int s = A.rsize[fo + r];
-        float2 f = A.rflow[fo + r];
-        ushort4 bb = A.rbbox[fo + r];
-        const int y = (int)r / A.W;
-        const bool row_ok = !(y < A.H / 10);                                  // graph.cpp:288
-        const double move_min = xddiv((double)(3 * (y + 1)), (double)A.H);    // graph.cpp:296
+        const u64 chain = ev_chain(key[i], A.eb);
+        if (i > w0 && ev_chain(key[i - 1], A.eb) == chain) continue;                            // not a head
+        if (i + REPLAY_SHORT < w1 && ev_chain(key[i + REPLAY_SHORT], A.eb) == chain) continue;  // long
+        float2 f = A.rflow[fo + ev_winner(key[i], A.eb)];
         int j = i;
-        u64 kj = k0;
         for (;;) {
-            const u32 a = A.ev_loser[fo + j];
-            const int sa = A.rsize[fo + a];
-            const float2 fa = A.rflow[fo + a];
-            const ushort4 ba = A.rbbox[fo + a];
-            const float fsa = (float)sa, fsb = (float)s;
-            const double inv = xddiv(1.0, (double)(sa + s));
-            f.x = merge_mean(xfmul(fa.x, fsa), f.x, fsb, inv);
-            f.y = merge_mean(xfmul(fa.y, fsa), f.y, fsb, inv);
-            s += sa;
-            bb.x = min(bb.x, ba.x);
-            bb.y = min(bb.y, ba.y);
-            bb.z = max(bb.z, ba.z);
-            bb.w = max(bb.w, ba.w);
-            if (s >= A.min_size && row_ok) {
-                const double move = norm2d(f.x, f.y);
-                if (!(move < move_min)) push_candidate(A, frame, r, ev_time(kj, A.eb), s, f, bb);
-            }
+            const float4 o = A.ev_op[fo + j];
+            const double inv = A.ev_inv[fo + j];
+            f.x = merge_mean(o.x, f.x, o.z, inv);
+            f.y = merge_mean(o.y, f.y, o.z, inv);
+            A.ev_flow[fo + j] = f;
             ++j;
-            if (j >= w1) break;
-            kj = key[j];
-            if (ev_chain(kj, A.eb) != chain) break;
+            if (j >= w1 || ev_chain(key[j], A.eb) != chain) break;
         }
-        A.rsize[fo + r] = s;
-        A.rflow[fo + r] = f;
-        A.rbbox[fo + r] = bb;
-        longest = max(longest, j - i);
     }
-    if (longest) atomicMax(&A.longest_chain[frame], longest);
 }
 
-// REPLAY_Q chunks of 32 events form one software-pipeline stage: while stage t is replayed, the gathers
-// of stage t+1 and the event reads of stage t+2 are in flight (nothing is unpacked or tested before
-// its use, so the warp never waits at the issue point of a load).
-#define REPLAY_Q 4
+// The update without double arithmetic on the critical path.  With n = size after the merge (an integer
+// <= 2^24, exact in float) the reference's (float)((double)u * (1.0 / n)) equals the correctly rounded float
+// quotient u / n: u / n is never closer than 2^-49 (relative) to a midpoint between two floats when u has 24 and n
+// at most 25 significant bits, while u * RN(1/n) rounded to double is within 2^-52 of it, so both round to the same
+// float.  q0 = u*r with r = RN(1/n), then one correction by the residual (two FMAs) lands on that float except
+// when u / n is within ~2^-46 of a midpoint.  Nothing here is trusted: every result is re-derived with merge_mean
+// by the lane that owns the event (in parallel, off the serial path) and a chunk with any mismatch is replayed exactly.
+DOFS_D float merge_mean_fast(float fa_times_sa, float f, float sb, float nf, float r) {
+    const float u = xfadd(fa_times_sa, xfmul(f, sb));
+    const float q0 = xfmul(u, r);
+    return __fmaf_rn(__fmaf_rn(-nf, q0, u), r, q0);
+}
+
+// the recurrence of a long chain: one warp per chain, 32 events per round.  Operands arrive coalesced, one round
+// ahead, and are broadcast through shared memory in groups of REPLAY_G so that no step waits for them.
 #define REPLAY_WARPS 4
 #define REPLAY_G 8
 
-struct ReplayEvent {  // stage 0: straight reads of the sorted event arrays
-    u64 key;
-    u32 a;
-};
-struct ReplayOperand {  // stage 1: state of the absorbed root, raw
-    int sa;
-    float2 fa;
-    uint2 ba;  // ushort4 bounding box, still packed
-};
-
-DOFS_D ReplayEvent replay_read(const ReplayArgs& A, size_t fo, int j, int w1, u32 r) {
-    ReplayEvent e;
-    e.key = EV_KEY_NONE;
-    e.a = r;  // any valid index
-    if (j < w1) {
-        e.key = A.ev_key[fo + j];
-        e.a = A.ev_loser[fo + j];
-    }
-    return e;
-}
-
-DOFS_D ReplayOperand replay_gather(const ReplayArgs& A, size_t fo, u32 a) {
-    ReplayOperand o;
-    o.sa = A.rsize[fo + a];
-    o.fa = A.rflow[fo + a];
-    o.ba = *reinterpret_cast<const uint2*>(&A.rbbox[fo + a]);
-    return o;
-}
-
-__global__ void __launch_bounds__(32 * REPLAY_WARPS, 1)
-k_replay_long(ReplayArgs A, int wave) {
-    __shared__ float4 s_op[REPLAY_WARPS][32];   // (loser mean * loser size).xy, size before the event, unused
-    __shared__ double s_inv[REPLAY_WARPS][32];  // 1 / size after the event
-    __shared__ float2 s_f[REPLAY_WARPS][32];    // mean flow after the event
+__global__ void __launch_bounds__(32 * REPLAY_WARPS)
+k_replay_serial_long(ReplayArgs A, int wave) {
+    __shared__ float4 s_op[REPLAY_WARPS][32];
+    __shared__ float s_rcp[REPLAY_WARPS][32];
+    __shared__ double s_inv[REPLAY_WARPS][32];
+    __shared__ float2 s_f[REPLAY_WARPS][33];  // [0] = mean before the round, [k+1] = after event k
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int n_warps = (gridDim.x * blockDim.x) >> 5;
     const int n_list = min(A.long_count[wave], A.list_cap);
     const unsigned FULL = 0xffffffffu;
+    int redone = 0;
     for (int item = warp; item < n_list; item += n_warps) {
         const uint2 it = A.long_list[item];
         const int frame = (int)it.x, i0 = (int)it.y;
@@ -709,149 +886,134 @@ k_replay_long(ReplayArgs A, int wave) {
         const int w1 = A.wave_start[frame * (EV_MAX_WAVES + 1) + wave + 1];
         const u64 k0 = A.ev_key[fo + i0];
         const u64 chain = ev_chain(k0, A.eb);
-        const u32 r = ev_winner(k0, A.eb);
-        int s = A.rsize[fo + r];
-        float2 f = A.rflow[fo + r];
-        ushort4 bb = A.rbbox[fo + r];
-        const int y = (int)r / A.W;
-        const bool row_ok = !(y < A.H / 10);
-        const double move_min = xddiv((double)(3 * (y + 1)), (double)A.H);
+        float2 f = A.rflow[fo + ev_winner(k0, A.eb)];
         int j0 = i0;
-        bool more = true;
-        ReplayEvent ev_cur[REPLAY_Q], ev_nxt[REPLAY_Q], ev_far[REPLAY_Q];
-        ReplayOperand op_cur[REPLAY_Q], op_nxt[REPLAY_Q];
-#pragma unroll
-        for (int q = 0; q < REPLAY_Q; ++q) ev_nxt[q] = replay_read(A, fo, j0 + 32 * q + lane, w1, r);
-#pragma unroll
-        for (int q = 0; q < REPLAY_Q; ++q) ev_far[q] = replay_read(A, fo, j0 + 32 * (REPLAY_Q + q) + lane, w1, r);
-#pragma unroll
-        for (int q = 0; q < REPLAY_Q; ++q) op_nxt[q] = replay_gather(A, fo, ev_nxt[q].a);
-        while (more) {
-#pragma unroll
-            for (int q = 0; q < REPLAY_Q; ++q) {
-                ev_cur[q] = ev_nxt[q];
-                op_cur[q] = op_nxt[q];
-                ev_nxt[q] = ev_far[q];
-            }
-#pragma unroll
-            for (int q = 0; q < REPLAY_Q; ++q) op_nxt[q] = replay_gather(A, fo, ev_nxt[q].a);
-#pragma unroll
-            for (int q = 0; q < REPLAY_Q; ++q) ev_far[q] = replay_read(A, fo, j0 + 32 * (2 * REPLAY_Q + q) + lane, w1, r);
-#pragma unroll
-            for (int q = 0; q < REPLAY_Q; ++q) {
-                const bool valid = ev_cur[q].key != EV_KEY_NONE && ev_chain(ev_cur[q].key, A.eb) == chain;
-                const unsigned vmask = __ballot_sync(FULL, valid);  // valid lanes are a prefix (events are sorted)
-                const int n_valid = __popc(vmask);
-                if (n_valid == 0) {
-                    more = false;
-                    break;
-                }
-                const int sa = valid ? op_cur[q].sa : 0;
-                const float2 fa = op_cur[q].fa;
-                // sizes and boxes after every event: inclusive warp scans
-                int s_inc = sa;
-                int bx0 = valid ? (int)(op_cur[q].ba.x & 0xffffu) : 65535, by0 = valid ? (int)(op_cur[q].ba.x >> 16) : 65535;
-                int bx1 = valid ? (int)(op_cur[q].ba.y & 0xffffu) : 0, by1 = valid ? (int)(op_cur[q].ba.y >> 16) : 0;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int t = __shfl_up_sync(FULL, s_inc, o);
-                    const int t0 = __shfl_up_sync(FULL, bx0, o), t1 = __shfl_up_sync(FULL, by0, o);
-                    const int t2 = __shfl_up_sync(FULL, bx1, o), t3 = __shfl_up_sync(FULL, by1, o);
-                    if (lane >= o) {
-                        s_inc += t;
-                        bx0 = min(bx0, t0);
-                        by0 = min(by0, t1);
-                        bx1 = max(bx1, t2);
-                        by1 = max(by1, t3);
-                    }
-                }
-                const int s_after = s + s_inc, s_before = s_after - sa;
-                ushort4 bb_after;
-                bb_after.x = (u16)min((int)bb.x, bx0);
-                bb_after.y = (u16)min((int)bb.y, by0);
-                bb_after.z = (u16)max((int)bb.z, bx1);
-                bb_after.w = (u16)max((int)bb.w, by1);
-                const float fsa = (float)sa;
-                // operands of the recurrence, broadcast through shared memory
-                s_op[wib][lane] = make_float4(xfmul(fa.x, fsa), xfmul(fa.y, fsa), (float)s_before, 0.f);
-                s_inv[wib][lane] = xddiv(1.0, (double)max(s_after, 1));
-                __syncwarp();
-                // the serial part: mean flow after each event; every lane runs the same recurrence
-                if (n_valid == 32) {
-                    // groups of REPLAY_G events: operands of the next group are read from shared memory before the
-                    // results of this group are stored, so no step waits for a shared-memory round trip
-                    float4 o4[REPLAY_G];
-                    double kv[REPLAY_G];
-#pragma unroll
-                    for (int k = 0; k < REPLAY_G; ++k) {
-                        o4[k] = s_op[wib][k];
-                        kv[k] = s_inv[wib][k];
-                    }
-#pragma unroll
-                    for (int g = 0; g < 32 / REPLAY_G; ++g) {
-                        float4 n4[REPLAY_G];
-                        double nv[REPLAY_G];
-                        if (g + 1 < 32 / REPLAY_G) {
-#pragma unroll
-                            for (int k = 0; k < REPLAY_G; ++k) {
-                                n4[k] = s_op[wib][(g + 1) * REPLAY_G + k];
-                                nv[k] = s_inv[wib][(g + 1) * REPLAY_G + k];
-                            }
-                        }
-                        float2 fh[REPLAY_G];
-#pragma unroll
-                        for (int k = 0; k < REPLAY_G; ++k) {
-                            f.x = merge_mean(o4[k].x, f.x, o4[k].z, kv[k]);
-                            f.y = merge_mean(o4[k].y, f.y, o4[k].z, kv[k]);
-                            fh[k] = f;
-                        }
-#pragma unroll
-                        for (int k = 0; k < REPLAY_G; ++k) s_f[wib][g * REPLAY_G + k] = fh[k];
-                        if (g + 1 < 32 / REPLAY_G) {
-#pragma unroll
-                            for (int k = 0; k < REPLAY_G; ++k) {
-                                o4[k] = n4[k];
-                                kv[k] = nv[k];
-                            }
-                        }
-                    }
-                } else {
-                    for (int k = 0; k < n_valid; ++k) {
-                        const float4 o4 = s_op[wib][k];
-                        const double kinv = s_inv[wib][k];
-                        f.x = merge_mean(o4.x, f.x, o4.z, kinv);
-                        f.y = merge_mean(o4.y, f.y, o4.z, kinv);
-                        s_f[wib][k] = f;
-                    }
-                }
-                __syncwarp();
-                // gates of the event this lane holds
-                if (valid && s_after >= A.min_size && row_ok) {
-                    const float2 mine = s_f[wib][lane];
-                    const double move = norm2d(mine.x, mine.y);
-                    if (!(move < move_min))
-                        push_candidate(A, frame, r, ev_time(ev_cur[q].key, A.eb), s_after, mine, bb_after);
-                }
-                __syncwarp();
-                // carry = state after the last valid event
-                const int last = n_valid - 1;
-                s = __shfl_sync(FULL, s_after, last);
-                bb.x = (u16)__shfl_sync(FULL, (int)bb_after.x, last);
-                bb.y = (u16)__shfl_sync(FULL, (int)bb_after.y, last);
-                bb.z = (u16)__shfl_sync(FULL, (int)bb_after.z, last);
-                bb.w = (u16)__shfl_sync(FULL, (int)bb_after.w, last);
-                j0 += n_valid;
-                if (n_valid < 32) {
-                    more = false;
-                    break;
-                }
+        // round t+1 is loaded while round t is replayed
+        float4 n_op = make_float4(0.f, 0.f, 0.f, 1.f);
+        double n_inv = 1.0;
+        bool n_valid = false;
+        {
+            const int j = j0 + lane;
+            if (j < w1 && ev_chain(A.ev_key[fo + j], A.eb) == chain) {
+                n_valid = true;
+                n_op = A.ev_op[fo + j];
+                n_inv = A.ev_inv[fo + j];
             }
         }
-        if (lane == 0) {
+        for (;;) {
+            const float4 c_op = n_op;
+            const double c_inv = n_inv;
+            const bool c_valid = n_valid;
+            {
+                const int j = j0 + 32 + lane;
+                n_valid = false;
+                if (j < w1 && ev_chain(A.ev_key[fo + j], A.eb) == chain) {
+                    n_valid = true;
+                    n_op = A.ev_op[fo + j];
+                    n_inv = A.ev_inv[fo + j];
+                }
+            }
+            const int cnt = __popc(__ballot_sync(FULL, c_valid));  // valid lanes are a prefix
+            if (cnt == 0) break;
+            s_op[wib][lane] = c_op;
+            s_inv[wib][lane] = c_inv;
+            s_rcp[wib][lane] = __frcp_rn(c_op.w);
+            if (lane == 0) s_f[wib][0] = f;
+            __syncwarp();
+            // sizes beyond 2^24 are not exact in float: such chunks take the double path directly
+            bool exact_needed = cnt < 32 || __shfl_sync(FULL, c_op.w, 31) > 16777216.f;
+            const float2 f_start = f;
+            if (!exact_needed) {
+                float4 o4[REPLAY_G];
+                float rc[REPLAY_G];
+#pragma unroll
+                for (int k = 0; k < REPLAY_G; ++k) {
+                    o4[k] = s_op[wib][k];
+                    rc[k] = s_rcp[wib][k];
+                }
+#pragma unroll
+                for (int g = 0; g < 32 / REPLAY_G; ++g) {
+                    float4 n4[REPLAY_G];
+                    float nr[REPLAY_G];
+                    if (g + 1 < 32 / REPLAY_G) {
+#pragma unroll
+                        for (int k = 0; k < REPLAY_G; ++k) {
+                            n4[k] = s_op[wib][(g + 1) * REPLAY_G + k];
+                            nr[k] = s_rcp[wib][(g + 1) * REPLAY_G + k];
+                        }
+                    }
+                    float2 fh[REPLAY_G];
+#pragma unroll
+                    for (int k = 0; k < REPLAY_G; ++k) {
+                        f.x = merge_mean_fast(o4[k].x, f.x, o4[k].z, o4[k].w, rc[k]);
+                        f.y = merge_mean_fast(o4[k].y, f.y, o4[k].z, o4[k].w, rc[k]);
+                        fh[k] = f;
+                    }
+#pragma unroll
+                    for (int k = 0; k < REPLAY_G; ++k) s_f[wib][g * REPLAY_G + k + 1] = fh[k];
+                    if (g + 1 < 32 / REPLAY_G) {
+#pragma unroll
+                        for (int k = 0; k < REPLAY_G; ++k) {
+                            o4[k] = n4[k];
+                            rc[k] = nr[k];
+                        }
+                    }
+                }
+                __syncwarp();
+                // every lane re-derives "its" step exactly from the mean before it
+                const float2 before = s_f[wib][lane], after = s_f[wib][lane + 1];
+                const float ex = merge_mean(c_op.x, before.x, c_op.z, c_inv), ey = merge_mean(c_op.y, before.y, c_op.z, c_inv);
+                const bool same = __float_as_uint(ex) == __float_as_uint(after.x) && __float_as_uint(ey) == __float_as_uint(after.y);
+                if (__ballot_sync(FULL, same) != FULL) {
+                    exact_needed = true;
+                    f = f_start;
+                    ++redone;
+                }
+                __syncwarp();
+            }
+            if (exact_needed) {
+                for (int k = 0; k < cnt; ++k) {
+                    const float4 o = s_op[wib][k];
+                    const double inv = s_inv[wib][k];
+                    f.x = merge_mean(o.x, f.x, o.z, inv);
+                    f.y = merge_mean(o.y, f.y, o.z, inv);
+                    s_f[wib][k + 1] = f;
+                }
+                __syncwarp();
+            }
+            if (c_valid) A.ev_flow[fo + j0 + lane] = s_f[wib][lane + 1];
+            __syncwarp();
+            j0 += cnt;
+            if (cnt < 32) break;
+        }
+        if (lane == 0) atomicMax(&A.longest_chain[frame], j0 - i0);
+    }
+    if (lane == 0 && redone) atomicAdd(&A.long_count[0], redone);  // slot 0 is no wave's counter: chunks replayed exactly
+}
+
+// gates of every event (graph.cpp:280-300); the last event of a chain leaves the root's state behind
+__global__ void __launch_bounds__(SEG_THREADS)
+k_replay_gates(ReplayArgs A, int wave) {
+    const int frame = blockIdx.y;
+    const int w0 = A.wave_start[frame * (EV_MAX_WAVES + 1) + wave];
+    const int w1 = A.wave_start[frame * (EV_MAX_WAVES + 1) + wave + 1];
+    const size_t fo = (size_t)frame * A.N;
+    for (int j = w0 + blockIdx.x * blockDim.x + threadIdx.x; j < w1; j += gridDim.x * blockDim.x) {
+        const u64 key = A.ev_key[fo + j];
+        const u32 r = ev_winner(key, A.eb);
+        const int s = A.ev_size[fo + j];
+        const float2 f = A.ev_flow[fo + j];
+        const ushort4 bb = A.ev_bbox[fo + j];
+        const int y = (int)r / A.W;
+        if (s >= A.min_size && !(y < A.H / 10)) {                                   // graph.cpp:280, 288
+            const double move = norm2d(f.x, f.y);
+            if (!(move < xddiv((double)(3 * (y + 1)), (double)A.H)))                 // graph.cpp:296
+                push_candidate(A, frame, r, ev_time(key, A.eb), s, f, bb);
+        }
+        if (j + 1 >= w1 || ev_chain(A.ev_key[fo + j + 1], A.eb) != ev_chain(key, A.eb)) {
             A.rsize[fo + r] = s;
             A.rflow[fo + r] = f;
             A.rbbox[fo + r] = bb;
-            atomicMax(&A.longest_chain[frame], j0 - i0);
         }
     }
 }
@@ -1060,7 +1222,7 @@ k_lift_problems(const float2* __restrict__ dir, const int4* __restrict__ bbox, c
 template <typename StatsT>
 __global__ void k_stats(StatsT* __restrict__ out, BorState S, const int* __restrict__ n_cand, const int* __restrict__ n_scored,
                         const int* __restrict__ n_boxes, const int* __restrict__ longest_chain, int n_frames, int N,
-                        int n_edges, int max_levels, const int* __restrict__ need_full) {
+                        int n_edges, int max_levels, const int* __restrict__ need_full, const int* __restrict__ replay_redone) {
     const int f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= n_frames) return;
     const int levels = S.levels[f];
@@ -1075,6 +1237,6 @@ __global__ void k_stats(StatsT* __restrict__ out, BorState S, const int* __restr
     st.longest_chain = longest_chain[f];
     st.final_root = roots == 1 ? S.final_root[f] : -1;
     st.sort_fallback = *need_full;
-    st.pad_ = 0;
+    st.replay_exact_chunks = *replay_redone;
     out[f] = st;
 }

@@ -87,7 +87,8 @@ typedef struct {
     int32_t longest_chain; /* longest run of merges won by one root (serial depth of the replay) */
     int32_t final_root;    /* root id of the single set the forest ends as (Forest::find of any pixel) */
     int32_t sort_fallback; /* 1 if the batch needed the full 64-bit radix sort of the edges */
-    int32_t pad_;
+    int32_t replay_exact_chunks; /* batch-wide: 32-event chunks of the mean-flow replay whose fast path failed its
+                                    exact check and were replayed in double arithmetic */
 } dofs3d_stats;
 
 /* Fills *p with the reference's constants (homographies from get_mat/get_mat_upper, etc.). */

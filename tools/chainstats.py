@@ -6,6 +6,4 @@ c=d.Context(W,H,max_pairs=B)
 fr=torch.empty((B+1,H,W,3),dtype=torch.uint8,device='cuda')
 c.synth_frames_dev(1234,8,0,B+1,fr.data_ptr()); c.sync()
 out=c.process(fr.cpu().numpy(), want_labels=False)
-for s in out['stats']: print(dict(zip(s.dtype.names, s.tolist())))
-g=c.gray(fr.cpu().numpy()[:2]); f=c.flow(g[:1],g[1:]); fb=c.blur(f)[0]
-print("zero flow pixels", (np.abs(fb).sum(-1)==0).mean(), " |flow|<1e-3:", (np.abs(fb).max(-1)<1e-3).mean())
+for s in out['stats'][:3]: print(dict(zip(s.dtype.names, s.tolist())))
