@@ -335,6 +335,7 @@ int segment_dev(dofs3d_ctx* ctx, const float* d_flow, int already_blurred, int n
     for (int level = 0; level < levels; ++level) {
         LAUNCH(ctx, k_bor_pixel, gS, SEG_THREADS, 0, B, ctx->valsB, ctx->S, W, N, level);
         LAUNCH(ctx, k_bor_root, gS, SEG_THREADS, 0, B, ctx->valsA, ctx->S, W, N, level);
+        LAUNCH(ctx, k_bor_contract, gS, SEG_THREADS, 0, B, N, level);
         LAUNCH(ctx, k_bor_relabel, gS, SEG_THREADS, 0, B, N, level);
     }
     LAUNCH(ctx, k_bor_finish, gS, SEG_THREADS, 0, B, N, levels);
@@ -622,6 +623,9 @@ int dofs3d_create(dofs3d_ctx** out, int device, int width, int height, int max_p
     DA(ctx->cand_score, F * ctx->cand_cap);
     DA(ctx->counters, (size_t)CNT_KINDS * F);
     DA(ctx->bor.n_roots, (size_t)EV_MAX_WAVES * F);
+    DA(ctx->bor.mask, F * N);
+    DA(ctx->bor.roots[0], F * N);
+    DA(ctx->bor.roots[1], F * N);
     DA(ctx->bor.levels, F);
     ctx->bor.final_root = ctx->counters + CNT_FINAL * F;
     ctx->bor.F = (int)F;

@@ -326,29 +326,48 @@ k_prefix_repair_long(RepairArgs A) {
 // ---------------------------------------------------------------------------------------------
 // K9a  Boruvka levels.  No host round trip: the host enqueues the guaranteed bound of levels
 // (components at least halve per level) and every kernel of a level returns at once for a frame that
-// is already one component.  Kernels are grid-stride with a small fixed grid, so a level that has
-// nothing left to do costs a few microseconds.
+// is already one component.  Work shrinks with the forest:
+//   * the pixel kernel skips pixels whose back-edges have all become internal (one byte of mask each:
+//     an edge that became internal stays internal);
+//   * the root kernels run over the list of live roots, rebuilt every level;
+//   * `comp` (root of every pixel) is refreshed by one streaming pass per level: one hop through the
+//     `up` link its root received in the contraction.
+// Kernels are grid-stride with a small fixed grid, so a level with nothing left costs microseconds.
 // ---------------------------------------------------------------------------------------------
+#define EV_MAX_WAVES 32
+
 struct BorState {
-    u32* comp;       // [F][N] current component root of each pixel
+    u32* comp;       // [F][N] current root of each pixel
     u32* best;       // [F][N] per root: minimum rank of an outgoing edge in this level
     u32* newp;       // [F][N] per root: hook target in this level
     u32* loss_time;  // [F][N] per root id: sorted position of the edge at which it loses (INF: never)
-    u32* up;         // [F][N] per root id: root of the next-level component it is contracted into
+    u32* up;         // [F][N] per root id: root of the next-level component it is contracted into (itself while live)
     u8* lvl;         // [F][N] per root id: level at which it loses == its final union-find rank
+    u8* mask;        // [F][N] per pixel: which of its 4 back-edges still join different components
+    u32* roots[2];   // [F][N] live roots, ping-pong by level parity (level 0: every pixel, implicit)
     int* n_roots;    // [EV_MAX_WAVES][F] number of roots after each level (zeroed per call)
     int* levels;     // [F] number of levels the frame needed (written by k_bor_finish)
     int* final_root; // [F]
     int F;
 };
 
-#define EV_MAX_WAVES 32
-
 DOFS_D bool bor_done(const BorState& S, int level, int frame) {
     return level > 0 && S.n_roots[(level - 1) * S.F + frame] == 1;
 }
 
 #define GRID_STRIDE(p, N) for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < (N); p += gridDim.x * blockDim.x)
+
+// append to a per-frame list with one atomic per warp
+DOFS_D void list_append(u32* list, int* counter, bool want, u32 value) {
+    const unsigned m = __ballot_sync(__activemask(), want);
+    if (!want) return;
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(m) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(counter, __popc(m));
+    base = __shfl_sync(m, base, leader);
+    list[base + __popc(m & ((1u << lane) - 1u))] = value;
+}
 
 __global__ void __launch_bounds__(SEG_THREADS)
 k_bor_init(BorState S, const float2* __restrict__ flow, int* __restrict__ rsize, ushort4* __restrict__ rbbox,
@@ -363,6 +382,7 @@ k_bor_init(BorState S, const float2* __restrict__ flow, int* __restrict__ rsize,
         S.loss_time[g] = DOFS_INF32;
         S.up[g] = (u32)p;
         S.lvl[g] = 0;
+        S.mask[g] = 15;
         // Forest::Forest (graph.cpp:129-148): singleton sets
         rsize[g] = 1;
         const int y = p / W, x = p - y * W;
@@ -374,54 +394,62 @@ k_bor_init(BorState S, const float2* __restrict__ flow, int* __restrict__ rsize,
     }
 }
 
-// every edge whose endpoints are in different components offers its rank to both components
+// every edge whose endpoints are in different components offers its rank to both components.  Pixels are
+// visited in image order (neighbouring component ids share cache lines); a pixel whose four back-edges have all
+// become internal costs one byte of mask.
 __global__ void __launch_bounds__(SEG_THREADS)
 k_bor_pixel(BorState S, const u32* __restrict__ rank, size_t rank_stride, int W, int N, int level) {
     const int frame = blockIdx.y;
     if (bor_done(S, level, frame)) return;
-    const u32* comp = S.comp + (size_t)frame * N;
-    u32* best = S.best + (size_t)frame * N;
+    const size_t fo = (size_t)frame * N;
+    const u32* comp = S.comp + fo;
+    u32* best = S.best + fo;
     GRID_STRIDE(p, N) {
+        const u32 m = S.mask[fo + p];
+        if (m == 0) continue;
         const uint4 r4 = *reinterpret_cast<const uint4*>(rank + (size_t)frame * rank_stride + 4 * (size_t)p);
         const u32 r[4] = {r4.x, r4.y, r4.z, r4.w};
         const u32 cp = comp[p];
-        u32 mine = DOFS_INF32;
+        u32 mine = DOFS_INF32, m_new = 0;
 #pragma unroll
         for (int d = 0; d < 4; ++d) {
-            if (r[d] != DOFS_INF32) {
-                u32 cq = comp[edge_other(p, d, W)];
+            if (((m >> d) & 1u) && r[d] != DOFS_INF32) {
+                const u32 cq = comp[edge_other(p, d, W)];
                 if (cq != cp) {
+                    m_new |= 1u << d;
                     mine = min(mine, r[d]);
                     if (r[d] < best[cq]) atomicMin(&best[cq], r[d]);  // best only decreases: a stale read is safe
                 }
             }
         }
         if (mine != DOFS_INF32 && mine < best[cp]) atomicMin(&best[cp], mine);
+        if (m_new != m) S.mask[fo + p] = (u8)m_new;
     }
 }
 
-// per root: classify its pick (mutual winner / loser), record the loss
+// per live root: classify its pick (mutual winner / loser), record the loss
 __global__ void __launch_bounds__(SEG_THREADS)
 k_bor_root(BorState S, const u32* __restrict__ sorted_seq, size_t seq_stride, int W, int N, int level) {
     const int frame = blockIdx.y;
     if (bor_done(S, level, frame)) return;
     const size_t fo = (size_t)frame * N;
-    const u32* comp = S.comp + fo;
-    GRID_STRIDE(c, N) {
-        if (comp[c] != (u32)c) continue;
+    const u32* list = S.roots[level & 1] + fo;
+    const int count = level == 0 ? N : S.n_roots[(level - 1) * S.F + frame];
+    GRID_STRIDE(i, count) {
+        const u32 c = level == 0 ? (u32)i : list[i];
         const u32 t = S.best[fo + c];
         if (t == DOFS_INF32) {  // the last component
-            S.newp[fo + c] = (u32)c;
+            S.newp[fo + c] = c;
             continue;
         }
         const u32 seq = sorted_seq[(size_t)frame * seq_stride + t];
         const int s = (int)(seq >> 2);
         const int e = edge_other(s, (int)(seq & 3u), W);
-        const u32 cs = comp[s], ce = comp[e];
-        const u32 other = (cs == (u32)c) ? ce : cs;
+        const u32 cs = S.comp[fo + s], ce = S.comp[fo + e];
+        const u32 other = (cs == c) ? ce : cs;
         const bool mutual = S.best[fo + other] == t;
-        if (mutual && ce == (u32)c) {
-            S.newp[fo + c] = (u32)c;  // rank tie: the `end` side survives (graph.cpp:177-182, 210-213)
+        if (mutual && ce == c) {
+            S.newp[fo + c] = c;  // rank tie: the `end` side survives (graph.cpp:177-182, 210-213)
         } else {
             S.newp[fo + c] = other;
             S.loss_time[fo + c] = t;
@@ -430,9 +458,9 @@ k_bor_root(BorState S, const u32* __restrict__ sorted_seq, size_t seq_stride, in
     }
 }
 
-// contract: every pixel follows the hooks to the group root; losers remember it in `up`
+// contract: every live root follows the hooks to its group root; losers link to it in `up`, survivors form the next list
 __global__ void __launch_bounds__(SEG_THREADS)
-k_bor_relabel(BorState S, int N, int level) {
+k_bor_contract(BorState S, int N, int level) {
     const int frame = blockIdx.y;
     if (bor_done(S, level, frame)) {
         if (blockIdx.x == 0 && threadIdx.x == 0) S.n_roots[level * S.F + frame] = 1;
@@ -440,33 +468,49 @@ k_bor_relabel(BorState S, int N, int level) {
     }
     const size_t fo = (size_t)frame * N;
     volatile u32* newp = S.newp + fo;
-    int roots = 0;
+    const u32* list = S.roots[level & 1] + fo;
+    u32* next = S.roots[(level + 1) & 1] + fo;
+    const int count = level == 0 ? N : S.n_roots[(level - 1) * S.F + frame];
+    const int rounds = (count + gridDim.x * blockDim.x - 1) / (gridDim.x * blockDim.x);
+    for (int it = 0; it < rounds; ++it) {
+        const int i = (it * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x;
+        bool survives = false;
+        u32 c = 0;
+        if (i < count) {
+            c = level == 0 ? (u32)i : list[i];
+            // follow the hooks with path halving: concurrent writers only ever replace a pointer by one of its
+            // ancestors, so any interleaving still ends at the same root
+            u32 g = c;
+            for (;;) {
+                const u32 nx = newp[g];
+                if (nx == g) break;
+                const u32 nn = newp[nx];
+                if (nn == nx) {
+                    g = nx;
+                    break;
+                }
+                newp[g] = nn;
+                g = nn;
+            }
+            S.best[fo + c] = DOFS_INF32;
+            survives = g == c;
+            if (!survives) S.up[fo + c] = g;
+        }
+        list_append(next, &S.n_roots[level * S.F + frame], survives, c);
+    }
+}
+
+// every pixel follows its root's new link (one hop: the contraction stored the group root itself)
+__global__ void __launch_bounds__(SEG_THREADS)
+k_bor_relabel(BorState S, int N, int level) {
+    const int frame = blockIdx.y;
+    if (bor_done(S, level, frame)) return;
+    const size_t fo = (size_t)frame * N;
     GRID_STRIDE(p, N) {
         const u32 c = S.comp[fo + p];
-        // follow the hooks to the group root with path halving: concurrent writers only ever replace a
-        // pointer by one of its ancestors, so any interleaving still ends at the same root
-        u32 g = c;
-        for (;;) {
-            const u32 nx = newp[g];
-            if (nx == g) break;
-            const u32 nn = newp[nx];
-            if (nn == nx) {
-                g = nx;
-                break;
-            }
-            newp[g] = nn;
-            g = nn;
-        }
-        if (c == (u32)p) {  // p was a root in this level
-            S.best[fo + p] = DOFS_INF32;
-            if (g != (u32)p) S.up[fo + p] = g;
-            else ++roots;
-        }
+        const u32 g = S.up[fo + c];
         if (g != c) S.comp[fo + p] = g;
     }
-    // one atomic per warp
-    for (int o = 16; o > 0; o >>= 1) roots += __shfl_down_sync(0xffffffffu, roots, o);
-    if ((threadIdx.x & 31) == 0 && roots) atomicAdd(&S.n_roots[level * S.F + frame], roots);
 }
 
 // final root: it loses never; its chain is replayed in the last wave
@@ -483,7 +527,7 @@ k_bor_finish(BorState S, int N, int max_levels) {
         const size_t g = (size_t)frame * N + p;
         if (S.loss_time[g] == DOFS_INF32) {
             S.lvl[g] = (u8)max_levels;  // every frame's last chain runs in the same (last) wave, side by side
-            S.final_root[frame] = p;  // if the frame did not converge several pixels land here; n_roots says so
+            S.final_root[frame] = p;    // if the frame did not converge several pixels land here; n_roots says so
             S.levels[frame] = levels;
         }
     }
@@ -888,29 +932,39 @@ k_replay_serial_long(ReplayArgs A, int wave) {
         const u64 chain = ev_chain(k0, A.eb);
         float2 f = A.rflow[fo + ev_winner(k0, A.eb)];
         int j0 = i0;
-        // round t+1 is loaded while round t is replayed
-        float4 n_op = make_float4(0.f, 0.f, 0.f, 1.f);
-        double n_inv = 1.0;
-        bool n_valid = false;
-        {
-            const int j = j0 + lane;
-            if (j < w1 && ev_chain(A.ev_key[fo + j], A.eb) == chain) {
-                n_valid = true;
-                n_op = A.ev_op[fo + j];
-                n_inv = A.ev_inv[fo + j];
+        // rounds t+1 and t+2 are in flight while round t is replayed; a load never waits for the chain test of its
+        // event (operands of any event position are readable), the test happens when the round is consumed
+        float4 n_op[2];
+        double n_inv[2];
+        u64 n_key[2];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const int j = j0 + 32 * q + lane;
+            n_key[q] = EV_KEY_NONE;
+            n_op[q] = make_float4(0.f, 0.f, 0.f, 1.f);
+            n_inv[q] = 1.0;
+            if (j < w1) {
+                n_key[q] = A.ev_key[fo + j];
+                n_op[q] = A.ev_op[fo + j];
+                n_inv[q] = A.ev_inv[fo + j];
             }
         }
         for (;;) {
-            const float4 c_op = n_op;
-            const double c_inv = n_inv;
-            const bool c_valid = n_valid;
+            const float4 c_op = n_op[0];
+            const double c_inv = n_inv[0];
+            const bool c_valid = n_key[0] != EV_KEY_NONE && ev_chain(n_key[0], A.eb) == chain;
+            n_op[0] = n_op[1];
+            n_inv[0] = n_inv[1];
+            n_key[0] = n_key[1];
             {
-                const int j = j0 + 32 + lane;
-                n_valid = false;
-                if (j < w1 && ev_chain(A.ev_key[fo + j], A.eb) == chain) {
-                    n_valid = true;
-                    n_op = A.ev_op[fo + j];
-                    n_inv = A.ev_inv[fo + j];
+                const int j = j0 + 64 + lane;
+                n_key[1] = EV_KEY_NONE;
+                n_op[1] = make_float4(0.f, 0.f, 0.f, 1.f);
+                n_inv[1] = 1.0;
+                if (j < w1) {
+                    n_key[1] = A.ev_key[fo + j];
+                    n_op[1] = A.ev_op[fo + j];
+                    n_inv[1] = A.ev_inv[fo + j];
                 }
             }
             const int cnt = __popc(__ballot_sync(FULL, c_valid));  // valid lanes are a prefix
