@@ -309,6 +309,18 @@ int build_sorted_edges(dofs3d_ctx* ctx, int n) {
 
 enum { CNT_CAND = 0, CNT_CHAIN = 1, CNT_SCORED = 2, CNT_BOXES = 3, CNT_ROOTS = 4, CNT_FINAL = 5, CNT_KINDS = 6 };
 
+// GaussianBlur(flow, sigma) (segment.cpp:52): the fused tile kernel for the reference's 25 taps, two passes otherwise
+void blur_launch(dofs3d_ctx* ctx, const float2* src, float2* dst, int n) {
+    const int W = ctx->W, H = ctx->H;
+    if (ctx->taps.radius == 12) {
+        LAUNCH(ctx, k_blur_fused<12>, dim3((W + FB_T - 1) / FB_T, (H + FB_T - 1) / FB_T, n), 256, 0, src, dst, W, H, ctx->taps);
+    } else {
+        const dim3 gN = grid1(ctx->N, SEG_THREADS, n);
+        LAUNCH(ctx, k_blur_rows, gN, SEG_THREADS, 0, src, ctx->flow_tmp, W, H, ctx->taps);
+        LAUNCH(ctx, k_blur_cols, gN, SEG_THREADS, 0, ctx->flow_tmp, dst, W, H, ctx->taps);
+    }
+}
+
 // get_segmented_array (segment.cpp:34-72) for n frames whose (unblurred or blurred) flow is at d_flow.
 int segment_dev(dofs3d_ctx* ctx, const float* d_flow, int already_blurred, int n) {
     const int N = ctx->N, W = ctx->W, H = ctx->H, F = ctx->F;
@@ -317,8 +329,7 @@ int segment_dev(dofs3d_ctx* ctx, const float* d_flow, int already_blurred, int n
     if (already_blurred) {
         CK(cudaMemcpyAsync(ctx->flow_blur, src, (size_t)n * N * sizeof(float2), cudaMemcpyDeviceToDevice, ctx->stream));
     } else {
-        LAUNCH(ctx, k_blur_rows, gN, SEG_THREADS, 0, src, ctx->flow_tmp, W, H, ctx->taps);
-        LAUNCH(ctx, k_blur_cols, gN, SEG_THREADS, 0, ctx->flow_tmp, ctx->flow_blur, W, H, ctx->taps);
+        blur_launch(ctx, src, ctx->flow_blur, n);
     }
     mark(ctx, "flow_blur");
     int rc = build_sorted_edges(ctx, n);
@@ -783,8 +794,7 @@ int dofs3d_blur(dofs3d_ctx* ctx, const float* flow_in, int n_pairs, float* flow_
     const size_t px = (size_t)ctx->N * n_pairs;
     const dim3 gN = grid1(ctx->N, SEG_THREADS, n_pairs);
     CK(cudaMemcpyAsync(ctx->flow_in, flow_in, px * sizeof(float2), cudaMemcpyHostToDevice, ctx->stream));
-    LAUNCH(ctx, k_blur_rows, gN, SEG_THREADS, 0, ctx->flow_in, ctx->flow_tmp, ctx->W, ctx->H, ctx->taps);
-    LAUNCH(ctx, k_blur_cols, gN, SEG_THREADS, 0, ctx->flow_tmp, ctx->flow_blur, ctx->W, ctx->H, ctx->taps);
+    blur_launch(ctx, ctx->flow_in, ctx->flow_blur, n_pairs);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(flow_out, ctx->flow_blur, px * sizeof(float2), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));

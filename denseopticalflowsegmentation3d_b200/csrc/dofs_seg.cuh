@@ -98,6 +98,68 @@ k_blur_cols(const float2* __restrict__ src, float2* __restrict__ dst, int W, int
     dst[(size_t)frame * N + p] = make_float2(sx, sy);
 }
 
+// Fused form of the two passes above for the reference's radius (sigma 3 -> 25 taps): a 32x32 output tile
+// with its halo is staged once in shared memory (reflected borders resolved while loading), filtered along
+// rows into a second shared buffer and along columns into the output.  Each thread produces 4 consecutive
+// outputs from one run of 2R+4 shared-memory reads, with exactly the accumulation order of k_blur_rows /
+// k_blur_cols (so the results are bit-identical to the two-pass kernels).  HBM: 8 B read + 8 B written per pixel
+// (the halo comes out of L2) instead of 32.
+#define FB_T 32
+template <int R>
+__global__ void __launch_bounds__(256)
+k_blur_fused(const float2* __restrict__ src, float2* __restrict__ dst, int W, int H, BlurTaps taps) {
+    constexpr int C = FB_T + 2 * R;  // tile columns / rows with halo
+    __shared__ float2 s_in[C][C + 1];
+    __shared__ float2 s_h[C][FB_T + 1];
+    const int frame = blockIdx.z;
+    const int x0 = blockIdx.x * FB_T, y0 = blockIdx.y * FB_T;
+    const float2* img = src + (size_t)frame * W * H;
+    const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+    for (int ry = wrp; ry < C; ry += 8) {
+        const int yy = reflect101(y0 + ry - R, H);
+        const float2* row = img + (size_t)yy * W;
+        for (int cx = lane; cx < C; cx += 32) s_in[ry][cx] = row[reflect101(x0 + cx - R, W)];
+    }
+    __syncthreads();
+    // rows: (tile row, group of 4 columns)
+    for (int w = threadIdx.x; w < C * (FB_T / 4); w += 256) {
+        const int ry = w / (FB_T / 4), g = w % (FB_T / 4);
+        float2 v[2 * R + 4];
+#pragma unroll
+        for (int i = 0; i < 2 * R + 4; ++i) v[i] = s_in[ry][4 * g + i];
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+            float sx = 0.f, sy = 0.f;
+#pragma unroll
+            for (int k = 0; k <= 2 * R; ++k) {
+                sx = fmaf(taps.k[k], v[o + k].x, sx);
+                sy = fmaf(taps.k[k], v[o + k].y, sy);
+            }
+            s_h[ry][4 * g + o] = make_float2(sx, sy);
+        }
+    }
+    __syncthreads();
+    // columns: (tile column, group of 4 rows)
+    {
+        const int tx = threadIdx.x & 31, g = threadIdx.x >> 5;  // 8 groups of 4 rows
+        float2 v[2 * R + 4];
+#pragma unroll
+        for (int i = 0; i < 2 * R + 4; ++i) v[i] = s_h[4 * g + i][tx];
+        const int x = x0 + tx;
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+            float sx = 0.f, sy = 0.f;
+#pragma unroll
+            for (int k = 0; k <= 2 * R; ++k) {
+                sx = fmaf(taps.k[k], v[o + k].x, sx);
+                sy = fmaf(taps.k[k], v[o + k].y, sy);
+            }
+            const int y = y0 + 4 * g + o;
+            if (x < W && y < H) dst[(size_t)frame * W * H + (size_t)y * W + x] = make_float2(sx, sy);
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // K7  edge weights: build_graph's enumeration (graph.cpp:62-93) with diff (segment.cpp:20-32).
 // Slot 4*p+d of pixel p=(x,y): d=0 left (x-1,y), d=1 up (x,y-1), d=2 up-left (x-1,y-1),
