@@ -98,6 +98,8 @@ void dofs3d_default_params(dofs3d_params* p);
  * params == NULL selects dofs3d_default_params. */
 int dofs3d_create(dofs3d_ctx** out, int device, int width, int height, int max_pairs, const dofs3d_params* params);
 void dofs3d_destroy(dofs3d_ctx* ctx);
+/* Waits for the context's stream.  After an asynchronous (_dev) segment/process call it also reports that call's
+ * deferred conditions: DOFS3D_ERR_OVERFLOW (more boxes than max_boxes, candidate queue full), DOFS3D_ERR_INTERNAL. */
 int dofs3d_sync(dofs3d_ctx* ctx);
 const char* dofs3d_last_error(const dofs3d_ctx* ctx);
 /* Raw cudaStream_t of the context (as void*), for callers that time with CUDA events. */
