@@ -417,3 +417,30 @@ def test_cpp_host_shim_matches_oracle(dofs, port, golden_pair, tmp_path):
             h = (h * 1000003 + px) % 2147483647
         assert int(kv["hash"]) == h
         assert abs(float(kv["score"]) - e["score"]) <= TOL_ERR and abs(float(kv["orient"]) - e["sol"]["orient"]) <= TOL_YAW
+
+
+def test_4k_sixty_objects_against_oracle(dofs, port):
+    """BASELINE config 4: one synthetic 3840x2160 pair with 60 overlapping moving objects (stresses the union-find
+    replay and the per-cluster lifting): whole path on the GPU, then the oracle on the GPU's own blurred flow."""
+    import torch
+    from denseopticalflowsegmentation3d_b200.capi import box_pixel_sets
+    W, H = 3840, 2160
+    with dofs.Context(W, H, max_pairs=1) as c:
+        d = torch.empty((2, H, W, 3), dtype=torch.uint8, device="cuda")
+        c.synth_frames_dev(1234, 60, 0, 2, d.data_ptr())
+        c.sync()
+        whole = c.process(d.cpu().numpy(), max_boxes=4096)
+        gray = c.gray(d.cpu().numpy())
+        flow = c.flow(gray[:1], gray[1:])
+        out = c.segment(flow, already_blurred=False, want_blurred=True, max_boxes=4096)
+    del d
+    assert np.array_equal(whole["labels"], out["labels"]) and whole["boxes"][0].tobytes() == out["boxes"][0].tobytes()
+    st = out["stats"][0]
+    assert st["n_merges"] == W * H - 1 and st["sort_fallback"] == 0
+    boxes, labels = out["boxes"][0], out["labels"][0]
+    assert len(boxes) >= 20
+    persp, inv, up = port.get_mats()
+    res = port.segment(out["flow_blurred"][0], persp, inv, up)
+    compare_boxes(boxes, box_pixel_sets(labels, boxes), res["entries"], W)
+    assert st["n_candidates"] == res["counters"]["get_score"]
+    print("4K: %d boxes, %d candidates, longest chain %d, levels %d" % (len(boxes), st["n_candidates"], st["longest_chain"], st["n_levels"]))
