@@ -21,7 +21,7 @@
 #include "dofs_common.cuh"
 
 #define RS_THREADS 256
-#define RS_ITEMS 16
+#define RS_ITEMS 8
 #define RS_TILE (RS_THREADS * RS_ITEMS)
 #define RS_WARPS (RS_THREADS / 32)
 #define RS_BINS 256
@@ -47,6 +47,18 @@ DOFS_D u32 rs_block_excl_scan(u32 v, u32* s_warp /* >= 8 */, u32* total) {
     __syncthreads();
     if (total) *total = tot;
     return wsum + inc - v;
+}
+
+// lanes of the warp holding the same 9-bit value (8-bit digit + the "out of range" flag), by ballots: one vote per bit
+DOFS_D u32 rs_match9(u32 d) {
+    u32 peers = 0xffffffffu;
+#pragma unroll
+    for (int b = 0; b < 9; ++b) {
+        const bool bit = (d >> b) & 1u;
+        const u32 m = __ballot_sync(0xffffffffu, bit);
+        peers &= bit ? m : ~m;
+    }
+    return peers;
 }
 
 // tile_hist layout: [frame][digit][tile]
@@ -99,7 +111,7 @@ constexpr int rs_smem_bytes() {
 }
 
 template <typename K>
-__global__ void __launch_bounds__(RS_THREADS)
+__global__ void __launch_bounds__(RS_THREADS, 4)
 k_radix_scatter(const K* __restrict__ keys_in, const u32* __restrict__ vals_in, K* __restrict__ keys_out,
                 u32* __restrict__ vals_out, size_t frame_stride, const u32* __restrict__ tile_offs,
                 const u32* __restrict__ digit_tot, int n, int shift, int num_tiles, int iota_vals,
@@ -145,7 +157,7 @@ k_radix_scatter(const K* __restrict__ keys_in, const u32* __restrict__ vals_in, 
             int idx = wbase + i * 32 + lane;
             bool ok = idx < n;
             u32 d = ok ? ((u32)(key[i] >> shift) & 255u) : 256u;  // out-of-range lanes form their own group
-            u32 peers = __match_any_sync(0xffffffffu, d);
+            u32 peers = rs_match9(d);
             u32 below = __popc(peers & ((1u << lane) - 1u));
             int leader = __ffs(peers) - 1;
             u32 pre = 0;
