@@ -58,7 +58,7 @@ STATS_DTYPE = np.dtype([(k, "<i4") for k in ("n_edges", "n_merges", "n_levels", 
 SYMBOLS = [
     "dofs3d_default_params", "dofs3d_create", "dofs3d_destroy", "dofs3d_sync", "dofs3d_last_error", "dofs3d_stream",
     "dofs3d_launch_count", "dofs3d_device_bytes", "dofs3d_gray", "dofs3d_gray_dev", "dofs3d_flow", "dofs3d_blur",
-    "dofs3d_segment", "dofs3d_lift", "dofs3d_edges_sorted", "dofs3d_process", "dofs3d_process_dev",
+    "dofs3d_segment", "dofs3d_paint", "dofs3d_lift", "dofs3d_edges_sorted", "dofs3d_process", "dofs3d_process_dev",
     "dofs3d_segment_dev", "dofs3d_flow_dev", "dofs3d_synth_frames_dev", "dofs3d_set_timing", "dofs3d_get_timing",
 ]
 
@@ -98,6 +98,7 @@ def load_library():
     L.dofs3d_segment.argtypes = [vp, fp, C.c_int, C.c_int, ip, vp, ip, C.c_int, vp, fp]
     L.dofs3d_segment_dev.argtypes = [vp, fp, C.c_int, C.c_int, ip, vp, ip, C.c_int, vp]
     L.dofs3d_lift.argtypes = [vp, fp, ip, ip, C.c_int, vp]
+    L.dofs3d_paint.argtypes = [vp, C.c_int, C.c_double, ip, u8p]
     L.dofs3d_edges_sorted.argtypes = [vp, fp, ip, ip, vp]
     L.dofs3d_edges_sorted.restype = C.c_longlong
     L.dofs3d_process.argtypes = [vp, u8p, C.c_int, ip, vp, ip, C.c_int, vp]
@@ -191,6 +192,14 @@ class Context:
                                        _ptr(n_boxes), max_boxes, _ptr(stats), _ptr(blurred)))
         return {"labels": labels, "boxes": [boxes[i, :n_boxes[i]] for i in range(n)], "n_boxes": n_boxes,
                 "stats": stats, "flow_blurred": blurred}
+
+    def paint(self, n_pairs, min_score=0.7, bgr=None):
+        """Display semantics of plot_best_segments_simple for the results of the last segment/process call."""
+        painted = np.empty((n_pairs, self.H, self.W), np.int32)
+        if bgr is not None:
+            bgr = np.ascontiguousarray(bgr, np.uint8).reshape(n_pairs, self.H, self.W, 3)
+        self._ck(self.L.dofs3d_paint(self.h, n_pairs, float(min_score), _ptr(painted), _ptr(bgr)))
+        return painted, bgr
 
     def lift(self, direction, bbox, cls):
         d = np.ascontiguousarray(direction, np.float32).reshape(-1, 2)

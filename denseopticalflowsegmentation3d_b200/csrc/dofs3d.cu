@@ -839,6 +839,29 @@ int dofs3d_segment(dofs3d_ctx* ctx, const float* flow, int already_blurred, int 
     return check_last_call(ctx, n_pairs, boxes_out ? max_boxes : -1);
 }
 
+// ------------------------------------------------------------------------------------- paint
+int dofs3d_paint(dofs3d_ctx* ctx, int n_pairs, double min_score, int32_t* painted_out, uint8_t* bgr_inout) {
+    int rc = check_batch(ctx, n_pairs);
+    if (rc) return rc;
+    if (!painted_out) return DOFS3D_ERR_ARG;
+    if (n_pairs == 0) return 0;
+    const size_t px = (size_t)ctx->N * n_pairs;
+    int32_t* d_painted = reinterpret_cast<int32_t*>(ctx->sel_box);  // dead after the labels were written
+    u8* d_bgr = nullptr;
+    if (bgr_inout) {
+        if ((rc = ensure_flow(ctx))) return rc;
+        d_bgr = ctx->bgr;
+        CK(cudaMemcpyAsync(d_bgr, bgr_inout, px * 3, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    LAUNCH(ctx, k_paint<dofs3d_box>, grid1(ctx->N, SEG_THREADS, n_pairs), SEG_THREADS, 0, ctx->labels, ctx->boxes, ctx->box_cap,
+           ctx->N, min_score, d_painted, d_bgr);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(painted_out, d_painted, px * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    if (bgr_inout) CK(cudaMemcpyAsync(bgr_inout, d_bgr, px * 3, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------- lift
 int dofs3d_lift(dofs3d_ctx* ctx, const float* dir2, const int32_t* bbox4, const int32_t* cls, int n, dofs3d_box* out) {
     if (!ctx || !dir2 || !bbox4 || !cls || !out || n < 0) return DOFS3D_ERR_ARG;

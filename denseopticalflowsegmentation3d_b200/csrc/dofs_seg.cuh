@@ -1356,3 +1356,29 @@ __global__ void k_stats(StatsT* __restrict__ out, BorState S, const int* __restr
     st.replay_exact_chunks = *replay_redone;
     out[f] = st;
 }
+
+// What the reference's display loop leaves in every pixel (draw.cpp:120-147): segments are painted in ascending root
+// order when score > min_score, later ones over earlier ones — i.e. the containing box with the largest index wins.
+// painted[p] = that box index or -1; bgr (optional) = the class colour draw.cpp uses (cls 0/2 (0,255,255), cls 1 (0,255,0)).
+template <typename Box>
+__global__ void __launch_bounds__(SEG_THREADS)
+k_paint(const int* __restrict__ labels, const Box* __restrict__ boxes, int box_cap, int N, double min_score,
+        int* __restrict__ painted, u8* __restrict__ bgr) {
+    const int frame = blockIdx.y;
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= N) return;
+    const Box* bx = boxes + (size_t)frame * box_cap;
+    int b = labels[(size_t)frame * N + p], best = -1;
+    while (b >= 0) {
+        if (bx[b].score > min_score && b > best) best = b;
+        b = bx[b].parent_box;
+    }
+    painted[(size_t)frame * N + p] = best;
+    if (bgr && best >= 0) {
+        u8* px = bgr + ((size_t)frame * N + p) * 3;
+        const int cls = bx[best].cls;
+        px[0] = 0;
+        px[1] = 255;
+        px[2] = cls == 1 ? 0 : 255;
+    }
+}

@@ -135,6 +135,13 @@ int dofs3d_segment(dofs3d_ctx* ctx, const float* flow, int already_blurred, int 
                    dofs3d_box* boxes_out, int32_t* n_boxes_out, int max_boxes, dofs3d_stats* stats_out,
                    float* flow_blurred_out);
 
+/* What plot_best_segments_simple (draw.cpp:102-160) leaves in every pixel, for the n_pairs results of the LAST
+ * segment/process call of this context: segments are painted in ascending root order when score > min_score, later over
+ * earlier (draw.cpp:120-147).  painted_out [n][H][W] = index of the box whose colour the pixel ends with, -1 if unpainted.
+ * bgr_inout (optional, [n][H][W][3]) receives the class colour of draw.cpp:130-141 in the painted pixels (the "seg"
+ * image before blending); cube wireframes are not drawn. */
+int dofs3d_paint(dofs3d_ctx* ctx, int n_pairs, double min_score, int32_t* painted_out, uint8_t* bgr_inout);
+
 /* get_bottom_variants (lifting_3d.cpp:350-439) for n independent (direction, box, cls) problems:
  * dir2 [n][2], bbox4 [n][4] = xmin,ymin,xmax,ymax, cls [n].  out[i].score = (w_error+h_error)/2,
  * out[i].size = 1 when the solution has a rectangle, 0 otherwise (Solution::rectangle.empty()). */

@@ -444,3 +444,27 @@ def test_4k_sixty_objects_against_oracle(dofs, port):
     compare_boxes(boxes, box_pixel_sets(labels, boxes), res["entries"], W)
     assert st["n_candidates"] == res["counters"]["get_score"]
     print("4K: %d boxes, %d candidates, longest chain %d, levels %d" % (len(boxes), st["n_candidates"], st["longest_chain"], st["n_levels"]))
+
+
+def test_paint_matches_reference_display_order(dofs, golden_pair):
+    """draw.cpp:120-147: ascending root order, score > 0.7, later segments paint over earlier ones."""
+    g = golden_pair
+    fb = g["flow_blurred"]
+    H, W = fb.shape[:2]
+    with dofs.Context(W, H) as c:
+        out = c.segment(fb, already_blurred=True)
+        canvas = np.full((1, H, W, 3), 7, np.uint8)
+        painted, bgr = c.paint(1, 0.7, canvas)
+    boxes = out["boxes"][0]
+    expect = np.full(H * W, -1, np.int32)
+    colour = np.full((H * W, 3), 7, np.uint8)
+    off = g["pixel_offsets"]
+    for i in range(len(g["root"])):  # the unchanged reference's segments, ascending root
+        if g["score"][i] > 0.7:
+            px = g["pixels"][off[i]:off[i + 1]]
+            expect[px] = i
+            colour[px] = (0, 255, 0) if g["cls"][i] == 1 else (0, 255, 255)
+    assert [int(b["root"]) for b in boxes] == list(g["root"])
+    assert np.array_equal(painted[0].reshape(-1), expect)
+    assert np.array_equal(bgr[0].reshape(-1, 3), colour)
+    assert (expect >= 0).sum() > 1000
