@@ -119,6 +119,8 @@ struct dofs3d_ctx {
     u64 *keysA = nullptr, *keysB = nullptr;
     u32 *valsA = nullptr, *valsB = nullptr;
     u32 *tile_hist = nullptr, *digit_tot = nullptr;
+    u32* sweep_hist = nullptr;   // [2][F][RS_MAX_PASSES][256] digit histograms and bases of the one-sweep sorts
+    int* sweep_ticket = nullptr; // [RS_MAX_PASSES] tile tickets + [1] look-back time-out flag
     int num_tiles = 0;
     BorState bor;
     u32* win = nullptr;
@@ -261,6 +263,38 @@ int radix_sort(dofs3d_ctx* ctx, K* kA, u32* vA, K* kB, u32* vB, size_t stride, i
     return side;
 }
 
+// the same sort in one-sweep form: one histogram pass for all digits, then one scatter kernel per digit whose tiles
+// find their offsets by decoupled look-back (dofs_sort.cuh).  Used by the unconditional sorts.
+template <typename K>
+int radix_sort_onesweep(dofs3d_ctx* ctx, K* kA, u32* vA, K* kB, u32* vB, size_t stride, int n, int frames, int key_bits,
+                        bool iota, const char* tag_hist, const char* tag_scatter) {
+    const int tiles = (n + RS_TILE - 1) / RS_TILE;
+    const int passes = (key_bits + 7) / 8;
+    if (passes > RS_MAX_PASSES) return -1;
+    u32* ghist = ctx->sweep_hist;
+    u32* gbase = ghist + (size_t)ctx->F * RS_MAX_PASSES * RS_BINS;
+    cudaMemsetAsync(ghist, 0, sizeof(u32) * (size_t)frames * RS_MAX_PASSES * RS_BINS, ctx->stream);
+    cudaMemsetAsync(ctx->sweep_ticket, 0, sizeof(int) * (RS_MAX_PASSES + 1), ctx->stream);
+    LAUNCH(ctx, k_radix_hist_all<K>, dim3(std::max(1, std::min(tiles, 148 * 8 / frames)), frames), RS_THREADS, 0, kA, stride, ghist,
+           n, passes);
+    LAUNCH(ctx, k_radix_bases, dim3(passes, frames), RS_THREADS, 0, ghist, gbase);
+    mark(ctx, tag_hist);
+    int side = 0;
+    for (int p = 0; p < passes; ++p) {
+        const K* kin = side ? kB : kA;
+        const u32* vin = side ? vB : vA;
+        K* kout = side ? kA : kB;
+        u32* vout = side ? vA : vB;
+        cudaMemsetAsync(ctx->tile_hist, 0, sizeof(u32) * (size_t)frames * tiles * RS_BINS, ctx->stream);  // status words
+        LAUNCH(ctx, k_radix_onesweep<K>, dim3((unsigned)tiles * frames), RS_THREADS, rs_smem_bytes<K>(), kin, vin, kout, vout,
+               stride, gbase + (size_t)p * RS_BINS, ctx->tile_hist, ctx->sweep_ticket + p, ctx->sweep_ticket + RS_MAX_PASSES, n,
+               8 * p, tiles, frames, (iota && p == 0) ? 1 : 0);
+        mark(ctx, tag_scatter);
+        side ^= 1;
+    }
+    return side;
+}
+
 int n_edges_of(int W, int H, int neighbors) {
     return neighbors == 8 ? 4 * W * H - 3 * W - 3 * H + 2 : 2 * W * H - W - H;
 }
@@ -276,8 +310,8 @@ int build_sorted_edges(dofs3d_ctx* ctx, int n) {
     LAUNCH(ctx, k_edge_keys, grid1(N, SEG_THREADS, n), SEG_THREADS, 0, ctx->flow_blur, ctx->keysA, preA, ctx->S, ctx->W,
            ctx->H, ctx->seg.neighbors == 8 ? 1 : 0);
     mark(ctx, "edge_keys");
-    int side = radix_sort<u32>(ctx, preA, ctx->valsA, preB, ctx->valsB, ctx->S, S, n, 32, true, "edge_sort.hist",
-                               "edge_sort.scan", "edge_sort.scatter");
+    int side = radix_sort_onesweep<u32>(ctx, preA, ctx->valsA, preB, ctx->valsB, ctx->S, S, n, 32, true, "edge_sort.hist",
+                                        "edge_sort.scatter");
     if (side != 0) {
         ctx->err = "internal: odd number of sort passes";
         return DOFS3D_ERR_INTERNAL;
@@ -362,8 +396,12 @@ int segment_dev(dofs3d_ctx* ctx, const float* d_flow, int already_blurred, int n
     u32* evlB = reinterpret_cast<u32*>(ctx->keysB + (size_t)F * N);
     LAUNCH(ctx, k_event_keys, gS, SEG_THREADS, 0, B, ctx->win, evA, N, eb);
     mark(ctx, "event_keys");
-    int side = radix_sort<u64>(ctx, evA, evlA, evB, evlB, (size_t)N, N, n, eb.tb + eb.wb + 5, true, "event_sort.hist",
-                          "event_sort.scan", "event_sort.scatter");
+    int side = radix_sort_onesweep<u64>(ctx, evA, evlA, evB, evlB, (size_t)N, N, n, eb.tb + eb.wb + 5, true,
+                                        "event_sort.hist", "event_sort.scatter");
+    if (side < 0) {
+        ctx->err = "internal: event key too wide";
+        return DOFS3D_ERR_INTERNAL;
+    }
     const u64* ev_key = side ? evB : evA;
     const u32* ev_loser = side ? evlB : evlA;
     LAUNCH(ctx, k_wave_starts, gS, SEG_THREADS, 0, ev_key, ctx->wave_start, N, eb);
@@ -439,7 +477,8 @@ int segment_dev(dofs3d_ctx* ctx, const float* d_flow, int already_blurred, int n
     // counters -> stats record, on the device; a copy lands in pinned host memory for the host-pointer entry points
     LAUNCH(ctx, k_stats<dofs3d_stats>, dim3((n + 63) / 64), 64, 0, ctx->stats, B, ctx->counters + CNT_CAND * F,
            ctx->counters + CNT_SCORED * F, ctx->counters + CNT_BOXES * F, ctx->counters + CNT_CHAIN * F, n, N,
-           n_edges_of(W, H, ctx->seg.neighbors), levels, ctx->repair_flags + 1, ctx->long_count);
+           n_edges_of(W, H, ctx->seg.neighbors), levels, ctx->repair_flags + 1, ctx->long_count,
+           ctx->sweep_ticket + RS_MAX_PASSES);
     CK(cudaMemcpyAsync(ctx->h_stats, ctx->stats, sizeof(dofs3d_stats) * n, cudaMemcpyDeviceToHost, ctx->stream));
     return 0;
 }
@@ -449,7 +488,7 @@ int check_last_call(dofs3d_ctx* ctx, int n, int max_boxes) {
     for (int f = 0; f < n; ++f) {
         const dofs3d_stats& st = ctx->h_stats[f];
         if (st.final_root < 0) {
-            ctx->err = "internal: Boruvka did not converge";
+            ctx->err = "internal: Boruvka did not converge or a sort look-back timed out";
             return DOFS3D_ERR_INTERNAL;
         }
         if (st.n_candidates > ctx->cand_cap) {
@@ -600,6 +639,10 @@ int dofs3d_create(dofs3d_ctx** out, int device, int width, int height, int max_p
     ctx->num_tiles = (int)((S + RS_TILE - 1) / RS_TILE);
     DA(ctx->tile_hist, F * RS_BINS * ctx->num_tiles);
     DA(ctx->digit_tot, F * RS_BINS);
+    DA(ctx->sweep_hist, 2 * F * RS_MAX_PASSES * RS_BINS);
+    DA(ctx->sweep_ticket, RS_MAX_PASSES + 1);
+    CK(cudaFuncSetAttribute(k_radix_onesweep<u64>, cudaFuncAttributeMaxDynamicSharedMemorySize, rs_smem_bytes<u64>()));
+    CK(cudaFuncSetAttribute(k_radix_onesweep<u32>, cudaFuncAttributeMaxDynamicSharedMemorySize, rs_smem_bytes<u32>()));
     DA(ctx->bor.comp, F * N);
     DA(ctx->bor.best, F * N);
     DA(ctx->bor.newp, F * N);

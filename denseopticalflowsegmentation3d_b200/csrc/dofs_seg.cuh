@@ -1338,7 +1338,8 @@ k_lift_problems(const float2* __restrict__ dir, const int4* __restrict__ bbox, c
 template <typename StatsT>
 __global__ void k_stats(StatsT* __restrict__ out, BorState S, const int* __restrict__ n_cand, const int* __restrict__ n_scored,
                         const int* __restrict__ n_boxes, const int* __restrict__ longest_chain, int n_frames, int N,
-                        int n_edges, int max_levels, const int* __restrict__ need_full, const int* __restrict__ replay_redone) {
+                        int n_edges, int max_levels, const int* __restrict__ need_full, const int* __restrict__ replay_redone,
+                        const int* __restrict__ sweep_timeout) {
     const int f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= n_frames) return;
     const int levels = S.levels[f];
@@ -1351,7 +1352,7 @@ __global__ void k_stats(StatsT* __restrict__ out, BorState S, const int* __restr
     st.n_scored = n_scored[f];
     st.n_boxes = n_boxes[f];
     st.longest_chain = longest_chain[f];
-    st.final_root = roots == 1 ? S.final_root[f] : -1;
+    st.final_root = (roots == 1 && *sweep_timeout == 0) ? S.final_root[f] : -1;  // -1: the call is reported as failed
     st.sort_fallback = *need_full;
     st.replay_exact_chunks = *replay_redone;
     out[f] = st;

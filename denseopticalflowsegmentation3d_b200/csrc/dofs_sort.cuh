@@ -206,3 +206,166 @@ k_radix_scatter(const K* __restrict__ keys_in, const u32* __restrict__ vals_in, 
         __syncthreads();
     }
 }
+
+
+// ---------------------------------------------------------------------------------------------
+// One-sweep variant (decoupled look-back) used by the unconditional sorts: the digit histograms of ALL passes are
+// taken in one read of the keys (k_radix_hist_all + k_radix_bases), and every scatter pass gets the position of its
+// tile among the tiles of its frame from a chained look-back over per-(tile, digit) status words instead of from a
+// separate histogram + scan pass:
+//   status word = flag (bits 31:30: 0 = not ready, 1 = tile aggregate, 2 = inclusive prefix) | count (30 bits)
+// Tiles take a ticket from one global counter (frame = ticket % frames, tile = ticket / frames), so a tile only ever
+// waits for tiles that started before it, and the tiles in flight are spread over all frames (short look-back chains).
+// Every spin is bounded: on a time-out *err is raised and the tile carries on with what it has (no hang).
+// ---------------------------------------------------------------------------------------------
+#define RS_FLAG_AGG 0x40000000u
+#define RS_FLAG_PREFIX 0x80000000u
+#define RS_COUNT_MASK 0x3FFFFFFFu
+#define RS_SPIN_LIMIT (1 << 22)
+#define RS_MAX_PASSES 8
+
+// ghist layout: [frame][pass][256]
+template <typename K>
+__global__ void __launch_bounds__(RS_THREADS)
+k_radix_hist_all(const K* __restrict__ keys, size_t frame_stride, u32* __restrict__ ghist, int n, int n_passes) {
+    __shared__ u32 s_hist[RS_MAX_PASSES * RS_BINS];
+    const int frame = blockIdx.y;
+    keys += (size_t)frame * frame_stride;
+    for (int i = threadIdx.x; i < n_passes * RS_BINS; i += RS_THREADS) s_hist[i] = 0;
+    __syncthreads();
+    for (int base = blockIdx.x * RS_TILE; base < n; base += gridDim.x * RS_TILE) {
+#pragma unroll
+        for (int i = 0; i < RS_ITEMS; ++i) {
+            const int idx = base + i * RS_THREADS + threadIdx.x;
+            if (idx < n) {
+                const K k = keys[idx];
+                for (int p = 0; p < n_passes; ++p) atomicAdd(&s_hist[p * RS_BINS + ((u32)(k >> (8 * p)) & 255u)], 1u);
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n_passes * RS_BINS; i += RS_THREADS) {
+        const u32 c = s_hist[i];
+        if (c) atomicAdd(&ghist[(size_t)frame * RS_MAX_PASSES * RS_BINS + i], c);
+    }
+}
+
+// grid (n_passes, frames): exclusive scan of the 256 digit totals -> first output position of every digit
+__global__ void __launch_bounds__(RS_THREADS)
+k_radix_bases(const u32* __restrict__ ghist, u32* __restrict__ gbase) {
+    __shared__ u32 s_warp[RS_WARPS];
+    const size_t o = ((size_t)blockIdx.y * RS_MAX_PASSES + blockIdx.x) * RS_BINS + threadIdx.x;
+    gbase[o] = rs_block_excl_scan(ghist[o], s_warp, nullptr);
+}
+
+template <typename K>
+__global__ void __launch_bounds__(RS_THREADS, 4)
+k_radix_onesweep(const K* __restrict__ keys_in, const u32* __restrict__ vals_in, K* __restrict__ keys_out,
+                 u32* __restrict__ vals_out, size_t frame_stride, const u32* __restrict__ gbase /* this pass: [frame][..] */,
+                 u32* __restrict__ status /* [frame][tile][256], zeroed */, int* __restrict__ ticket /* zeroed */,
+                 int* __restrict__ err, int n, int shift, int num_tiles, int frames, int iota_vals) {
+    extern __shared__ __align__(16) unsigned char rs_smem[];
+    K* s_keys = reinterpret_cast<K*>(rs_smem);
+    u32* s_vals = reinterpret_cast<u32*>(rs_smem + RS_TILE * sizeof(K));
+    u32* s_whist = s_vals + RS_TILE;               // [warp][digit]
+    u32* s_dlocal = s_whist + RS_WARPS * RS_BINS;  // exclusive prefix of the digit inside this tile
+    u32* s_dbase = s_dlocal + RS_BINS;             // global position of the tile's first element of the digit
+    u32* s_warp = s_dbase + RS_BINS;
+    __shared__ int s_ticket;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_ticket = atomicAdd(ticket, 1);
+    for (int i = tid; i < RS_WARPS * RS_BINS; i += RS_THREADS) s_whist[i] = 0;
+    __syncthreads();
+    const int frame = s_ticket % frames, tile = s_ticket / frames;
+    if (tile >= num_tiles) return;
+    keys_in += (size_t)frame * frame_stride;
+    vals_in += (size_t)frame * frame_stride;
+    keys_out += (size_t)frame * frame_stride;
+    vals_out += (size_t)frame * frame_stride;
+
+    // warp-striped load: element order inside the tile is (warp, item, lane) == memory order
+    const int wbase = tile * RS_TILE + warp * (32 * RS_ITEMS);
+    K key[RS_ITEMS];
+    u32 val[RS_ITEMS];
+    u32 rnk[RS_ITEMS];
+#pragma unroll
+    for (int i = 0; i < RS_ITEMS; ++i) {
+        const int idx = wbase + i * 32 + lane;
+        const bool ok = idx < n;
+        key[i] = ok ? keys_in[idx] : (K)~(K)0;
+        val[i] = ok ? (iota_vals ? (u32)idx : vals_in[idx]) : 0u;
+    }
+    u32* my_hist = s_whist + warp * RS_BINS;
+#pragma unroll
+    for (int i = 0; i < RS_ITEMS; ++i) {
+        const bool ok = wbase + i * 32 + lane < n;
+        const u32 d = ok ? ((u32)(key[i] >> shift) & 255u) : 256u;  // out-of-range lanes form their own group
+        const u32 peers = rs_match9(d);
+        const u32 below = __popc(peers & ((1u << lane) - 1u));
+        const int leader = __ffs(peers) - 1;
+        u32 pre = 0;
+        if (lane == leader && ok) {
+            pre = my_hist[d];
+            my_hist[d] = pre + __popc(peers);
+        }
+        pre = __shfl_sync(0xffffffffu, pre, leader);
+        rnk[i] = pre + below;
+        __syncwarp();
+    }
+    __syncthreads();
+
+    // digit = tid: exclusive scan over the warps of this digit, tile total of the digit
+    u32 run = 0;
+#pragma unroll
+    for (int w = 0; w < RS_WARPS; ++w) {
+        const u32 c = s_whist[w * RS_BINS + tid];
+        s_whist[w * RS_BINS + tid] = run;
+        run += c;
+    }
+    // publish the tile's count of this digit, then look back over the earlier tiles of the frame
+    volatile u32* st = status + ((size_t)frame * num_tiles) * RS_BINS + tid;
+    u32 before = 0;
+    if (tile == 0) {
+        st[0] = RS_FLAG_PREFIX | run;
+    } else {
+        st[(size_t)tile * RS_BINS] = RS_FLAG_AGG | run;
+        for (int t = tile - 1; t >= 0; --t) {
+            u32 w = 0;
+            int spin = 0;
+            do {
+                w = st[(size_t)t * RS_BINS];
+            } while ((w & ~RS_COUNT_MASK) == 0u && ++spin < RS_SPIN_LIMIT);
+            if ((w & ~RS_COUNT_MASK) == 0u) {  // timed out: never expected, but never hang
+                atomicExch(err, 1);
+                break;
+            }
+            before += w & RS_COUNT_MASK;
+            if (w & RS_FLAG_PREFIX) break;
+        }
+        st[(size_t)tile * RS_BINS] = RS_FLAG_PREFIX | (before + run);
+    }
+    u32 tile_total;
+    const u32 dl = rs_block_excl_scan(run, s_warp, &tile_total);
+    s_dlocal[tid] = dl;
+    s_dbase[tid] = gbase[(size_t)frame * RS_MAX_PASSES * RS_BINS + tid] + before;
+    __syncthreads();
+
+#pragma unroll
+    for (int i = 0; i < RS_ITEMS; ++i) {
+        const int idx = wbase + i * 32 + lane;
+        if (idx < n) {
+            const u32 d = (u32)(key[i] >> shift) & 255u;
+            const u32 pos = s_dlocal[d] + my_hist[d] + rnk[i];
+            s_keys[pos] = key[i];
+            s_vals[pos] = val[i];
+        }
+    }
+    __syncthreads();
+    for (u32 j = tid; j < tile_total; j += RS_THREADS) {
+        const K k = s_keys[j];
+        const u32 d = (u32)(k >> shift) & 255u;
+        const u32 dst = s_dbase[d] + (j - s_dlocal[d]);
+        keys_out[dst] = k;
+        vals_out[dst] = s_vals[j];
+    }
+}
