@@ -250,7 +250,20 @@ def ours(args):
         import torch.distributed as dist
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
             os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # NCCL writes its version banner to stdout when the communicator is created: keep fd 1 clean for the JSON line
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        devnull = os.open(os.devnull, os.O_WRONLY)
+        os.dup2(devnull, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            torch.cuda.set_device(local)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
+            os.close(devnull)
     torch.cuda.set_device(local)
     W, H, B, K, Wm, NC = args.width, args.height, args.batch, args.steps, args.warmup, args.contexts
     assert B % NC == 0, "--batch must be a multiple of --contexts"
