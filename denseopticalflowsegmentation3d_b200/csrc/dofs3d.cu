@@ -378,8 +378,13 @@ int segment_dev(dofs3d_ctx* ctx, const float* d_flow, int already_blurred, int n
     CK(cudaMemsetAsync(B.n_roots, 0, sizeof(int) * EV_MAX_WAVES * F, ctx->stream));
     const int levels = ctx->max_levels;
     for (int level = 0; level < levels; ++level) {
-        LAUNCH(ctx, k_bor_pixel, gS, SEG_THREADS, 0, B, ctx->valsB, ctx->S, W, N, level);
-        LAUNCH(ctx, k_bor_root, gS, SEG_THREADS, 0, B, ctx->valsA, ctx->S, W, N, level);
+        if (level == 0) {
+            LAUNCH(ctx, k_bor_level0_pick, gS, SEG_THREADS, 0, B, ctx->valsB, ctx->S, W, H, N);
+            LAUNCH(ctx, k_bor_level0_root, gS, SEG_THREADS, 0, B, W, N);
+        } else {
+            LAUNCH(ctx, k_bor_pixel, gS, SEG_THREADS, 0, B, ctx->valsB, ctx->S, W, N, level);
+            LAUNCH(ctx, k_bor_root, gS, SEG_THREADS, 0, B, ctx->valsA, ctx->S, W, N, level);
+        }
         LAUNCH(ctx, k_bor_contract, gS, SEG_THREADS, 0, B, N, level);
         LAUNCH(ctx, k_bor_relabel, gS, SEG_THREADS, 0, B, N, level);
     }

@@ -489,6 +489,62 @@ k_bor_pixel(BorState S, const u32* __restrict__ rank, size_t rank_stride, int W,
     }
 }
 
+// Level 0 without atomics: every pixel is its own component, so its minimum outgoing edge is the minimum rank
+// among its (up to) eight incident edges — its four back-edges and the back-edges of the four neighbours that point
+// at it.  k_bor_level0_pick stores that rank in `best` and the neighbour in `newp`; k_bor_level0_root applies the
+// same mutual-pick rule as k_bor_root (the edge's `end` side survives a tie; the pixel owning the slot is `start`).
+__global__ void __launch_bounds__(SEG_THREADS)
+k_bor_level0_pick(BorState S, const u32* __restrict__ rank, size_t rank_stride, int W, int H, int N) {
+    const int frame = blockIdx.y;
+    const size_t fo = (size_t)frame * N;
+    const u32* rk = rank + (size_t)frame * rank_stride;
+    GRID_STRIDE(p, N) {
+        const int y = p / W, x = p - y * W;
+        const uint4 r4 = *reinterpret_cast<const uint4*>(rk + 4 * (size_t)p);
+        u32 b = r4.x;
+        int q = p - 1;
+        u8 own = 1;  // the winning edge sits in one of p's own slots: p is its `start`
+        if (r4.y < b) { b = r4.y; q = p - W; }
+        if (r4.z < b) { b = r4.z; q = p - W - 1; }
+        if (r4.w < b) { b = r4.w; q = p + W - 1; }
+        if (x + 1 < W) {
+            const u32 r = rk[4 * (size_t)(p + 1)];                       // right neighbour's left edge
+            if (r < b) { b = r; q = p + 1; own = 0; }
+            if (y + 1 < H) {
+                const u32 r2 = rk[4 * (size_t)(p + W + 1) + 2];          // down-right neighbour's up-left edge
+                if (r2 < b) { b = r2; q = p + W + 1; own = 0; }
+            }
+            if (y > 0) {
+                const u32 r3 = rk[4 * (size_t)(p - W + 1) + 3];          // up-right neighbour's down-left edge
+                if (r3 < b) { b = r3; q = p - W + 1; own = 0; }
+            }
+        }
+        if (y + 1 < H) {
+            const u32 r1 = rk[4 * (size_t)(p + W) + 1];                  // lower neighbour's up edge
+            if (r1 < b) { b = r1; q = p + W; own = 0; }
+        }
+        S.best[fo + p] = b;
+        S.newp[fo + p] = b == DOFS_INF32 ? (u32)p : (u32)q;
+        S.lvl[fo + p] = own;  // scratch until k_bor_level0_root (a root's lvl is only meaningful once it has lost)
+    }
+}
+
+__global__ void __launch_bounds__(SEG_THREADS)
+k_bor_level0_root(BorState S, int W, int N) {
+    const int frame = blockIdx.y;
+    const size_t fo = (size_t)frame * N;
+    GRID_STRIDE(p, N) {
+        const u32 t = S.best[fo + p];
+        if (t == DOFS_INF32) continue;  // a frame of one pixel
+        const int q = (int)S.newp[fo + p];
+        const bool p_is_start = S.lvl[fo + p] != 0;  // the slot belongs to p
+        const bool mutual = S.best[fo + q] == t;
+        if (mutual && !p_is_start) S.newp[fo + p] = (u32)p;  // rank tie: the `end` side survives (graph.cpp:177-182, 210-213)
+        else S.loss_time[fo + p] = t;
+        S.lvl[fo + p] = 0;
+    }
+}
+
 // per live root: classify its pick (mutual winner / loser), record the loss
 __global__ void __launch_bounds__(SEG_THREADS)
 k_bor_root(BorState S, const u32* __restrict__ sorted_seq, size_t seq_stride, int W, int N, int level) {
