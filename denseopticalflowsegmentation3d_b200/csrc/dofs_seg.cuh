@@ -419,16 +419,28 @@ DOFS_D bool bor_done(const BorState& S, int level, int frame) {
 
 #define GRID_STRIDE(p, N) for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < (N); p += gridDim.x * blockDim.x)
 
-// append to a per-frame list with one atomic per warp
-DOFS_D void list_append(u32* list, int* counter, bool want, u32 value) {
-    const unsigned m = __ballot_sync(__activemask(), want);
-    if (!want) return;
-    const int lane = threadIdx.x & 31;
-    const int leader = __ffs(m) - 1;
-    int base = 0;
-    if (lane == leader) base = atomicAdd(counter, __popc(m));
-    base = __shfl_sync(m, base, leader);
-    list[base + __popc(m & ((1u << lane) - 1u))] = value;
+// append to a per-frame list with ONE atomic per block (all threads of the block must call it; `want` selects).
+// One atomic per warp is not enough here: a level-0 contraction appends from every warp of a frame to the same
+// counter, and same-address atomics that return a value serialise in L2.
+DOFS_D void list_append_block(u32* list, int* counter, bool want, u32 value) {
+    __shared__ int s_count[SEG_THREADS / 32];
+    __shared__ int s_base;
+    const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+    const unsigned m = __ballot_sync(0xffffffffu, want);
+    if (lane == 0) s_count[wrp] = __popc(m);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int tot = 0;
+        for (int w = 0; w < SEG_THREADS / 32; ++w) {
+            const int c = s_count[w];
+            s_count[w] = tot;
+            tot += c;
+        }
+        s_base = tot ? atomicAdd(counter, tot) : 0;
+    }
+    __syncthreads();
+    if (want) list[s_base + s_count[wrp] + __popc(m & ((1u << lane) - 1u))] = value;
+    __syncthreads();
 }
 
 __global__ void __launch_bounds__(SEG_THREADS)
@@ -472,16 +484,23 @@ k_bor_pixel(BorState S, const u32* __restrict__ rank, size_t rank_stride, int W,
         const uint4 r4 = *reinterpret_cast<const uint4*>(rank + (size_t)frame * rank_stride + 4 * (size_t)p);
         const u32 r[4] = {r4.x, r4.y, r4.z, r4.w};
         const u32 cp = comp[p];
+        // all four neighbour components first, then all four current minima: eight independent loads in flight instead
+        // of a load - compare - load chain per edge (the kernel is bound by memory latency, not bandwidth)
+        u32 cq[4], bq[4];
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+            const bool live = ((m >> d) & 1u) && r[d] != DOFS_INF32;
+            cq[d] = live ? comp[edge_other(p, d, W)] : cp;
+        }
+#pragma unroll
+        for (int d = 0; d < 4; ++d) bq[d] = cq[d] != cp ? best[cq[d]] : 0u;
         u32 mine = DOFS_INF32, m_new = 0;
 #pragma unroll
         for (int d = 0; d < 4; ++d) {
-            if (((m >> d) & 1u) && r[d] != DOFS_INF32) {
-                const u32 cq = comp[edge_other(p, d, W)];
-                if (cq != cp) {
-                    m_new |= 1u << d;
-                    mine = min(mine, r[d]);
-                    if (r[d] < best[cq]) atomicMin(&best[cq], r[d]);  // best only decreases: a stale read is safe
-                }
+            if (cq[d] != cp) {
+                m_new |= 1u << d;
+                mine = min(mine, r[d]);
+                if (r[d] < bq[d]) atomicMin(&best[cq[d]], r[d]);  // best only decreases: a stale read is safe
             }
         }
         if (mine != DOFS_INF32 && mine < best[cp]) atomicMin(&best[cp], mine);
@@ -614,7 +633,7 @@ k_bor_contract(BorState S, int N, int level) {
             survives = g == c;
             if (!survives) S.up[fo + c] = g;
         }
-        list_append(next, &S.n_roots[level * S.F + frame], survives, c);
+        list_append_block(next, &S.n_roots[level * S.F + frame], survives, c);
     }
 }
 
