@@ -479,9 +479,15 @@ k_update_matrices(const float* __restrict__ R, const float2* __restrict__ flow, 
 // solve, in double.  Block = 32x8 pixels; the M tile with its halo is staged in shared memory, the
 // vertical window sums are formed once per column and reused by the horizontal window.
 // ---------------------------------------------------------------------------------------------
+#ifndef BS_COLS
 #define BS_COLS 64   // output columns per block
+#endif
+#ifndef BS_ROWS
 #define BS_ROWS 64   // rows per block (one marching segment)
+#endif
+#ifndef BS_BATCH
 #define BS_BATCH 8   // rows of vertical sums staged per horizontal phase
+#endif
 #define BS_GROUP 8   // consecutive outputs one thread produces with a sliding horizontal window
 
 // Each thread owns one (column, channel) of a strip of BS_COLS + 2m columns and marches down BS_ROWS
