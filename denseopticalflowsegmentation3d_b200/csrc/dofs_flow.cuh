@@ -312,6 +312,30 @@ k_pyr_level(ImageSet imgs, float* __restrict__ I, int W, int H, int Wk, int Hk, 
     I[((size_t)img * Hk + y) * Wk + x] = v;
 }
 
+// Level 0 of the pyramid (same size as the frame, 3 taps): the general kernel's arithmetic, without its loops
+// (same fmaf chains in the same order, so the result is bit-identical to k_pyr_level).
+__global__ void __launch_bounds__(256)
+k_pyr_level0(ImageSet imgs, float* __restrict__ I, int W, int H, SmoothTaps taps) {
+    const int img = blockIdx.z;
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= W || y >= H) return;
+    const size_t N = (size_t)W * H;
+    const u8* src = img < imgs.split ? imgs.base0 + (size_t)img * N : imgs.base1 + (size_t)(img - imgs.split) * N;
+    const int xm = flow_reflect101(x - 1, W), xp = flow_reflect101(x + 1, W);
+    const float k0 = taps.k[0], k1 = taps.k[1], k2 = taps.k[2];
+    float acc = 0.f;
+#pragma unroll
+    for (int j = -1; j <= 1; ++j) {
+        const u8* row = src + (size_t)flow_reflect101(y + j, H) * W;
+        float h = fmaf(k0, (float)row[xm], 0.f);
+        h = fmaf(k1, (float)row[x], h);
+        h = fmaf(k2, (float)row[xp], h);
+        acc = fmaf(j == -1 ? k0 : j == 0 ? k1 : k2, h, acc);
+    }
+    I[(size_t)img * N + (size_t)y * W + x] = acc;
+}
+
 // ---------------------------------------------------------------------------------------------
 // K2  FarnebackPolyExp: 3 vertical moment sums in float (rows clamped), 6 horizontal sums in double
 // (columns clamped), projected through inv(G).  Block = 32x8 pixels; the vertical pass of the tile
@@ -616,7 +640,10 @@ inline int farneback_run(FlowBuffers& fb, const u8* d_gray0, const u8* d_gray1, 
             k_flow_upsample<<<g_pair, blk, 0, stream>>>(prev, cur, Wp, Hp, L.w, L.h, 1.0 / fb.cfg.pyr_scale);
             st->launches++;
         }
-        k_pyr_level<<<g_img, blk, 0, stream>>>(imgs, fb.I, fb.W, fb.H, L.w, L.h, L.taps);
+        if (L.w == fb.W && L.h == fb.H && L.taps.radius == 1)
+            k_pyr_level0<<<g_img, blk, 0, stream>>>(imgs, fb.I, fb.W, fb.H, L.taps);
+        else
+            k_pyr_level<<<g_img, blk, 0, stream>>>(imgs, fb.I, fb.W, fb.H, L.w, L.h, L.taps);
         k_polyexp<<<g_img, blk, 0, stream>>>(fb.I, fb.R, L.w, L.h, fb.poly);
         k_update_matrices<<<g_pair, blk, 0, stream>>>(fb.R, cur, fb.M, L.w, L.h, ps);
         st->launches += 3;
