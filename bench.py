@@ -317,25 +317,29 @@ def ours(args):
         ctxs[c].process_dev(frames[c][i % n_inputs].data_ptr(), Bc + 1, o["labels"].data_ptr(), o["boxes"].data_ptr(),
                             o["nbox"].data_ptr(), MAXB, o["stats"].data_ptr())
 
-    # stagger the contexts by 1/NC of a step (once, untimed) so that the latency-bound tail of one sub-batch runs
-    # under the bandwidth-bound head of the next; nothing couples the streams afterwards, so the phase persists
+    # stagger the contexts by 1/NC of a sub-batch, once, at the start of the timed region (its cost is part of the
+    # measured time): context c first sleeps c/NC of the time one sub-batch takes alone.  Nothing couples the streams
+    # afterwards, so the phase difference persists and the latency-bound tail of one sub-batch keeps running under the
+    # bandwidth-bound kernels of the others.
+    pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
-    t_probe = time.perf_counter()
+    pe0.record(streams[0])
     enqueue(0, Wm)
+    pe1.record(streams[0])
     ctxs[0].sync()
-    alone_ms = 1e3 * (time.perf_counter() - t_probe)
+    alone_ms = min(max(pe0.elapsed_time(pe1), 1.0), 500.0)  # one sub-batch alone on the GPU (device time)
     clocks = ClockSampler(local)
     barrier()
     clocks.start()
-    launches0 = sum(c.launch_count for c in ctxs)
+    launches0 = sum(c.launch_count for c in ctxs) + 0
     ev0 = [torch.cuda.Event(enable_timing=True) for _ in ctxs]
     ev1 = [torch.cuda.Event(enable_timing=True) for _ in ctxs]
     ctxs[0].set_timing(True)  # per-kernel CUDA events on context 0's stream, live in the timed region
     for c in range(NC):
+        ev0[c].record(streams[c])  # the timed region starts here for every context; the stagger is inside it
         if c > 0:
             with torch.cuda.stream(streams[c]):
                 torch.cuda._sleep(int(alone_ms * 1e-3 * c / NC * 1.9e9))
-        ev0[c].record(streams[c])
     for i in range(K):  # every step of every context is enqueued without a host wait in between
         for c in range(NC):
             enqueue(c, Wm + 1 + i)
@@ -349,7 +353,12 @@ def ours(args):
     ctxs[0].set_timing(False)
     clk = clocks.stop()
     launches = sum(c.launch_count for c in ctxs) - launches0
-    ms_total = max(ev0[0].elapsed_time(e) for e in ev1)  # first start to last end (context 0 starts first)
+    # first start to last end over all contexts: K steps of B pairs plus the stagger
+    starts = [ev0[0].elapsed_time(e) for e in ev0]
+    ends = [ev0[0].elapsed_time(e) for e in ev1]
+    ms_total = max(ends) - min(min(starts), 0.0)
+    timeline = {"sub_batch_alone_ms": alone_ms, "context_start_ms": [round(v, 2) for v in starts],
+                "context_end_ms": [round(v, 2) for v in ends]}
     n_boxes_dev = int(sum(int(o["nbox"].sum().item()) for o in outs))
 
     # ---- the same kernels alone on the GPU (one context, nothing overlapping): the per-kernel roofline numbers
@@ -473,7 +482,7 @@ def ours(args):
             "whole_path": {"algorithmic_GBps": whole_bytes / (ms_total / K / 1e3) / 1e9,
                            "frac_of_peak": whole_bytes / (ms_total / K / 1e3) / 1e9 / peak,
                            "bytes_per_pixel_per_pair": 1476},
-            "stage_ms_per_step_context0_live": stages, "stage_ms_per_call_alone": stages_iso,
+            "timeline": timeline, "stage_ms_per_step_context0_live": stages, "stage_ms_per_call_alone": stages_iso,
             "boxes_found": total_boxes, "boxes_found_e2e_rank0": n_boxes_host, "nccl_gather_boxes_ms": gather_ms,
             "device_bytes": sum(c.device_bytes for c in ctxs),
         }
