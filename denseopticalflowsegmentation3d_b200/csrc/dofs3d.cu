@@ -69,8 +69,6 @@ void perspective_transform(const double src[4][2], const double dst[4][2], float
 // of the rounded taps.
 void gaussian_taps(int ksize, double sigma, float* out) {
     if (sigma <= 0) sigma = ((ksize - 1) * 0.5 - 1) * 0.3 + 0.8;
-    if (ksize == 3 && sigma <= 0) {  // unreachable after the line above; small fixed kernels only for sigma <= 0
-    }
     const double scale2x = -0.5 / (sigma * sigma);
     double sum = 0;
     for (int i = 0; i < ksize; ++i) {
@@ -527,7 +525,7 @@ int export_results(dofs3d_ctx* ctx, int n, int32_t* labels_out, dofs3d_box* boxe
 }
 
 // cvtColor + Farneback for n pairs out of n+1 consecutive gray frames already in ctx->gray
-int flow_dev(dofs3d_ctx* ctx, const u8* d_gray0, const u8* d_gray1, size_t pair_stride1, int n, float2* d_flow_out) {
+int flow_dev(dofs3d_ctx* ctx, const u8* d_gray0, const u8* d_gray1, int n, float2* d_flow_out) {
     FlowLaunchStats st;
     int rc = farneback_run(ctx->fb, d_gray0, d_gray1, n, d_flow_out, ctx->stream, &st);
     ctx->launches += st.launches;
@@ -535,7 +533,6 @@ int flow_dev(dofs3d_ctx* ctx, const u8* d_gray0, const u8* d_gray1, size_t pair_
         ctx->err = "farneback_run failed";
         return DOFS3D_ERR_CUDA;
     }
-    (void)pair_stride1;
     mark(ctx, "farneback");
     return 0;
 }
@@ -810,7 +807,7 @@ int dofs3d_flow_dev(dofs3d_ctx* ctx, const uint8_t* d_gray0, const uint8_t* d_gr
     if (n_pairs == 0) return 0;
     if ((rc = ensure_flow(ctx))) return rc;
     timer_begin(ctx);
-    rc = flow_dev(ctx, d_gray0, d_gray1, 0, n_pairs, reinterpret_cast<float2*>(d_flow_out));
+    rc = flow_dev(ctx, d_gray0, d_gray1, n_pairs, reinterpret_cast<float2*>(d_flow_out));
     if (rc) return rc;
     CK(cudaGetLastError());
     return 0;
@@ -988,7 +985,7 @@ int dofs3d_process_dev(dofs3d_ctx* ctx, const uint8_t* d_bgr_frames, int n_frame
     const size_t N = ctx->N;
     LAUNCH(ctx, k_bgr2gray, grid1(N * n_frames / 4 + 1, 256, 1), 256, 0, d_bgr_frames, ctx->gray, N * n_frames);
     mark(ctx, "gray");
-    rc = flow_dev(ctx, ctx->gray, ctx->gray + N, 0, n, ctx->flow_raw);  // pair i = frames (i, i+1)
+    rc = flow_dev(ctx, ctx->gray, ctx->gray + N, n, ctx->flow_raw);  // pair i = frames (i, i+1)
     if (rc) return rc;
     rc = segment_dev(ctx, reinterpret_cast<const float*>(ctx->flow_raw), 0, n);
     if (rc) return rc;
@@ -1012,7 +1009,7 @@ int dofs3d_process(dofs3d_ctx* ctx, const uint8_t* bgr_frames, int n_frames, int
     timer_begin(ctx);
     LAUNCH(ctx, k_bgr2gray, grid1(N * n_frames / 4 + 1, 256, 1), 256, 0, ctx->bgr, ctx->gray, N * n_frames);
     mark(ctx, "gray");
-    rc = flow_dev(ctx, ctx->gray, ctx->gray + N, 0, n, ctx->flow_raw);
+    rc = flow_dev(ctx, ctx->gray, ctx->gray + N, n, ctx->flow_raw);
     if (rc) return rc;
     rc = segment_dev(ctx, reinterpret_cast<const float*>(ctx->flow_raw), 0, n);
     if (rc) return rc;

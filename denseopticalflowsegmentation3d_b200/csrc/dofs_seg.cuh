@@ -25,10 +25,6 @@
 
 #define SEG_THREADS 256
 
-struct SegFrame {  // per-frame strided views: element i of frame f at [f * stride + i]
-    int W, H, N;   // N = W*H pixels; 4N edge slots
-};
-
 // ---------------------------------------------------------------------------------------------
 // K6  cv::GaussianBlur(flow, flow, Size(0,0), sigma) (segment.cpp:52): separable, BORDER_REFLECT_101.
 // taps: 2*radius+1 float coefficients (host-computed like cv::getGaussianKernel, CV_32F).
