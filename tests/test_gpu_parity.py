@@ -468,3 +468,19 @@ def test_paint_matches_reference_display_order(dofs, golden_pair):
     assert np.array_equal(painted[0].reshape(-1), expect)
     assert np.array_equal(bgr[0].reshape(-1, 3), colour)
     assert (expect >= 0).sum() > 1000
+
+
+@pytest.mark.parametrize("W,H,nb", [(2, 50, 8), (50, 2, 8), (5, 3, 8), (33, 17, 4), (3, 200, 8)])
+def test_segments_tiny_and_thin_images(dofs, port, W, H, nb):
+    """Image shapes where neighbour offsets coincide (W = 2: the left neighbour of one pixel is the up-right neighbour of
+    another) and where whole rows / columns of edge slots do not exist."""
+    rng = np.random.default_rng(W * 1000 + H)
+    fields = []
+    for k in range(3):
+        f = (rng.normal(size=(H, W, 2)) * 2).astype(np.float32)
+        if k == 1:
+            f[: H // 2] = 0.0  # ties
+        if k == 2:
+            f = np.round(f)    # many equal weights
+        fields.append(f)
+    run_and_compare(dofs, port, fields, neighbors=nb, min_size=3, score_threshold=-1.0)
