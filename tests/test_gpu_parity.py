@@ -484,3 +484,20 @@ def test_segments_tiny_and_thin_images(dofs, port, W, H, nb):
             f = np.round(f)    # many equal weights
         fields.append(f)
     run_and_compare(dofs, port, fields, neighbors=nb, min_size=3, score_threshold=-1.0)
+
+
+def test_context_reuse_with_partial_batches(dofs, port):
+    """One context, calls with different batch sizes back to back: nothing may leak from one call into the next."""
+    from denseopticalflowsegmentation3d_b200.capi import box_pixel_sets
+    W, H = 160, 96
+    fields = [random_flow(50 + k, W, H, scale=4.0) for k in range(4)]
+    persp, inv, up = port.get_mats()
+    p = dofs.default_params()
+    p.min_size = 60
+    with dofs.Context(W, H, max_pairs=4, params=p) as c:
+        for batch in ([0, 1, 2], [3], [2, 0, 3, 1], [1, 1]):
+            out = c.segment(np.stack([fields[i] for i in batch]), already_blurred=True)
+            for slot, i in enumerate(batch):
+                res = port.segment(fields[i], persp, inv, up, min_size=60)
+                compare_boxes(out["boxes"][slot], box_pixel_sets(out["labels"][slot], out["boxes"][slot]), res["entries"], W)
+                assert out["stats"][slot]["n_candidates"] == res["counters"]["get_score"]
