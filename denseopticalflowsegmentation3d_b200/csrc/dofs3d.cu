@@ -686,6 +686,10 @@ int dofs3d_create(dofs3d_ctx** out, int device, int width, int height, int max_p
     ctx->bor.final_root = ctx->counters + CNT_FINAL * F;
     ctx->bor.F = (int)F;
     ctx->max_levels = std::min(EV_MAX_WAVES - 2, ceil_log2((unsigned long long)N) + 1);  // components at least halve per level
+    if (const char* e = getenv("DOFS3D_MAX_LEVELS")) {  // experiment knob: fewer levels than the guaranteed bound (a frame that
+        const int v = atoi(e);                           // needs more is reported as failed, never silently wrong)
+        if (v >= 1 && v < ctx->max_levels) ctx->max_levels = v;
+    }
     CK(cudaMallocHost(&ctx->h_stats, sizeof(dofs3d_stats) * F));
     DA(ctx->boxes_tmp, F * ctx->box_cap);
     DA(ctx->boxes, F * ctx->box_cap);

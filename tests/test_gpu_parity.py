@@ -501,3 +501,26 @@ def test_context_reuse_with_partial_batches(dofs, port):
                 res = port.segment(fields[i], persp, inv, up, min_size=60)
                 compare_boxes(out["boxes"][slot], box_pixel_sets(out["labels"][slot], out["boxes"][slot]), res["entries"], W)
                 assert out["stats"][slot]["n_candidates"] == res["counters"]["get_score"]
+
+
+def test_video_driver_example(dofs, tmp_path):
+    """examples/video_driver.cpp (the reference's main1 loop over the shim's process_video) agrees with the C ABI."""
+    import os
+    import subprocess
+    from denseopticalflowsegmentation3d_b200 import build as b, synth
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    b.build_host()
+    exe = b.build_host_program(os.path.join(root, "examples", "video_driver.cpp"), str(tmp_path / "video_driver"))
+    W, H, n = 320, 180, 3
+    fr = synth.frames(77, 5, 0, n + 1, W, H)
+    raw = tmp_path / "clip.bgr"
+    fr.tofile(raw)
+    r = subprocess.run([exe, str(raw), str(W), str(H), "0.5"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    with dofs.Context(W, H, max_pairs=n) as c:
+        out = c.process(fr)
+    for i in range(n):
+        want = [(int(bx["root"]), int(bx["cls"])) for bx in out["boxes"][i] if bx["score"] > 0.5]
+        got = [(int(l.split()[3]), int(l.split()[5])) for l in r.stdout.splitlines() if l.startswith(f"pair {i} root")]
+        assert got == want
+        assert f"pair {i}: {len(want)} boxes drawn" in r.stdout
