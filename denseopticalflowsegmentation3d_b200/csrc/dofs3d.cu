@@ -147,6 +147,7 @@ struct dofs3d_ctx {
     int* counters = nullptr;    // [6][F]: n_cand, longest_chain, n_scored, n_boxes, n_roots, final_root
     dofs3d_stats* h_stats = nullptr;  // pinned copy of the stats of the last call
     int max_levels = 0;               // guaranteed bound of Boruvka levels for this frame size
+    bool force_time_fallback = false; // test knob (DOFS3D_FORCE_TIME_FALLBACK=1): always take the exact 64-bit fallback of K8
     int pending_pairs = 0, pending_max_boxes = -1;  // last asynchronous call, validated by dofs3d_sync
     dofs3d_box *boxes_tmp = nullptr, *boxes = nullptr;
     int32_t* labels = nullptr;
@@ -364,24 +365,28 @@ int segment_dev(dofs3d_ctx* ctx, const float* d_flow, int already_blurred, int n
         blur_launch(ctx, src, ctx->flow_blur, n);
     }
     mark(ctx, "flow_blur");
-    int rc = build_sorted_edges(ctx, n);
-    if (rc) return rc;
 
-    // K9a Boruvka levels (== union-by-rank ranks): the guaranteed bound of levels is enqueued, finished frames skip
+    // K7: one 32-bit order-preserving prefix of the weight per edge slot (lives in keysB until the events need it)
+    u32* prefix = reinterpret_cast<u32*>(ctx->keysB);
+    LAUNCH(ctx, k_edge_prefix, gN, SEG_THREADS, 0, ctx->flow_blur, prefix, ctx->S, W, H, ctx->seg.neighbors == 8 ? 1 : 0);
+    mark(ctx, "edge_keys");
+
+    // K9a Boruvka levels (== union-by-rank ranks) on direct edge comparisons: the guaranteed bound of levels is
+    // enqueued, finished frames skip
     BorState& B = ctx->bor;
     const dim3 gS = grid_stride(ctx, n);
     LAUNCH(ctx, k_bor_init, gS, SEG_THREADS, 0, B, ctx->flow_blur, ctx->rsize, ctx->rbbox, ctx->rflow, ctx->best_score,
-           ctx->sel_time, ctx->sel_box, W, N);
+           ctx->sel_time, ctx->sel_box, W, H, N, ctx->seg.neighbors == 8 ? 1 : 0);
     CK(cudaMemsetAsync(ctx->counters, 0, sizeof(int) * CNT_KINDS * F, ctx->stream));
     CK(cudaMemsetAsync(B.n_roots, 0, sizeof(int) * EV_MAX_WAVES * F, ctx->stream));
     const int levels = ctx->max_levels;
     for (int level = 0; level < levels; ++level) {
         if (level == 0) {
-            LAUNCH(ctx, k_bor_level0_pick, gS, SEG_THREADS, 0, B, ctx->valsB, ctx->S, W, H, N);
+            LAUNCH(ctx, k_bor_level0_pick, gS, SEG_THREADS, 0, B, prefix, ctx->S, ctx->flow_blur, W, H, N);
             LAUNCH(ctx, k_bor_level0_root, gS, SEG_THREADS, 0, B, W, N);
         } else {
-            LAUNCH(ctx, k_bor_pixel, gS, SEG_THREADS, 0, B, ctx->valsB, ctx->S, W, N, level);
-            LAUNCH(ctx, k_bor_root, gS, SEG_THREADS, 0, B, ctx->valsA, ctx->S, W, N, level);
+            LAUNCH(ctx, k_bor_pixel, gS, SEG_THREADS, 0, B, prefix, ctx->S, ctx->flow_blur, W, N, level);
+            LAUNCH(ctx, k_bor_root, gS, SEG_THREADS, 0, B, W, N, level);
         }
         LAUNCH(ctx, k_bor_contract, gS, SEG_THREADS, 0, B, N, level);
         LAUNCH(ctx, k_bor_relabel, gS, SEG_THREADS, 0, B, N, level);
@@ -389,18 +394,69 @@ int segment_dev(dofs3d_ctx* ctx, const float* d_flow, int already_blurred, int n
     LAUNCH(ctx, k_bor_finish, gS, SEG_THREADS, 0, B, N, levels);
     mark(ctx, "boruvka");
 
-    // K9b events: winner of every loss, sorted by (wave, winner, time); buffers alias the edge keys
+    // K8 merge times: only the edges Boruvka picked are sorted (<= N-1 of the 4N slots)
+    const int tb = ceil_log2(ctx->S);
+    u64* tkA = ctx->keysA;                   // keysA holds F*4N u64: two key buffers, two fallback key buffers
+    u64* tkB = ctx->keysA + (size_t)F * N;
+    u32* tvA = ctx->valsA;
+    u32* tvB = ctx->valsB;
+    LAUNCH(ctx, k_time_keys, gS, SEG_THREADS, 0, B, prefix, ctx->S, tkA, N, tb);
+    mark(ctx, "time_keys");
+    int side = radix_sort_onesweep<u64>(ctx, tkA, tvA, tkB, tvB, (size_t)N, N, n, 32 + tb, true, "time_sort.hist",
+                                        "time_sort.scatter");
+    if (side < 0) {
+        ctx->err = "internal: time key too wide";
+        return DOFS3D_ERR_INTERNAL;
+    }
+    u64* tk = side ? tkB : tkA;        // sorted keys
+    u64* tk_other = side ? tkA : tkB;  // dead
+    u32* order = side ? tvB : tvA;     // losing roots in (prefix, slot) order
+    u32* order_other = side ? tvA : tvB;
+    CK(cudaMemsetAsync(ctx->repair_flags, 0, 2 * sizeof(int), ctx->stream));
+    if (ctx->force_time_fallback) CK(cudaMemsetAsync(ctx->repair_flags + 1, 1, 1, ctx->stream));
+    {
+        TimeRepairArgs R;
+        R.key = tk;
+        R.comp = order;
+        R.flow = ctx->flow_blur;
+        R.time = B.loss_time;
+        R.long_list = ctx->long_list;
+        R.long_count = ctx->repair_flags;
+        R.need_full = ctx->repair_flags + 1;
+        R.list_cap = ctx->list_cap;
+        R.N = N;
+        R.W = W;
+        R.tb = tb;
+        LAUNCH(ctx, k_time_repair_short, gN, SEG_THREADS, 0, R);
+        LAUNCH(ctx, k_time_repair_long, dim3(148 * 2), 256, 0, R);
+        mark(ctx, "time_repair");
+        // fallback, enabled on the device by *need_full: stable 64-bit sort of the (prefix, slot)-ordered list by weight
+        const int* enable = ctx->repair_flags + 1;
+        u64* fwA = ctx->keysA + 2 * (size_t)F * N;
+        LAUNCH(ctx, k_time_fallback_keys, dim3(std::max(1, 148 * 4 / n), n), SEG_THREADS, 0, tk, ctx->flow_blur, fwA, N, W, tb,
+               enable);
+        const int fside = radix_sort<u64>(ctx, fwA, order, tk_other, order_other, (size_t)N, N, n, 64, false, "time_fallback",
+                                          "time_fallback", "time_fallback", enable);
+        if (fside != 0) {
+            ctx->err = "internal: odd number of sort passes";
+            return DOFS3D_ERR_INTERNAL;
+        }
+        LAUNCH(ctx, k_time_fallback_rank, dim3(std::max(1, 148 * 4 / n), n), SEG_THREADS, 0, fwA, order, B.loss_time, N, enable);
+        mark(ctx, "time_fallback");
+    }
+
+    // K9b events: winner of every loss, sorted by (wave, winner, time); buffers alias the dead edge prefixes / time keys
     EvBits eb;
-    eb.tb = ceil_log2(ctx->S);
+    eb.tb = ceil_log2((unsigned long long)N);  // times are positions among the <= N-1 merges
     eb.wb = ceil_log2((unsigned long long)N);
-    u64* evA = ctx->keysA;
-    u64* evB = ctx->keysB;
-    u32* evlA = reinterpret_cast<u32*>(ctx->keysA + (size_t)F * N);  // losers, after the F*N keys
-    u32* evlB = reinterpret_cast<u32*>(ctx->keysB + (size_t)F * N);
+    u64* evA = ctx->keysB;
+    u64* evB = ctx->keysB + (size_t)F * N;
+    u32* evlA = ctx->valsA;
+    u32* evlB = ctx->valsB;
     LAUNCH(ctx, k_event_keys, gS, SEG_THREADS, 0, B, ctx->win, evA, N, eb);
     mark(ctx, "event_keys");
-    int side = radix_sort_onesweep<u64>(ctx, evA, evlA, evB, evlB, (size_t)N, N, n, eb.tb + eb.wb + 5, true,
-                                        "event_sort.hist", "event_sort.scatter");
+    side = radix_sort_onesweep<u64>(ctx, evA, evlA, evB, evlB, (size_t)N, N, n, eb.tb + eb.wb + 5, true, "event_sort.hist",
+                                    "event_sort.scatter");
     if (side < 0) {
         ctx->err = "internal: event key too wide";
         return DOFS3D_ERR_INTERNAL;
@@ -690,6 +746,7 @@ int dofs3d_create(dofs3d_ctx** out, int device, int width, int height, int max_p
         const int v = atoi(e);                           // needs more is reported as failed, never silently wrong)
         if (v >= 1 && v < ctx->max_levels) ctx->max_levels = v;
     }
+    if (const char* e = getenv("DOFS3D_FORCE_TIME_FALLBACK")) ctx->force_time_fallback = atoi(e) != 0;
     CK(cudaMallocHost(&ctx->h_stats, sizeof(dofs3d_stats) * F));
     DA(ctx->boxes_tmp, F * ctx->box_cap);
     DA(ctx->boxes, F * ctx->box_cap);

@@ -209,6 +209,60 @@ DOFS_D int edge_other(int s, int d, int W) {
     return d == 0 ? s - 1 : d == 1 ? s - W : d == 2 ? s - W - 1 : s + W - 1;
 }
 
+// The segmentation itself never sorts the 4N edge slots: Kruskal only acts on the edges it accepts, and those are
+// the N-1 edges of the minimum spanning forest under the strict order (weight, insertion sequence).  Boruvka finds
+// them by comparing edges directly (below), and only they are sorted afterwards (k_time_*).  So the per-slot state
+// is just the 32-bit prefix; the exact weight of a slot is recomputed from the flow field when two prefixes tie.
+__global__ void __launch_bounds__(SEG_THREADS)
+k_edge_prefix(const float2* __restrict__ flow, u32* __restrict__ prefix, size_t stride, int W, int H, int neighbors8) {
+    const int frame = blockIdx.y;
+    const int N = W * H;
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= N) return;
+    const int y = p / W, x = p - y * W;
+    const float2* f = flow + (size_t)frame * N;
+    const float2 c = f[p];
+    u32 k0 = EDGE_PREFIX_INVALID, k1 = EDGE_PREFIX_INVALID, k2 = EDGE_PREFIX_INVALID, k3 = EDGE_PREFIX_INVALID;
+    if (x > 0) k0 = edge_prefix(edge_key(c, f[p - 1]));
+    if (y > 0) k1 = edge_prefix(edge_key(c, f[p - W]));
+    if (neighbors8) {
+        if (x > 0 && y > 0) k2 = edge_prefix(edge_key(c, f[p - W - 1]));
+        if (x > 0 && y < H - 1) k3 = edge_prefix(edge_key(c, f[p + W - 1]));
+    }
+    *reinterpret_cast<uint4*>(prefix + (size_t)frame * stride + 4 * (size_t)p) = make_uint4(k0, k1, k2, k3);
+}
+
+// weight (bit pattern of the f64) of an existing slot, from the blurred flow of its frame
+DOFS_D u64 slot_weight(const float2* __restrict__ f, u32 slot, int W) {
+    const int s = (int)(slot >> 2);
+    return edge_key(f[s], f[edge_other(s, (int)(slot & 3u), W)]);
+}
+
+// A pick = (prefix << 32) | slot of an existing edge; PICK_NONE (prefix of a non-existent slot) is larger than any pick.
+#define PICK_NONE 0xFFFFFFFFFFFFFFFFull
+DOFS_D u64 make_pick(u32 prefix, u32 slot) { return ((u64)prefix << 32) | slot; }
+
+__device__ __noinline__ bool pick_less_tie(u32 sa, u32 sb, const float2* __restrict__ f, int W) {
+    const u64 wa = slot_weight(f, sa, W), wb = slot_weight(f, sb, W);
+    return wa != wb ? wa < wb : sa < sb;
+}
+// the reference's edge order (graph.cpp:55-60: weight, then insertion sequence) between two picks of one frame
+DOFS_D bool pick_less(u64 a, u64 b, const float2* __restrict__ f, int W) {
+    const u32 pa = (u32)(a >> 32), pb = (u32)(b >> 32);
+    if (pa != pb) return pa < pb;
+    if (a == b) return false;
+    if (pa == 0u) return (u32)a < (u32)b;  // prefix 0 is the weight 0 exactly (any other weight of a float field is >= 2^-149)
+    return pick_less_tie((u32)a, (u32)b, f, W);
+}
+// lock-free minimum under that order; `seen` is a (possibly stale) read of *best, which only ever decreases
+DOFS_D void pick_offer(u64* best, u64 cand, u64 seen, const float2* __restrict__ f, int W) {
+    while (pick_less(cand, seen, f, W)) {
+        const u64 old = atomicCAS(reinterpret_cast<unsigned long long*>(best), (unsigned long long)seen, (unsigned long long)cand);
+        if (old == seen) return;
+        seen = old;
+    }
+}
+
 // rank[seq] = position in the sorted list (INF for the non-existent slots, which sort last); only used
 // after the full 64-bit fallback sort
 __global__ void __launch_bounds__(SEG_THREADS)
@@ -393,15 +447,19 @@ k_prefix_repair_long(RepairArgs A) {
 // Kernels are grid-stride with a small fixed grid, so a level with nothing left costs microseconds.
 // ---------------------------------------------------------------------------------------------
 #define EV_MAX_WAVES 32
+#ifndef BOR_PIXEL_BLOCKS
+#define BOR_PIXEL_BLOCKS 5  // resident blocks per SM the pixel kernel is compiled for (it is bound by memory latency)
+#endif
 
 struct BorState {
     u32* comp;       // [F][N] current root of each pixel
-    u32* best;       // [F][N] per root: minimum rank of an outgoing edge in this level
+    u64* best;       // [F][N] per root: its minimum outgoing edge in this level, as a pick (prefix << 32 | slot)
     u32* newp;       // [F][N] per root: hook target in this level
-    u32* loss_time;  // [F][N] per root id: sorted position of the edge at which it loses (INF: never)
+    u32* loss_time;  // [F][N] per root id: while the levels run, the slot of the edge at which it loses; after k_time_*
+                     //         the position of that edge in the reference's merge sequence (INF: never loses)
     u32* up;         // [F][N] per root id: root of the next-level component it is contracted into (itself while live)
     u8* lvl;         // [F][N] per root id: level at which it loses == its final union-find rank
-    u8* mask;        // [F][N] per pixel: which of its 4 back-edges still join different components
+    u8* mask;        // [F][N] per pixel: which of its 8 incident edges still join different components
     u32* roots[2];   // [F][N] live roots, ping-pong by level parity (level 0: every pixel, implicit)
     int* n_roots;    // [EV_MAX_WAVES][F] number of roots after each level (zeroed per call)
     int* levels;     // [F] number of levels the frame needed (written by k_bor_finish)
@@ -414,6 +472,25 @@ DOFS_D bool bor_done(const BorState& S, int level, int frame) {
 }
 
 #define GRID_STRIDE(p, N) for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < (N); p += gridDim.x * blockDim.x)
+
+// Incident edge e of pixel p: e < 4 its own back-edge slots 4p+e; e = 4..7 the back-edges of the right, lower-right,
+// upper-right and lower neighbours that point at p.
+DOFS_D int incident_pixel(int p, int e, int W) {
+    return e < 4 ? edge_other(p, e, W) : e == 4 ? p + 1 : e == 5 ? p + W + 1 : e == 6 ? p - W + 1 : p + W;
+}
+DOFS_D u32 incident_slot(int p, int e, int W) {
+    return e < 4 ? 4u * (u32)p + e
+                 : e == 4 ? 4u * (u32)(p + 1) : e == 5 ? 4u * (u32)(p + W + 1) + 2u : e == 6 ? 4u * (u32)(p - W + 1) + 3u
+                                                                                              : 4u * (u32)(p + W) + 1u;
+}
+// which of the eight incident edges of (x, y) exist
+DOFS_D u32 incident_mask(int x, int y, int W, int H, int neighbors8) {
+    const bool l = x > 0, r = x + 1 < W, u = y > 0, d = y + 1 < H;
+    u32 m = (l ? 1u : 0u) | (u ? 2u : 0u) | (r ? 16u : 0u) | (d ? 128u : 0u);
+    if (neighbors8) m |= (l && u ? 4u : 0u) | (l && d ? 8u : 0u) | (r && d ? 32u : 0u) | (r && u ? 64u : 0u);
+    return m;
+}
+
 
 // append to a per-frame list with ONE atomic per block (all threads of the block must call it; `want` selects).
 // One atomic per warp is not enough here: a level-0 contraction appends from every warp of a frame to the same
@@ -442,20 +519,19 @@ DOFS_D void list_append_block(u32* list, int* counter, bool want, u32 value) {
 __global__ void __launch_bounds__(SEG_THREADS)
 k_bor_init(BorState S, const float2* __restrict__ flow, int* __restrict__ rsize, ushort4* __restrict__ rbbox,
            float2* __restrict__ rflow, u64* __restrict__ best_score, u32* __restrict__ sel_time,
-           int* __restrict__ sel_box, int W, int N) {
+           int* __restrict__ sel_box, int W, int H, int N, int neighbors8) {
     const int frame = blockIdx.y;
     GRID_STRIDE(p, N) {
         const size_t g = (size_t)frame * N + p;
         S.comp[g] = (u32)p;
-        S.best[g] = DOFS_INF32;
         S.newp[g] = (u32)p;
         S.loss_time[g] = DOFS_INF32;
         S.up[g] = (u32)p;
         S.lvl[g] = 0;
-        S.mask[g] = 15;
+        const int y = p / W, x = p - y * W;
+        S.mask[g] = (u8)incident_mask(x, y, W, H, neighbors8);
         // Forest::Forest (graph.cpp:129-148): singleton sets
         rsize[g] = 1;
-        const int y = p / W, x = p - y * W;
         rbbox[g] = make_ushort4((u16)x, (u16)y, (u16)x, (u16)y);
         rflow[g] = flow[g];
         best_score[g] = 0ull;
@@ -464,83 +540,135 @@ k_bor_init(BorState S, const float2* __restrict__ flow, int* __restrict__ rsize,
     }
 }
 
-// every edge whose endpoints are in different components offers its rank to both components.  Pixels are
-// visited in image order (neighbouring component ids share cache lines); a pixel whose four back-edges have all
-// become internal costs one byte of mask.
-__global__ void __launch_bounds__(SEG_THREADS)
-k_bor_pixel(BorState S, const u32* __restrict__ rank, size_t rank_stride, int W, int N, int level) {
+// Every pixel offers the smallest of its (up to eight) incident edges that leave its component to ITS OWN component:
+// one atomic per boundary pixel, and neighbouring pixels mostly address the same word.  Pixels are visited in image
+// order (neighbouring component ids share cache lines); a pixel whose incident edges have all become internal costs
+// one byte of mask.  Incident edge e of pixel p: e < 4 its own back-edge slots 4p+e; e = 4..7 the back-edges of the
+// right, lower-right, upper-right and lower neighbours that point at p.
+//
+// The minimum is taken with one native 64-bit atomicMin per offer on (prefix << 32 | slot), i.e. in (prefix, slot)
+// order L.  That is the reference's (weight, slot) order E unless two offers to the same component share a prefix with
+// different weights (prefix 0 is the weight 0 exactly, so there L == E).  An offer that meets another offer x of its
+// own prefix — in the value it read or in the value its atomicMin returned — settles the pair under E with a CAS loop
+// (pick_offer): it offers itself, and it offers x again if its atomicMin displaced x.  The E-minimum m of a component
+// is therefore installed when its own offer completes (either it is L-smaller than what is there, or it sees its
+// prefix and installs itself under E), nothing can remove it under E, and whoever removes it under L puts it back.
+// A pixel whose own candidates share the prefix of its L-smallest one offers them all under E.
+#define PIX_SENT 1u       // the atomicMin was issued
+#define PIX_TIE_SEEN 2u   // the offer met another offer of its prefix
+#define PIX_TIE_LOCAL 4u  // two of the pixel's own candidates share the smallest prefix
+
+__device__ __noinline__ void bor_pixel_settle(u64* best, const u32* __restrict__ pre, const float2* __restrict__ f, int W, int p,
+                                              u32 cp, u32 out, u64 mine, u64 seen, u32 flags) {
+    u64* b = &best[cp];
+    if (flags & PIX_TIE_SEEN) {
+        pick_offer(b, mine, *reinterpret_cast<volatile u64*>(b), f, W);
+        if ((flags & PIX_SENT) && mine < seen) pick_offer(b, seen, *reinterpret_cast<volatile u64*>(b), f, W);
+    }
+    if (flags & PIX_TIE_LOCAL) {
+#pragma unroll 1
+        for (int e = 0; e < 8; ++e) {
+            if (!((out >> e) & 1u)) continue;
+            const u32 slot = incident_slot(p, e, W);
+            pick_offer(b, make_pick(pre[slot], slot), *reinterpret_cast<volatile u64*>(b), f, W);
+        }
+    }
+}
+
+// an offer `cand` met `seen` in best: same prefix, another edge, and not the exact weight 0
+DOFS_D bool pick_meets(u64 cand, u64 seen) {
+    return (u32)(seen >> 32) == (u32)(cand >> 32) && seen != cand && (u32)(cand >> 32) != 0u;
+}
+
+__global__ void __launch_bounds__(SEG_THREADS, BOR_PIXEL_BLOCKS)
+k_bor_pixel(BorState S, const u32* __restrict__ prefix, size_t prefix_stride, const float2* __restrict__ flow, int W, int N,
+            int level) {
     const int frame = blockIdx.y;
     if (bor_done(S, level, frame)) return;
     const size_t fo = (size_t)frame * N;
     const u32* comp = S.comp + fo;
-    u32* best = S.best + fo;
+    const u32* pre = prefix + (size_t)frame * prefix_stride;
+    u64* best = S.best + fo;
     GRID_STRIDE(p, N) {
         const u32 m = S.mask[fo + p];
         if (m == 0) continue;
-        const uint4 r4 = *reinterpret_cast<const uint4*>(rank + (size_t)frame * rank_stride + 4 * (size_t)p);
-        const u32 r[4] = {r4.x, r4.y, r4.z, r4.w};
         const u32 cp = comp[p];
-        // all four neighbour components first, then all four current minima: eight independent loads in flight instead
-        // of a load - compare - load chain per edge (the kernel is bound by memory latency, not bandwidth)
-        u32 cq[4], bq[4];
+        const u64 seen0 = best[cp];
+        // independent loads first (the kernel is bound by memory latency): neighbour components, then their prefixes
+        u32 cq[8];
 #pragma unroll
-        for (int d = 0; d < 4; ++d) {
-            const bool live = ((m >> d) & 1u) && r[d] != DOFS_INF32;
-            cq[d] = live ? comp[edge_other(p, d, W)] : cp;
+        for (int e = 0; e < 8; ++e) cq[e] = ((m >> e) & 1u) ? comp[incident_pixel(p, e, W)] : cp;
+        u32 out = 0;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) out |= cq[e] != cp ? 1u << e : 0u;
+        if (out != m) S.mask[fo + p] = (u8)out;  // an edge that became internal stays internal
+        if (out == 0) continue;
+        u64 cand[8];
+        if (out & 15u) {
+            const uint4 r4 = *reinterpret_cast<const uint4*>(pre + 4 * (size_t)p);
+            cand[0] = make_pick(r4.x, 4u * (u32)p);
+            cand[1] = make_pick(r4.y, 4u * (u32)p + 1u);
+            cand[2] = make_pick(r4.z, 4u * (u32)p + 2u);
+            cand[3] = make_pick(r4.w, 4u * (u32)p + 3u);
         }
 #pragma unroll
-        for (int d = 0; d < 4; ++d) bq[d] = cq[d] != cp ? best[cq[d]] : 0u;
-        u32 mine = DOFS_INF32, m_new = 0;
-#pragma unroll
-        for (int d = 0; d < 4; ++d) {
-            if (cq[d] != cp) {
-                m_new |= 1u << d;
-                mine = min(mine, r[d]);
-                if (r[d] < bq[d]) atomicMin(&best[cq[d]], r[d]);  // best only decreases: a stale read is safe
-            }
+        for (int e = 4; e < 8; ++e) {
+            const u32 slot = incident_slot(p, e, W);
+            cand[e] = ((out >> e) & 1u) ? make_pick(pre[slot], slot) : PICK_NONE;
         }
-        if (mine != DOFS_INF32 && mine < best[cp]) atomicMin(&best[cp], mine);
-        if (m_new != m) S.mask[fo + p] = (u8)m_new;
+        u64 mine = PICK_NONE;
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+            if ((out >> e) & 1u) mine = min(mine, cand[e]);
+        u32 flags = 0;
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+            if (((out >> e) & 1u) && pick_meets(cand[e], mine)) flags |= PIX_TIE_LOCAL;
+        u64 seen = seen0;
+        if (mine < seen) {
+            seen = atomicMin(reinterpret_cast<unsigned long long*>(&best[cp]), (unsigned long long)mine);
+            flags |= PIX_SENT;
+        }
+        if (pick_meets(mine, seen)) flags |= PIX_TIE_SEEN;
+        if (flags & (PIX_TIE_SEEN | PIX_TIE_LOCAL)) bor_pixel_settle(best, pre, flow + fo, W, p, cp, out, mine, seen, flags);
     }
 }
 
-// Level 0 without atomics: every pixel is its own component, so its minimum outgoing edge is the minimum rank
-// among its (up to) eight incident edges — its four back-edges and the back-edges of the four neighbours that point
-// at it.  k_bor_level0_pick stores that rank in `best` and the neighbour in `newp`; k_bor_level0_root applies the
-// same mutual-pick rule as k_bor_root (the edge's `end` side survives a tie; the pixel owning the slot is `start`).
+// Level 0 without atomics: every pixel is its own component, so its minimum outgoing edge is the minimum among its
+// (up to) eight incident edges — its four back-edges and the back-edges of the four neighbours that point at it.
+// k_bor_level0_pick stores that pick in `best`; k_bor_level0_root applies the same mutual-pick rule as k_bor_root (the
+// edge's `end` side survives a tie; the pixel owning the slot is `start`).
 __global__ void __launch_bounds__(SEG_THREADS)
-k_bor_level0_pick(BorState S, const u32* __restrict__ rank, size_t rank_stride, int W, int H, int N) {
+k_bor_level0_pick(BorState S, const u32* __restrict__ prefix, size_t prefix_stride, const float2* __restrict__ flow, int W,
+                  int H, int N) {
     const int frame = blockIdx.y;
     const size_t fo = (size_t)frame * N;
-    const u32* rk = rank + (size_t)frame * rank_stride;
+    const u32* pre = prefix + (size_t)frame * prefix_stride;
+    const float2* f = flow + fo;
     GRID_STRIDE(p, N) {
         const int y = p / W, x = p - y * W;
-        const uint4 r4 = *reinterpret_cast<const uint4*>(rk + 4 * (size_t)p);
-        u32 b = r4.x;
-        int q = p - 1;
-        u8 own = 1;  // the winning edge sits in one of p's own slots: p is its `start`
-        if (r4.y < b) { b = r4.y; q = p - W; }
-        if (r4.z < b) { b = r4.z; q = p - W - 1; }
-        if (r4.w < b) { b = r4.w; q = p + W - 1; }
+        const uint4 r4 = *reinterpret_cast<const uint4*>(pre + 4 * (size_t)p);
+        u64 b = PICK_NONE;
+#define L0_CONSIDER(pr, slot)                                     \
+    do {                                                          \
+        const u32 pr_ = (pr);                                     \
+        if (pr_ != EDGE_PREFIX_INVALID) {                         \
+            const u64 c_ = make_pick(pr_, (u32)(slot));           \
+            if (pick_less(c_, b, f, W)) b = c_;                   \
+        }                                                         \
+    } while (0)
+        L0_CONSIDER(r4.x, 4 * p);
+        L0_CONSIDER(r4.y, 4 * p + 1);
+        L0_CONSIDER(r4.z, 4 * p + 2);
+        L0_CONSIDER(r4.w, 4 * p + 3);
         if (x + 1 < W) {
-            const u32 r = rk[4 * (size_t)(p + 1)];                       // right neighbour's left edge
-            if (r < b) { b = r; q = p + 1; own = 0; }
-            if (y + 1 < H) {
-                const u32 r2 = rk[4 * (size_t)(p + W + 1) + 2];          // down-right neighbour's up-left edge
-                if (r2 < b) { b = r2; q = p + W + 1; own = 0; }
-            }
-            if (y > 0) {
-                const u32 r3 = rk[4 * (size_t)(p - W + 1) + 3];          // up-right neighbour's down-left edge
-                if (r3 < b) { b = r3; q = p - W + 1; own = 0; }
-            }
+            L0_CONSIDER(pre[4 * (size_t)(p + 1)], 4 * (p + 1));                                   // right neighbour's left edge
+            if (y + 1 < H) L0_CONSIDER(pre[4 * (size_t)(p + W + 1) + 2], 4 * (p + W + 1) + 2);    // down-right: its up-left edge
+            if (y > 0) L0_CONSIDER(pre[4 * (size_t)(p - W + 1) + 3], 4 * (p - W + 1) + 3);        // up-right: its down-left edge
         }
-        if (y + 1 < H) {
-            const u32 r1 = rk[4 * (size_t)(p + W) + 1];                  // lower neighbour's up edge
-            if (r1 < b) { b = r1; q = p + W; own = 0; }
-        }
+        if (y + 1 < H) L0_CONSIDER(pre[4 * (size_t)(p + W) + 1], 4 * (p + W) + 1);                // lower neighbour's up edge
+#undef L0_CONSIDER
         S.best[fo + p] = b;
-        S.newp[fo + p] = b == DOFS_INF32 ? (u32)p : (u32)q;
-        S.lvl[fo + p] = own;  // scratch until k_bor_level0_root (a root's lvl is only meaningful once it has lost)
     }
 }
 
@@ -549,20 +677,21 @@ k_bor_level0_root(BorState S, int W, int N) {
     const int frame = blockIdx.y;
     const size_t fo = (size_t)frame * N;
     GRID_STRIDE(p, N) {
-        const u32 t = S.best[fo + p];
-        if (t == DOFS_INF32) continue;  // a frame of one pixel
-        const int q = (int)S.newp[fo + p];
-        const bool p_is_start = S.lvl[fo + p] != 0;  // the slot belongs to p
+        const u64 t = S.best[fo + p];
+        if (t == PICK_NONE) continue;  // a frame of one pixel
+        const u32 slot = (u32)t;
+        const int s = (int)(slot >> 2), e = edge_other(s, (int)(slot & 3u), W);
+        const int q = s == p ? e : s;
         const bool mutual = S.best[fo + q] == t;
-        if (mutual && !p_is_start) S.newp[fo + p] = (u32)p;  // rank tie: the `end` side survives (graph.cpp:177-182, 210-213)
-        else S.loss_time[fo + p] = t;
-        S.lvl[fo + p] = 0;
+        if (mutual && p == e) continue;  // rank tie: the `end` side survives (graph.cpp:177-182, 210-213); newp[p] is p
+        S.newp[fo + p] = (u32)q;
+        S.loss_time[fo + p] = slot;
     }
 }
 
 // per live root: classify its pick (mutual winner / loser), record the loss
 __global__ void __launch_bounds__(SEG_THREADS)
-k_bor_root(BorState S, const u32* __restrict__ sorted_seq, size_t seq_stride, int W, int N, int level) {
+k_bor_root(BorState S, int W, int N, int level) {
     const int frame = blockIdx.y;
     if (bor_done(S, level, frame)) return;
     const size_t fo = (size_t)frame * N;
@@ -570,14 +699,14 @@ k_bor_root(BorState S, const u32* __restrict__ sorted_seq, size_t seq_stride, in
     const int count = level == 0 ? N : S.n_roots[(level - 1) * S.F + frame];
     GRID_STRIDE(i, count) {
         const u32 c = level == 0 ? (u32)i : list[i];
-        const u32 t = S.best[fo + c];
-        if (t == DOFS_INF32) {  // the last component
+        const u64 t = S.best[fo + c];
+        if (t == PICK_NONE) {  // the last component
             S.newp[fo + c] = c;
             continue;
         }
-        const u32 seq = sorted_seq[(size_t)frame * seq_stride + t];
-        const int s = (int)(seq >> 2);
-        const int e = edge_other(s, (int)(seq & 3u), W);
+        const u32 slot = (u32)t;
+        const int s = (int)(slot >> 2);
+        const int e = edge_other(s, (int)(slot & 3u), W);
         const u32 cs = S.comp[fo + s], ce = S.comp[fo + e];
         const u32 other = (cs == c) ? ce : cs;
         const bool mutual = S.best[fo + other] == t;
@@ -585,7 +714,7 @@ k_bor_root(BorState S, const u32* __restrict__ sorted_seq, size_t seq_stride, in
             S.newp[fo + c] = c;  // rank tie: the `end` side survives (graph.cpp:177-182, 210-213)
         } else {
             S.newp[fo + c] = other;
-            S.loss_time[fo + c] = t;
+            S.loss_time[fo + c] = slot;
             S.lvl[fo + c] = (u8)level;
         }
     }
@@ -625,7 +754,7 @@ k_bor_contract(BorState S, int N, int level) {
                 newp[g] = nn;
                 g = nn;
             }
-            S.best[fo + c] = DOFS_INF32;
+            S.best[fo + c] = PICK_NONE;
             survives = g == c;
             if (!survives) S.up[fo + c] = g;
         }
@@ -667,10 +796,190 @@ k_bor_finish(BorState S, int N, int max_levels) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// K8  merge times.  The reference's loop accepts exactly the edges Boruvka picked (the minimum spanning forest
+// under (weight, sequence)); their relative order in the sorted edge list is all that the merge sequence depends
+// on.  So only those <= N-1 edges are sorted: key = prefix << tb | slot (tb = bits of a slot), payload = the root
+// that loses at the edge; runs of equal prefix are then put in exact (weight, slot) order (stable by weight: they
+// are already in slot order) and loss_time[c] becomes the position = the index of the merge in the reference's
+// sequence of accepted edges.
+//   k_time_keys           one key per root id (roots that never lose: TIME_KEY_NONE, sorted last)
+//   k_time_repair_short   runs of <= REPAIR_SHORT edges: insertion sort in the head thread
+//   k_time_repair_long    longer runs, a block each: identical weights are already in order; <= REPAIR_SMEM edges
+//                         are sorted in shared memory; beyond that *need_full enables the exact fallback:
+//   k_time_fallback_keys  full weights of the sorted list, stably sorted by the conditional 64-bit radix sort
+//   k_time_fallback_rank  positions after that sort
+// ---------------------------------------------------------------------------------------------
+#define TIME_KEY_NONE 0xFFFFFFFFFFFFFFFFull
+
+__global__ void __launch_bounds__(SEG_THREADS)
+k_time_keys(BorState S, const u32* __restrict__ prefix, size_t prefix_stride, u64* __restrict__ tkey, int N, int tb) {
+    const int frame = blockIdx.y;
+    const size_t fo = (size_t)frame * N;
+    GRID_STRIDE(c, N) {
+        const u32 slot = S.loss_time[fo + c];
+        tkey[fo + c] = slot == DOFS_INF32 ? TIME_KEY_NONE : (((u64)prefix[(size_t)frame * prefix_stride + slot] << tb) | slot);
+    }
+}
+
+struct TimeRepairArgs {
+    const u64* key;      // [F][N] sorted keys
+    const u32* comp;     // [F][N] sorted payload (losing roots); the list itself is left as it is
+    const float2* flow;  // [F][N] blurred flow
+    u32* time;           // [F][N] out: time[c] = position, INF for roots that never lose
+    uint2* long_list;    // (frame, start)
+    int* long_count;
+    int* need_full;
+    int list_cap;
+    int N, W, tb;
+};
+
+__global__ void __launch_bounds__(SEG_THREADS)
+k_time_repair_short(TimeRepairArgs A) {
+    const int frame = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= A.N) return;
+    const size_t fo = (size_t)frame * A.N;
+    const u64* key = A.key + fo;
+    const u64 k = key[i];
+    if (k == TIME_KEY_NONE) {
+        A.time[fo + A.comp[fo + i]] = DOFS_INF32;
+        return;
+    }
+    const u64 pre = k >> A.tb;
+    const bool prev_same = i > 0 && (key[i - 1] >> A.tb) == pre;
+    const bool next_same = i + 1 < A.N && (key[i + 1] >> A.tb) == pre;  // TIME_KEY_NONE >> tb is no edge's prefix
+    if (!prev_same && !next_same) {
+        A.time[fo + A.comp[fo + i]] = (u32)i;
+        return;
+    }
+    if (prev_same) return;  // the head of the run does the work
+    int len = 2;
+    while (len <= REPAIR_SHORT && i + len < A.N && (key[i + len] >> A.tb) == pre) ++len;
+    if (len > REPAIR_SHORT) {
+        const int slot = atomicAdd(A.long_count, 1);
+        if (slot < A.list_cap) A.long_list[slot] = make_uint2((u32)frame, (u32)i);
+        else atomicExch(A.need_full, 1);
+        return;
+    }
+    const u32 slot_mask = (u32)((1ull << A.tb) - 1ull);
+    u32 cc[REPAIR_SHORT];
+    u64 kk[REPAIR_SHORT];
+    for (int j = 0; j < len; ++j) {
+        cc[j] = A.comp[fo + i + j];
+        kk[j] = slot_weight(A.flow + fo, (u32)key[i + j] & slot_mask, A.W);
+    }
+    for (int j = 1; j < len; ++j) {  // stable insertion sort by weight
+        const u32 c = cc[j];
+        const u64 w = kk[j];
+        int m = j - 1;
+        while (m >= 0 && kk[m] > w) {
+            cc[m + 1] = cc[m];
+            kk[m + 1] = kk[m];
+            --m;
+        }
+        cc[m + 1] = c;
+        kk[m + 1] = w;
+    }
+    for (int j = 0; j < len; ++j) A.time[fo + cc[j]] = (u32)(i + j);
+}
+
+__global__ void __launch_bounds__(256)
+k_time_repair_long(TimeRepairArgs A) {
+    __shared__ u64 s_key[REPAIR_SMEM];
+    __shared__ u32 s_cmp[REPAIR_SMEM];
+    __shared__ int s_flag, s_len;
+    const int n_list = min(*A.long_count, A.list_cap);
+    const u32 slot_mask = (u32)((1ull << A.tb) - 1ull);
+    for (int item = blockIdx.x; item < n_list; item += gridDim.x) {
+        const uint2 it = A.long_list[item];
+        const size_t fo = (size_t)it.x * A.N;
+        const int i0 = (int)it.y;
+        const u64* key = A.key + fo;
+        const float2* f = A.flow + fo;
+        const u64 pre = key[i0] >> A.tb;
+        // length of the run
+        if (threadIdx.x == 0) s_len = A.N - i0;
+        __syncthreads();
+        for (int base = 0; base < A.N - i0; base += 256) {
+            const int j = base + threadIdx.x;
+            if (j < A.N - i0 && (key[i0 + j] >> A.tb) != pre) atomicMin(&s_len, j);
+            __syncthreads();
+            const int seen = s_len;
+            __syncthreads();
+            if (seen <= base + 256) break;
+        }
+        const int len = s_len;
+        // identical weights?
+        const u64 w0 = slot_weight(f, (u32)key[i0] & slot_mask, A.W);
+        if (threadIdx.x == 0) s_flag = 0;
+        __syncthreads();
+        int differs = 0;
+        for (int j = threadIdx.x; j < len; j += 256) differs |= slot_weight(f, (u32)key[i0 + j] & slot_mask, A.W) != w0;
+        if (differs) s_flag = 1;
+        __syncthreads();
+        const bool trivial = s_flag == 0;
+        __syncthreads();
+        if (!trivial && len > REPAIR_SMEM) {
+            if (threadIdx.x == 0) atomicExch(A.need_full, 1);
+            continue;  // block-uniform
+        }
+        if (!trivial) {
+            // odd-even transposition sort in shared memory: stable, len rounds of disjoint compare-exchanges
+            for (int j = threadIdx.x; j < len; j += 256) {
+                s_cmp[j] = A.comp[fo + i0 + j];
+                s_key[j] = slot_weight(f, (u32)key[i0 + j] & slot_mask, A.W);
+            }
+            __syncthreads();
+            for (int round = 0; round < len; ++round) {
+                for (int j = 2 * threadIdx.x + (round & 1); j + 1 < len; j += 512) {
+                    if (s_key[j] > s_key[j + 1]) {
+                        const u64 tk = s_key[j];
+                        s_key[j] = s_key[j + 1];
+                        s_key[j + 1] = tk;
+                        const u32 ts = s_cmp[j];
+                        s_cmp[j] = s_cmp[j + 1];
+                        s_cmp[j + 1] = ts;
+                    }
+                }
+                __syncthreads();
+            }
+            for (int j = threadIdx.x; j < len; j += 256) A.time[fo + s_cmp[j]] = (u32)(i0 + j);
+        } else {
+            for (int j = threadIdx.x; j < len; j += 256) A.time[fo + A.comp[fo + i0 + j]] = (u32)(i0 + j);
+        }
+        __syncthreads();
+    }
+}
+
+// fallback (enabled on the device by *enable): the list is in (prefix, slot) order; a stable sort by the full weight
+// gives (weight, slot) order
+__global__ void __launch_bounds__(SEG_THREADS)
+k_time_fallback_keys(const u64* __restrict__ key, const float2* __restrict__ flow, u64* __restrict__ wkey, int N, int W, int tb,
+                     const int* __restrict__ enable) {
+    if (*enable == 0) return;
+    const int frame = blockIdx.y;
+    const size_t fo = (size_t)frame * N;
+    const u32 slot_mask = (u32)((1ull << tb) - 1ull);
+    GRID_STRIDE(i, N) {
+        const u64 k = key[fo + i];
+        wkey[fo + i] = k == TIME_KEY_NONE ? TIME_KEY_NONE : slot_weight(flow + fo, (u32)k & slot_mask, W);
+    }
+}
+
+__global__ void __launch_bounds__(SEG_THREADS)
+k_time_fallback_rank(const u64* __restrict__ wkey, const u32* __restrict__ comp, u32* __restrict__ time, int N,
+                     const int* __restrict__ enable) {
+    if (*enable == 0) return;
+    const int frame = blockIdx.y;
+    const size_t fo = (size_t)frame * N;
+    GRID_STRIDE(i, N) time[fo + comp[fo + i]] = wkey[fo + i] == TIME_KEY_NONE ? DOFS_INF32 : (u32)i;
+}
+
+// ---------------------------------------------------------------------------------------------
 // K9b  winner of every merge event (one event per losing root) and the event sort key
 //      key = lvl[winner] << (tb + wb) | winner << tb | time ; payload = loser
-//      tb = bits of a sorted edge position (< 4N), wb = bits of a pixel id (< N): as few radix
-//      passes as the frame size allows (1080p: 23 + 21 + 5 = 49 bits -> 7 passes instead of 8)
+//      tb = bits of a time (< N), wb = bits of a pixel id (< N): as few radix passes as the frame size
+//      allows (1080p: 21 + 21 + 5 = 47 bits -> 6 passes)
 // ---------------------------------------------------------------------------------------------
 #define EV_KEY_NONE 0xFFFFFFFFFFFFFFFFull
 

@@ -172,18 +172,16 @@ def near_tie_field(W, H, seed=0):
     return f
 
 
-@pytest.mark.parametrize("W,H,fallback", [(24, 20, 0), (300, 200, 1)])
-def test_sorted_edges_long_prefix_runs(dofs, port, W, H, fallback):
-    """Runs of equal prefix longer than a thread repairs: shared-memory sort (<= 2048 edges) or, beyond that, the
-    full 64-bit radix sort enabled on the device."""
+@pytest.mark.parametrize("W,H", [(24, 20), (300, 200)])
+def test_sorted_edges_long_prefix_runs(dofs, port, W, H):
+    """Parity hook (full edge list): runs of equal prefix longer than a thread repairs: shared-memory sort (<= 2048 edges)
+    or, beyond that, the full 64-bit radix sort enabled on the device."""
     fb = near_tie_field(W, H)
     s, e, w = port.build_graph(fb, True)
     with dofs.Context(W, H) as c:
         gs, ge, gw = c.edges_sorted(fb)
-        st = c.segment(fb, already_blurred=True)["stats"][0]
     assert np.array_equal(gw.view(np.uint64), w.view(np.uint64))
     assert np.array_equal(gs, s) and np.array_equal(ge, e)
-    assert st["sort_fallback"] == fallback
 
 
 def test_sorted_edges_reference_golden(dofs, golden_pair):
@@ -216,7 +214,7 @@ def compare_boxes(boxes, psets, entries, W):
             assert np.array_equal(np.asarray(b["mean_flow"]).view(np.uint32), e["flow"].view(np.uint32))  # bit-exact running mean
 
 
-def run_and_compare(dofs, port, fields, neighbors=8, min_size=500, score_threshold=0.3):
+def run_and_compare(dofs, port, fields, neighbors=8, min_size=500, score_threshold=0.3, want_stats=False):
     from denseopticalflowsegmentation3d_b200.capi import box_pixel_sets
     fields = np.stack(fields)
     n, H, W, _ = fields.shape
@@ -234,7 +232,7 @@ def run_and_compare(dofs, port, fields, neighbors=8, min_size=500, score_thresho
         assert st["n_candidates"] == cn["get_score"]
         assert st["n_boxes"] == len(res["entries"])
         total += len(boxes)
-    return total
+    return (total, out["stats"]) if want_stats else total
 
 
 @pytest.mark.parametrize("seed,W,H,nb", [(11, 160, 96, 8), (12, 131, 77, 4), (13, 200, 120, 8)])
@@ -251,6 +249,30 @@ def test_segments_degenerate_fields(dofs, port):
     ramp = np.zeros((H, W, 2), np.float32)
     ramp[..., 1] = np.linspace(0, 6, H, dtype=np.float32)[:, None]  # strictly ordered rows
     run_and_compare(dofs, port, [zero, const, ramp, near_tie_field(W, H)], min_size=50)
+
+
+def near_tie_columns(W, H, seed=0):
+    """near_tie_field with columns 1000 apart: the cheapest edge of every pixel is its vertical one, so the spanning forest
+    holds (H-1)*W edges of weight 1 + O(1e-8) — one long run of equal prefix among the ACCEPTED edges."""
+    f = near_tie_field(W, H, seed)
+    f[..., 1] += 1000.0 * np.arange(W, dtype=np.float32)[None, :]
+    return f
+
+
+@pytest.mark.parametrize("W,H,fallback", [(24, 20, 0), (300, 200, 1)])
+def test_merge_times_long_prefix_runs(dofs, port, W, H, fallback):
+    """Merge times (sort of the accepted edges only): a long run of equal prefix is ordered in shared memory
+    (<= 2048 edges) or by the exact 64-bit fallback sort enabled on the device."""
+    _, stats = run_and_compare(dofs, port, [near_tie_columns(W, H), near_tie_field(W, H)], min_size=50, want_stats=True)
+    assert stats[0]["sort_fallback"] == fallback
+
+
+def test_merge_times_forced_fallback(dofs, port, monkeypatch):
+    """DOFS3D_FORCE_TIME_FALLBACK=1: every frame takes the exact fallback sort; results must not change."""
+    monkeypatch.setenv("DOFS3D_FORCE_TIME_FALLBACK", "1")
+    fields = [random_flow(21 + 100 * k, 160, 96, scale=4.0) for k in range(2)]
+    n, stats = run_and_compare(dofs, port, fields, min_size=60, want_stats=True)
+    assert n > 0 and all(st["sort_fallback"] == 1 for st in stats)
 
 
 @pytest.mark.parametrize("name", ["golden_pair", "golden_synth"])
