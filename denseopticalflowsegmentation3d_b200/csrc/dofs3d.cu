@@ -394,56 +394,58 @@ int segment_dev(dofs3d_ctx* ctx, const float* d_flow, int already_blurred, int n
     LAUNCH(ctx, k_bor_finish, gS, SEG_THREADS, 0, B, N, levels);
     mark(ctx, "boruvka");
 
-    // K8 merge times: only the edges Boruvka picked are sorted (<= N-1 of the 4N slots)
-    const int tb = ceil_log2(ctx->S);
-    u64* tkA = ctx->keysA;                   // keysA holds F*4N u64: two key buffers, two fallback key buffers
-    u64* tkB = ctx->keysA + (size_t)F * N;
+    // K8 merge times: only the edges Boruvka picked are sorted (<= N-1 of the 4N slots), on a 32-bit key
+    u32* tkA = reinterpret_cast<u32*>(ctx->keysA);  // keysA holds F*4N u64: two u32 key buffers, then two u64 fallback buffers
+    u32* tkB = tkA + (size_t)F * N;
     u32* tvA = ctx->valsA;
     u32* tvB = ctx->valsB;
-    LAUNCH(ctx, k_time_keys, gS, SEG_THREADS, 0, B, prefix, ctx->S, tkA, N, tb);
+    LAUNCH(ctx, k_time_keys, gS, SEG_THREADS, 0, B, prefix, ctx->S, tkA, N);
     mark(ctx, "time_keys");
-    int side = radix_sort_onesweep<u64>(ctx, tkA, tvA, tkB, tvB, (size_t)N, N, n, 32 + tb, true, "time_sort.hist",
-                                        "time_sort.scatter");
+    int side = radix_sort_onesweep<u32>(ctx, tkA, tvA, tkB, tvB, (size_t)N, N, n, 32, true, "time_sort.hist", "time_sort.scatter");
     if (side < 0) {
         ctx->err = "internal: time key too wide";
         return DOFS3D_ERR_INTERNAL;
     }
-    u64* tk = side ? tkB : tkA;        // sorted keys
-    u64* tk_other = side ? tkA : tkB;  // dead
-    u32* order = side ? tvB : tvA;     // losing roots in (prefix, slot) order
+    const u32* tk = side ? tkB : tkA;  // sorted keys
+    u32* order = side ? tvB : tvA;     // losing roots in key order
     u32* order_other = side ? tvA : tvB;
+    u32* times = B.newp;               // the hook targets are dead: per root id, the position of its loss in the merge sequence
     CK(cudaMemsetAsync(ctx->repair_flags, 0, 2 * sizeof(int), ctx->stream));
     if (ctx->force_time_fallback) CK(cudaMemsetAsync(ctx->repair_flags + 1, 1, 1, ctx->stream));
     {
         TimeRepairArgs R;
         R.key = tk;
         R.comp = order;
+        R.slot = B.loss_time;
         R.flow = ctx->flow_blur;
-        R.time = B.loss_time;
+        R.time = times;
         R.long_list = ctx->long_list;
         R.long_count = ctx->repair_flags;
         R.need_full = ctx->repair_flags + 1;
         R.list_cap = ctx->list_cap;
         R.N = N;
         R.W = W;
-        R.tb = tb;
         LAUNCH(ctx, k_time_repair_short, gN, SEG_THREADS, 0, R);
         LAUNCH(ctx, k_time_repair_long, dim3(148 * 2), 256, 0, R);
         mark(ctx, "time_repair");
-        // fallback, enabled on the device by *need_full: stable 64-bit sort of the (prefix, slot)-ordered list by weight
+        // fallback, enabled on the device by *need_full: stable 64-bit sorts by slot, then by weight
         const int* enable = ctx->repair_flags + 1;
-        u64* fwA = ctx->keysA + 2 * (size_t)F * N;
-        LAUNCH(ctx, k_time_fallback_keys, dim3(std::max(1, 148 * 4 / n), n), SEG_THREADS, 0, tk, ctx->flow_blur, fwA, N, W, tb,
-               enable);
-        const int fside = radix_sort<u64>(ctx, fwA, order, tk_other, order_other, (size_t)N, N, n, 64, false, "time_fallback",
-                                          "time_fallback", "time_fallback", enable);
-        if (fside != 0) {
-            ctx->err = "internal: odd number of sort passes";
-            return DOFS3D_ERR_INTERNAL;
-        }
-        LAUNCH(ctx, k_time_fallback_rank, dim3(std::max(1, 148 * 4 / n), n), SEG_THREADS, 0, fwA, order, B.loss_time, N, enable);
+        const dim3 gF(std::max(1, 148 * 4 / n), n);
+        u64* fA = ctx->keysA + (size_t)F * N;
+        u64* fB = ctx->keysA + 2 * (size_t)F * N;
+        LAUNCH(ctx, k_time_fallback_slots, gF, SEG_THREADS, 0, order, B.loss_time, fA, N, enable);
+        int fs = radix_sort<u64>(ctx, fA, order, fB, order_other, (size_t)N, N, n, ceil_log2(ctx->S), false, "time_fallback",
+                                 "time_fallback", "time_fallback", enable);
+        u32* o1 = fs ? order_other : order;  // roots in slot order
+        u32* o1_other = fs ? order : order_other;
+        LAUNCH(ctx, k_time_fallback_weights, gF, SEG_THREADS, 0, o1, B.loss_time, ctx->flow_blur, fA, N, W, enable);
+        fs = radix_sort<u64>(ctx, fA, o1, fB, o1_other, (size_t)N, N, n, 64, false, "time_fallback", "time_fallback",
+                             "time_fallback", enable);
+        LAUNCH(ctx, k_time_fallback_rank, gF, SEG_THREADS, 0, fs ? fB : fA, fs ? o1_other : o1, times, N, enable);
         mark(ctx, "time_fallback");
     }
+    BorState BT = B;  // from here on loss_time means time
+    BT.loss_time = times;
 
     // K9b events: winner of every loss, sorted by (wave, winner, time); buffers alias the dead edge prefixes / time keys
     EvBits eb;
@@ -453,7 +455,7 @@ int segment_dev(dofs3d_ctx* ctx, const float* d_flow, int already_blurred, int n
     u64* evB = ctx->keysB + (size_t)F * N;
     u32* evlA = ctx->valsA;
     u32* evlB = ctx->valsB;
-    LAUNCH(ctx, k_event_keys, gS, SEG_THREADS, 0, B, ctx->win, evA, N, eb);
+    LAUNCH(ctx, k_event_keys, gS, SEG_THREADS, 0, BT, ctx->win, evA, N, eb);
     mark(ctx, "event_keys");
     side = radix_sort_onesweep<u64>(ctx, evA, evlA, evB, evlB, (size_t)N, N, n, eb.tb + eb.wb + 5, true, "event_sort.hist",
                                     "event_sort.scatter");
@@ -528,9 +530,9 @@ int segment_dev(dofs3d_ctx* ctx, const float* d_flow, int already_blurred, int n
     const dim3 gB = grid1(ctx->box_cap, SEG_THREADS, n);
     LAUNCH(ctx, k_sort_boxes<dofs3d_box>, gB, SEG_THREADS, 0, ctx->boxes_tmp, ctx->boxes, A.n_boxes, ctx->box_cap,
            ctx->sel_box, N);
-    LAUNCH(ctx, k_box_parents<dofs3d_box>, gB, SEG_THREADS, 0, ctx->boxes, A.n_boxes, ctx->box_cap, B.loss_time,
+    LAUNCH(ctx, k_box_parents<dofs3d_box>, gB, SEG_THREADS, 0, ctx->boxes, A.n_boxes, ctx->box_cap, BT.loss_time,
            ctx->win, ctx->sel_time, ctx->sel_box, N);
-    LAUNCH(ctx, k_labels, gN, SEG_THREADS, 0, ctx->labels, B.loss_time, ctx->win, ctx->sel_time, ctx->sel_box, N);
+    LAUNCH(ctx, k_labels, gN, SEG_THREADS, 0, ctx->labels, BT.loss_time, ctx->win, ctx->sel_time, ctx->sel_box, N);
     mark(ctx, "labels");
 
     // counters -> stats record, on the device; a copy lands in pinned host memory for the host-pointer entry points
@@ -645,7 +647,7 @@ int dofs3d_create(dofs3d_ctx** out, int device, int width, int height, int max_p
     if (!out) return DOFS3D_ERR_ARG;
     *out = nullptr;
     if (width < 2 || height < 2 || width > 65535 || height > 65535 || max_pairs < 1) return DOFS3D_ERR_ARG;
-    if ((unsigned long long)width * height > (1ull << 27)) return DOFS3D_ERR_ARG;
+    if ((unsigned long long)width * height > (1ull << 26)) return DOFS3D_ERR_ARG;  // 4N slots stay below TIME_KEY_MIN_PREFIX
     int n_dev = 0;
     if (cudaGetDeviceCount(&n_dev) != cudaSuccess || device < 0 || device >= n_dev) return DOFS3D_ERR_CUDA;
     dofs3d_ctx* ctx = new dofs3d_ctx();

@@ -455,8 +455,9 @@ struct BorState {
     u32* comp;       // [F][N] current root of each pixel
     u64* best;       // [F][N] per root: its minimum outgoing edge in this level, as a pick (prefix << 32 | slot)
     u32* newp;       // [F][N] per root: hook target in this level
-    u32* loss_time;  // [F][N] per root id: while the levels run, the slot of the edge at which it loses; after k_time_*
-                     //         the position of that edge in the reference's merge sequence (INF: never loses)
+    u32* loss_time;  // [F][N] per root id: the slot of the edge at which it loses (INF: never loses).  The kernels after
+                     //         K8 get a copy of this struct whose loss_time is the time array instead: the position of that
+                     //         edge in the reference's merge sequence
     u32* up;         // [F][N] per root id: root of the next-level component it is contracted into (itself while live)
     u8* lvl;         // [F][N] per root id: level at which it loses == its final union-find rank
     u8* mask;        // [F][N] per pixel: which of its 8 incident edges still join different components
@@ -595,35 +596,37 @@ k_bor_pixel(BorState S, const u32* __restrict__ prefix, size_t prefix_stride, co
         const u32 cp = comp[p];
         const u64 seen0 = best[cp];
         // independent loads first (the kernel is bound by memory latency): neighbour components, then their prefixes
-        u32 cq[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) cq[e] = ((m >> e) & 1u) ? comp[incident_pixel(p, e, W)] : cp;
         u32 out = 0;
 #pragma unroll
-        for (int e = 0; e < 8; ++e) out |= cq[e] != cp ? 1u << e : 0u;
+        for (int e = 0; e < 8; ++e)
+            if (((m >> e) & 1u) && comp[incident_pixel(p, e, W)] != cp) out |= 1u << e;
         if (out != m) S.mask[fo + p] = (u8)out;  // an edge that became internal stays internal
         if (out == 0) continue;
-        u64 cand[8];
-        if (out & 15u) {
-            const uint4 r4 = *reinterpret_cast<const uint4*>(pre + 4 * (size_t)p);
-            cand[0] = make_pick(r4.x, 4u * (u32)p);
-            cand[1] = make_pick(r4.y, 4u * (u32)p + 1u);
-            cand[2] = make_pick(r4.z, 4u * (u32)p + 2u);
-            cand[3] = make_pick(r4.w, 4u * (u32)p + 3u);
+        u32 pr[8];
+        {
+            uint4 r4 = make_uint4(0u, 0u, 0u, 0u);
+            if (out & 15u) r4 = *reinterpret_cast<const uint4*>(pre + 4 * (size_t)p);
+            pr[0] = r4.x, pr[1] = r4.y, pr[2] = r4.z, pr[3] = r4.w;
         }
 #pragma unroll
-        for (int e = 4; e < 8; ++e) {
-            const u32 slot = incident_slot(p, e, W);
-            cand[e] = ((out >> e) & 1u) ? make_pick(pre[slot], slot) : PICK_NONE;
+        for (int e = 4; e < 8; ++e) pr[e] = ((out >> e) & 1u) ? pre[incident_slot(p, e, W)] : 0u;
+        // smallest (prefix, slot) among the outgoing edges: visited in ascending slot order, so '<' keeps the first
+        u32 pmin = 0xFFFFFFFFu, smin = 0, same = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            constexpr int order[8] = {6, 0, 1, 2, 3, 4, 7, 5};
+            const int e = order[k];
+            if ((out >> e) & 1u) {
+                same += pr[e] == pmin ? 1u : 0u;
+                if (pr[e] < pmin) {
+                    pmin = pr[e];
+                    smin = incident_slot(p, e, W);
+                    same = 0;
+                }
+            }
         }
-        u64 mine = PICK_NONE;
-#pragma unroll
-        for (int e = 0; e < 8; ++e)
-            if ((out >> e) & 1u) mine = min(mine, cand[e]);
-        u32 flags = 0;
-#pragma unroll
-        for (int e = 0; e < 8; ++e)
-            if (((out >> e) & 1u) && pick_meets(cand[e], mine)) flags |= PIX_TIE_LOCAL;
+        const u64 mine = make_pick(pmin, smin);
+        u32 flags = (same != 0 && pmin != 0u) ? PIX_TIE_LOCAL : 0u;
         u64 seen = seen0;
         if (mine < seen) {
             seen = atomicMin(reinterpret_cast<unsigned long long*>(&best[cp]), (unsigned long long)mine);
@@ -798,40 +801,52 @@ k_bor_finish(BorState S, int N, int max_levels) {
 // ---------------------------------------------------------------------------------------------
 // K8  merge times.  The reference's loop accepts exactly the edges Boruvka picked (the minimum spanning forest
 // under (weight, sequence)); their relative order in the sorted edge list is all that the merge sequence depends
-// on.  So only those <= N-1 edges are sorted: key = prefix << tb | slot (tb = bits of a slot), payload = the root
-// that loses at the edge; runs of equal prefix are then put in exact (weight, slot) order (stable by weight: they
-// are already in slot order) and loss_time[c] becomes the position = the index of the merge in the reference's
-// sequence of accepted edges.
+// on.  So only those <= N-1 edges are sorted, on ONE 32-bit key per losing root:
+//     weight == 0 (prefix 0)  ->  key = slot            (exact order among them; below every other key, see TIME_KEY_MIN_PREFIX)
+//     otherwise               ->  key = prefix
+// Four 8-bit passes (payload = the root).  Keys below TIME_KEY_MIN_PREFIX are unique, so their position is their
+// time.  Runs of an equal prefix are rare and short; they are put in exact (weight, slot) order:
 //   k_time_keys           one key per root id (roots that never lose: TIME_KEY_NONE, sorted last)
 //   k_time_repair_short   runs of <= REPAIR_SHORT edges: insertion sort in the head thread
-//   k_time_repair_long    longer runs, a block each: identical weights are already in order; <= REPAIR_SMEM edges
-//                         are sorted in shared memory; beyond that *need_full enables the exact fallback:
-//   k_time_fallback_keys  full weights of the sorted list, stably sorted by the conditional 64-bit radix sort
-//   k_time_fallback_rank  positions after that sort
+//   k_time_repair_long    longer runs, a block each: <= REPAIR_SMEM edges are sorted in shared memory; beyond that
+//                         *need_full enables the exact fallback: a stable 64-bit radix sort by slot, then by weight
+//                         (k_time_fallback_slots / k_time_fallback_weights / k_time_fallback_rank)
+// time[c] = position = index of the merge in the reference's sequence of accepted edges.
 // ---------------------------------------------------------------------------------------------
-#define TIME_KEY_NONE 0xFFFFFFFFFFFFFFFFull
+#define TIME_KEY_NONE 0xFFFFFFFFu
+// the smallest prefix of a non-zero weight: a float flow field has no difference below 2^-149, i.e. (200 - 149) << 23
+#define TIME_KEY_MIN_PREFIX 0x19800000u
 
 __global__ void __launch_bounds__(SEG_THREADS)
-k_time_keys(BorState S, const u32* __restrict__ prefix, size_t prefix_stride, u64* __restrict__ tkey, int N, int tb) {
+k_time_keys(BorState S, const u32* __restrict__ prefix, size_t prefix_stride, u32* __restrict__ tkey, int N) {
     const int frame = blockIdx.y;
     const size_t fo = (size_t)frame * N;
     GRID_STRIDE(c, N) {
         const u32 slot = S.loss_time[fo + c];
-        tkey[fo + c] = slot == DOFS_INF32 ? TIME_KEY_NONE : (((u64)prefix[(size_t)frame * prefix_stride + slot] << tb) | slot);
+        u32 k = TIME_KEY_NONE;
+        if (slot != DOFS_INF32) {
+            const u32 pr = prefix[(size_t)frame * prefix_stride + slot];
+            k = pr == 0u ? slot : pr;
+        }
+        tkey[fo + c] = k;
     }
 }
 
 struct TimeRepairArgs {
-    const u64* key;      // [F][N] sorted keys
+    const u32* key;      // [F][N] sorted keys
     const u32* comp;     // [F][N] sorted payload (losing roots); the list itself is left as it is
+    const u32* slot;     // [F][N] by root id: the slot of the edge at which it loses
     const float2* flow;  // [F][N] blurred flow
     u32* time;           // [F][N] out: time[c] = position, INF for roots that never lose
     uint2* long_list;    // (frame, start)
     int* long_count;
     int* need_full;
     int list_cap;
-    int N, W, tb;
+    int N, W;
 };
+
+// (weight, slot) order of two edges that share a prefix
+DOFS_D bool run_less(u64 wa, u32 sa, u64 wb, u32 sb) { return wa != wb ? wa < wb : sa < sb; }
 
 __global__ void __launch_bounds__(SEG_THREADS)
 k_time_repair_short(TimeRepairArgs A) {
@@ -839,45 +854,46 @@ k_time_repair_short(TimeRepairArgs A) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= A.N) return;
     const size_t fo = (size_t)frame * A.N;
-    const u64* key = A.key + fo;
-    const u64 k = key[i];
+    const u32* key = A.key + fo;
+    const u32 k = key[i];
     if (k == TIME_KEY_NONE) {
         A.time[fo + A.comp[fo + i]] = DOFS_INF32;
         return;
     }
-    const u64 pre = k >> A.tb;
-    const bool prev_same = i > 0 && (key[i - 1] >> A.tb) == pre;
-    const bool next_same = i + 1 < A.N && (key[i + 1] >> A.tb) == pre;  // TIME_KEY_NONE >> tb is no edge's prefix
+    const bool prev_same = k >= TIME_KEY_MIN_PREFIX && i > 0 && key[i - 1] == k;
+    const bool next_same = k >= TIME_KEY_MIN_PREFIX && i + 1 < A.N && key[i + 1] == k;
     if (!prev_same && !next_same) {
         A.time[fo + A.comp[fo + i]] = (u32)i;
         return;
     }
     if (prev_same) return;  // the head of the run does the work
     int len = 2;
-    while (len <= REPAIR_SHORT && i + len < A.N && (key[i + len] >> A.tb) == pre) ++len;
+    while (len <= REPAIR_SHORT && i + len < A.N && key[i + len] == k) ++len;
     if (len > REPAIR_SHORT) {
         const int slot = atomicAdd(A.long_count, 1);
         if (slot < A.list_cap) A.long_list[slot] = make_uint2((u32)frame, (u32)i);
         else atomicExch(A.need_full, 1);
         return;
     }
-    const u32 slot_mask = (u32)((1ull << A.tb) - 1ull);
-    u32 cc[REPAIR_SHORT];
+    u32 cc[REPAIR_SHORT], ss[REPAIR_SHORT];
     u64 kk[REPAIR_SHORT];
     for (int j = 0; j < len; ++j) {
         cc[j] = A.comp[fo + i + j];
-        kk[j] = slot_weight(A.flow + fo, (u32)key[i + j] & slot_mask, A.W);
+        ss[j] = A.slot[fo + cc[j]];
+        kk[j] = slot_weight(A.flow + fo, ss[j], A.W);
     }
-    for (int j = 1; j < len; ++j) {  // stable insertion sort by weight
-        const u32 c = cc[j];
+    for (int j = 1; j < len; ++j) {  // insertion sort by (weight, slot)
+        const u32 c = cc[j], sl = ss[j];
         const u64 w = kk[j];
         int m = j - 1;
-        while (m >= 0 && kk[m] > w) {
+        while (m >= 0 && run_less(w, sl, kk[m], ss[m])) {
             cc[m + 1] = cc[m];
+            ss[m + 1] = ss[m];
             kk[m + 1] = kk[m];
             --m;
         }
         cc[m + 1] = c;
+        ss[m + 1] = sl;
         kk[m + 1] = w;
     }
     for (int j = 0; j < len; ++j) A.time[fo + cc[j]] = (u32)(i + j);
@@ -887,82 +903,84 @@ __global__ void __launch_bounds__(256)
 k_time_repair_long(TimeRepairArgs A) {
     __shared__ u64 s_key[REPAIR_SMEM];
     __shared__ u32 s_cmp[REPAIR_SMEM];
-    __shared__ int s_flag, s_len;
+    __shared__ u32 s_slot[REPAIR_SMEM];
+    __shared__ int s_len;
     const int n_list = min(*A.long_count, A.list_cap);
-    const u32 slot_mask = (u32)((1ull << A.tb) - 1ull);
     for (int item = blockIdx.x; item < n_list; item += gridDim.x) {
         const uint2 it = A.long_list[item];
         const size_t fo = (size_t)it.x * A.N;
         const int i0 = (int)it.y;
-        const u64* key = A.key + fo;
+        const u32* key = A.key + fo;
         const float2* f = A.flow + fo;
-        const u64 pre = key[i0] >> A.tb;
+        const u32 k = key[i0];
         // length of the run
         if (threadIdx.x == 0) s_len = A.N - i0;
         __syncthreads();
         for (int base = 0; base < A.N - i0; base += 256) {
             const int j = base + threadIdx.x;
-            if (j < A.N - i0 && (key[i0 + j] >> A.tb) != pre) atomicMin(&s_len, j);
+            if (j < A.N - i0 && key[i0 + j] != k) atomicMin(&s_len, j);
             __syncthreads();
             const int seen = s_len;
             __syncthreads();
             if (seen <= base + 256) break;
         }
         const int len = s_len;
-        // identical weights?
-        const u64 w0 = slot_weight(f, (u32)key[i0] & slot_mask, A.W);
-        if (threadIdx.x == 0) s_flag = 0;
         __syncthreads();
-        int differs = 0;
-        for (int j = threadIdx.x; j < len; j += 256) differs |= slot_weight(f, (u32)key[i0 + j] & slot_mask, A.W) != w0;
-        if (differs) s_flag = 1;
-        __syncthreads();
-        const bool trivial = s_flag == 0;
-        __syncthreads();
-        if (!trivial && len > REPAIR_SMEM) {
+        if (len > REPAIR_SMEM) {
             if (threadIdx.x == 0) atomicExch(A.need_full, 1);
             continue;  // block-uniform
         }
-        if (!trivial) {
-            // odd-even transposition sort in shared memory: stable, len rounds of disjoint compare-exchanges
-            for (int j = threadIdx.x; j < len; j += 256) {
-                s_cmp[j] = A.comp[fo + i0 + j];
-                s_key[j] = slot_weight(f, (u32)key[i0 + j] & slot_mask, A.W);
+        // odd-even transposition sort in shared memory by (weight, slot): len rounds of disjoint compare-exchanges
+        for (int j = threadIdx.x; j < len; j += 256) {
+            const u32 c = A.comp[fo + i0 + j];
+            s_cmp[j] = c;
+            s_slot[j] = A.slot[fo + c];
+            s_key[j] = slot_weight(f, s_slot[j], A.W);
+        }
+        __syncthreads();
+        for (int round = 0; round < len; ++round) {
+            for (int j = 2 * threadIdx.x + (round & 1); j + 1 < len; j += 512) {
+                if (run_less(s_key[j + 1], s_slot[j + 1], s_key[j], s_slot[j])) {
+                    const u64 tk = s_key[j];
+                    s_key[j] = s_key[j + 1];
+                    s_key[j + 1] = tk;
+                    const u32 ts = s_cmp[j];
+                    s_cmp[j] = s_cmp[j + 1];
+                    s_cmp[j + 1] = ts;
+                    const u32 tl = s_slot[j];
+                    s_slot[j] = s_slot[j + 1];
+                    s_slot[j + 1] = tl;
+                }
             }
             __syncthreads();
-            for (int round = 0; round < len; ++round) {
-                for (int j = 2 * threadIdx.x + (round & 1); j + 1 < len; j += 512) {
-                    if (s_key[j] > s_key[j + 1]) {
-                        const u64 tk = s_key[j];
-                        s_key[j] = s_key[j + 1];
-                        s_key[j + 1] = tk;
-                        const u32 ts = s_cmp[j];
-                        s_cmp[j] = s_cmp[j + 1];
-                        s_cmp[j + 1] = ts;
-                    }
-                }
-                __syncthreads();
-            }
-            for (int j = threadIdx.x; j < len; j += 256) A.time[fo + s_cmp[j]] = (u32)(i0 + j);
-        } else {
-            for (int j = threadIdx.x; j < len; j += 256) A.time[fo + A.comp[fo + i0 + j]] = (u32)(i0 + j);
         }
+        for (int j = threadIdx.x; j < len; j += 256) A.time[fo + s_cmp[j]] = (u32)(i0 + j);
         __syncthreads();
     }
 }
 
-// fallback (enabled on the device by *enable): the list is in (prefix, slot) order; a stable sort by the full weight
-// gives (weight, slot) order
+// fallback (enabled on the device by *enable): LSD order (weight, slot) = stable sort by slot, then stable sort by weight
 __global__ void __launch_bounds__(SEG_THREADS)
-k_time_fallback_keys(const u64* __restrict__ key, const float2* __restrict__ flow, u64* __restrict__ wkey, int N, int W, int tb,
-                     const int* __restrict__ enable) {
+k_time_fallback_slots(const u32* __restrict__ comp, const u32* __restrict__ slot, u64* __restrict__ skey, int N,
+                      const int* __restrict__ enable) {
     if (*enable == 0) return;
     const int frame = blockIdx.y;
     const size_t fo = (size_t)frame * N;
-    const u32 slot_mask = (u32)((1ull << tb) - 1ull);
     GRID_STRIDE(i, N) {
-        const u64 k = key[fo + i];
-        wkey[fo + i] = k == TIME_KEY_NONE ? TIME_KEY_NONE : slot_weight(flow + fo, (u32)k & slot_mask, W);
+        const u32 sl = slot[fo + comp[fo + i]];
+        skey[fo + i] = sl == DOFS_INF32 ? 0xFFFFFFFFFFFFFFFFull : (u64)sl;
+    }
+}
+
+__global__ void __launch_bounds__(SEG_THREADS)
+k_time_fallback_weights(const u32* __restrict__ comp, const u32* __restrict__ slot, const float2* __restrict__ flow,
+                        u64* __restrict__ wkey, int N, int W, const int* __restrict__ enable) {
+    if (*enable == 0) return;
+    const int frame = blockIdx.y;
+    const size_t fo = (size_t)frame * N;
+    GRID_STRIDE(i, N) {
+        const u32 sl = slot[fo + comp[fo + i]];
+        wkey[fo + i] = sl == DOFS_INF32 ? 0xFFFFFFFFFFFFFFFFull : slot_weight(flow + fo, sl, W);
     }
 }
 
@@ -972,7 +990,7 @@ k_time_fallback_rank(const u64* __restrict__ wkey, const u32* __restrict__ comp,
     if (*enable == 0) return;
     const int frame = blockIdx.y;
     const size_t fo = (size_t)frame * N;
-    GRID_STRIDE(i, N) time[fo + comp[fo + i]] = wkey[fo + i] == TIME_KEY_NONE ? DOFS_INF32 : (u32)i;
+    GRID_STRIDE(i, N) time[fo + comp[fo + i]] = wkey[fo + i] == 0xFFFFFFFFFFFFFFFFull ? DOFS_INF32 : (u32)i;
 }
 
 // ---------------------------------------------------------------------------------------------
