@@ -347,7 +347,6 @@ k_pyr_level0(ImageSet imgs, float* __restrict__ I, int W, int H, SmoothTaps taps
 __global__ void __launch_bounds__(PE_TW * PE_TH)
 k_polyexp(const float* __restrict__ I, float* __restrict__ R, int Wk, int Hk, PolyCoef pc) {
     __shared__ float s_row[3][PE_TH][PE_TW + 2 * FLOW_MAX_POLY_N];
-    __shared__ float s_out[PE_TH][PE_TW * 5];
     const int img = blockIdx.z;
     const int n = pc.n;
     const int x0 = blockIdx.x * PE_TW, y0 = blockIdx.y * PE_TH;
@@ -373,38 +372,29 @@ k_polyexp(const float* __restrict__ I, float* __restrict__ R, int Wk, int Hk, Po
     }
     __syncthreads();
     const int tx = threadIdx.x & (PE_TW - 1), ty = threadIdx.x / PE_TW;
-    {
-        const float* r0 = &s_row[0][ty][tx + n];
-        const float* r1 = &s_row[1][ty][tx + n];
-        const float* r2 = &s_row[2][ty][tx + n];
-        double b1 = (double)xfmul(r0[0], pc.g[0]), b2 = 0, b3 = (double)xfmul(r1[0], pc.g[0]), b4 = 0;
-        double b5 = (double)xfmul(r2[0], pc.g[0]), b6 = 0;
-        for (int k = 1; k <= n; ++k) {
-            const double tg = (double)xfadd(r0[k], r0[-k]);
-            const float g0 = pc.g[k];
-            b1 = xdadd(b1, xdmul(tg, (double)g0));
-            b4 = xdadd(b4, xdmul(tg, (double)pc.xxg[k]));
-            b2 = xdadd(b2, (double)xfmul(xfsub(r0[k], r0[-k]), pc.xg[k]));
-            b3 = xdadd(b3, (double)xfmul(xfadd(r1[k], r1[-k]), g0));
-            b6 = xdadd(b6, (double)xfmul(xfsub(r1[k], r1[-k]), pc.xg[k]));
-            b5 = xdadd(b5, (double)xfmul(xfadd(r2[k], r2[-k]), g0));
-        }
-        // the five coefficients of a pixel are 20 contiguous bytes: stage the tile row (32 x 5 floats, stride 5 is
-        // conflict-free) and write it out as whole coalesced lines instead of five stride-20 stores per warp
-        float* o = &s_out[ty][tx * 5];
-        o[0] = (float)xdmul(b3, pc.ig11);
-        o[1] = (float)xdmul(b2, pc.ig11);
-        o[2] = (float)xdadd(xdmul(b1, pc.ig03), xdmul(b5, pc.ig33));
-        o[3] = (float)xdadd(xdmul(b1, pc.ig03), xdmul(b4, pc.ig33));
-        o[4] = (float)xdmul(b6, pc.ig55);
+    const int x = x0 + tx, y = y0 + ty;
+    if (x >= Wk || y >= Hk) return;
+    const float* r0 = &s_row[0][ty][tx + n];
+    const float* r1 = &s_row[1][ty][tx + n];
+    const float* r2 = &s_row[2][ty][tx + n];
+    double b1 = (double)xfmul(r0[0], pc.g[0]), b2 = 0, b3 = (double)xfmul(r1[0], pc.g[0]), b4 = 0;
+    double b5 = (double)xfmul(r2[0], pc.g[0]), b6 = 0;
+    for (int k = 1; k <= n; ++k) {
+        const double tg = (double)xfadd(r0[k], r0[-k]);
+        const float g0 = pc.g[k];
+        b1 = xdadd(b1, xdmul(tg, (double)g0));
+        b4 = xdadd(b4, xdmul(tg, (double)pc.xxg[k]));
+        b2 = xdadd(b2, (double)xfmul(xfsub(r0[k], r0[-k]), pc.xg[k]));
+        b3 = xdadd(b3, (double)xfmul(xfadd(r1[k], r1[-k]), g0));
+        b6 = xdadd(b6, (double)xfmul(xfsub(r1[k], r1[-k]), pc.xg[k]));
+        b5 = xdadd(b5, (double)xfmul(xfadd(r2[k], r2[-k]), g0));
     }
-    __syncthreads();
-    const int valid = min(PE_TW, Wk - x0) * 5;  // floats per tile row inside the image
-    for (int idx = threadIdx.x; idx < PE_TH * PE_TW * 5; idx += PE_TW * PE_TH) {
-        const int r = idx / (PE_TW * 5), j = idx - r * (PE_TW * 5);
-        const int y = y0 + r;
-        if (y < Hk && j < valid) R[(((size_t)img * Hk + y) * Wk + x0) * 5 + j] = s_out[r][j];
-    }
+    float* out = R + (((size_t)img * Hk + y) * Wk + x) * 5;
+    out[0] = (float)xdmul(b3, pc.ig11);
+    out[1] = (float)xdmul(b2, pc.ig11);
+    out[2] = (float)xdadd(xdmul(b1, pc.ig03), xdmul(b5, pc.ig33));
+    out[3] = (float)xdadd(xdmul(b1, pc.ig03), xdmul(b4, pc.ig33));
+    out[4] = (float)xdmul(b6, pc.ig55);
 }
 
 // ---------------------------------------------------------------------------------------------
