@@ -442,32 +442,45 @@ def ours(args):
         value = world * B * K / (ms_total / 1e3)
         e2e_value = world * B * K / (e2e_ms / 1e3)
         peak, peak_src = measured_peak_gbs()
-        # dominant kernel: one radix pass (scatter) over the 4N edge slots of a sub-batch, 32-bit prefix key + 32-bit
-        # sequence number: algorithmic bytes per launch = read (4 + 4) + write (4 + 4) per slot
-        slots = 4 * N * Bc
+        # Dominant bandwidth-bound kernel of the path: k_box_solve (FarnebackUpdateFlow_Blur: 15x15 box mean of the five
+        # matrix channels + the 2x2 solve).  The roofline figure is taken on its full-resolution launches (3 per call, one per
+        # iteration of pyramid level 0): algorithmic bytes per launch = (20 B of M read once + 8 B of flow written) per pixel.
+        box_bytes = 28 * N * Bc
 
         def roof_of(stages):
-            sc = stages.get("edge_sort.scatter", [0.0, 0])
+            sc = stages.get("flow.box_solve.L0", [0.0, 0])
             if sc[1] == 0:
                 return None
             ms_launch = sc[0] / sc[1]
-            achieved = slots * 16 / (ms_launch / 1e3) / 1e9
+            achieved = box_bytes / (ms_launch / 1e3) / 1e9
             return {"achieved": achieved, "frac": achieved / peak, "ms_per_launch": ms_launch, "launches_timed": sc[1]}
 
+        def sort_gbs(stages, name, bytes_per_launch):
+            sc = stages.get(name, [0.0, 0])
+            if sc[1] == 0:
+                return None
+            g = bytes_per_launch / (sc[0] / sc[1] / 1e3) / 1e9
+            return {"achieved": g, "frac": g / peak, "ms_per_launch": sc[0] / sc[1], "algorithmic_bytes_per_launch": bytes_per_launch}
+
+        n_iso = max(2, min(K, 3))
         live, iso = roof_of(stage_ms), roof_of(iso_ms)
         roof = None
         if iso:
             # the per-kernel figure is the kernel alone on the GPU (CUDA events around every launch, one context, right after
             # the timed region): inside the timed region NC contexts overlap, so an event-bracketed launch there also contains
             # the time it spends sharing the SMs and HBM with the other contexts' kernels (reported as in_timed_region)
-            roof = {"bound": "hbm", "kernel": "k_radix_onesweep<u32> (one 8-bit pass of the edge sort)", "achieved": iso["achieved"],
-                    "peak": peak, "unit": "GB/s", "frac": iso["frac"], "traffic": ncu_traffic_bytes("k_radix_onesweep<u32>"),
-                    "peak_source": peak_src, "algorithmic_bytes_per_launch": slots * 16, "ms_per_launch": iso["ms_per_launch"],
-                    "launches_timed": iso["launches_timed"],
+            roof = {"bound": "hbm", "kernel": "k_box_solve (15x15 box mean of M + 2x2 solve), full-resolution launches",
+                    "achieved": iso["achieved"], "peak": peak, "unit": "GB/s", "frac": iso["frac"],
+                    "traffic": ncu_traffic_bytes("k_box_solve"), "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": box_bytes,
+                    "ms_per_launch": iso["ms_per_launch"], "launches_timed": iso["launches_timed"],
                     "how": "CUDA events on the launching stream around each launch, bench.py, one context alone on the GPU",
-                    "in_timed_region": dict(live or {}, note=f"context 0's launches while {NC - 1} other context(s) share the GPU")}
+                    "in_timed_region": dict(live or {}, note=f"context 0's launches while {NC - 1} other context(s) share the GPU"),
+                    "other_kernels": {
+                        "k_radix_onesweep<u32> (one 8-bit pass of the merge-time sort, key+payload read and written)":
+                            sort_gbs(iso_ms, "time_sort.scatter", 16 * N * Bc),
+                        "k_radix_onesweep<u64> (one 8-bit pass of the event sort)": sort_gbs(iso_ms, "event_sort.scatter", 24 * N * Bc)}}
         stages = {k: round(v[0] / K, 4) for k, v in sorted(stage_ms.items(), key=lambda kv: -kv[1][0])}
-        n_iso = max(2, min(K, 3))
         stages_iso = {k: round(v[0] / n_iso, 4) for k, v in sorted(iso_ms.items(), key=lambda kv: -kv[1][0])}
         whole_bytes = 1476 * N * B  # algorithmic HBM bytes per pixel per pair, whole path
         cfg = workload_config(args, world)

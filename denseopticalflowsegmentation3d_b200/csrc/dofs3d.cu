@@ -585,13 +585,14 @@ int export_results(dofs3d_ctx* ctx, int n, int32_t* labels_out, dofs3d_box* boxe
 // cvtColor + Farneback for n pairs out of n+1 consecutive gray frames already in ctx->gray
 int flow_dev(dofs3d_ctx* ctx, const u8* d_gray0, const u8* d_gray1, int n, float2* d_flow_out) {
     FlowLaunchStats st;
+    st.mark = [](void* u, const char* name) { mark(static_cast<dofs3d_ctx*>(u), name); };
+    st.user = ctx;
     int rc = farneback_run(ctx->fb, d_gray0, d_gray1, n, d_flow_out, ctx->stream, &st);
     ctx->launches += st.launches;
     if (rc) {
         ctx->err = "farneback_run failed";
         return DOFS3D_ERR_CUDA;
     }
-    mark(ctx, "farneback");
     return 0;
 }
 

@@ -90,7 +90,13 @@ struct FlowBuffers {
 
 struct FlowLaunchStats {
     long long launches = 0;
+    void (*mark)(void* user, const char* name) = nullptr;  // optional: called after the launches of every stage (timing marks)
+    void* user = nullptr;
 };
+#define FLOW_MARK(st, name)                              \
+    do {                                                  \
+        if ((st)->mark) (st)->mark((st)->user, name);     \
+    } while (0)
 
 inline int flow_cv_round(double v) { return (int)lrint(v); }  // round half to even, like cvRound
 
@@ -640,19 +646,25 @@ inline int farneback_run(FlowBuffers& fb, const u8* d_gray0, const u8* d_gray1, 
             k_flow_upsample<<<g_pair, blk, 0, stream>>>(prev, cur, Wp, Hp, L.w, L.h, 1.0 / fb.cfg.pyr_scale);
             st->launches++;
         }
+        FLOW_MARK(st, "flow.init");
         if (L.w == fb.W && L.h == fb.H && L.taps.radius == 1)
             k_pyr_level0<<<g_img, blk, 0, stream>>>(imgs, fb.I, fb.W, fb.H, L.taps);
         else
             k_pyr_level<<<g_img, blk, 0, stream>>>(imgs, fb.I, fb.W, fb.H, L.w, L.h, L.taps);
+        FLOW_MARK(st, "flow.pyramid");
         k_polyexp<<<g_img, blk, 0, stream>>>(fb.I, fb.R, L.w, L.h, fb.poly);
+        FLOW_MARK(st, "flow.polyexp");
         k_update_matrices<<<g_pair, blk, 0, stream>>>(fb.R, cur, fb.M, L.w, L.h, ps);
+        FLOW_MARK(st, "flow.update_matrices");
         st->launches += 3;
         for (int it = 0; it < fb.cfg.iters; ++it) {
             k_box_solve<<<g_box, box_solve_threads(m), bx_smem, stream>>>(fb.M, cur, L.w, L.h, m);
             st->launches++;
+            FLOW_MARK(st, k == 0 ? "flow.box_solve.L0" : "flow.box_solve");
             if (it < fb.cfg.iters - 1) {
                 k_update_matrices<<<g_pair, blk, 0, stream>>>(fb.R, cur, fb.M, L.w, L.h, ps);
                 st->launches++;
+                FLOW_MARK(st, "flow.update_matrices");
             }
         }
         prev = cur;
