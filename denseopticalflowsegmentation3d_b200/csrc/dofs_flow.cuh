@@ -599,6 +599,117 @@ k_box_solve(const float* __restrict__ M, float2* __restrict__ flow, int Wk, int 
     }
 }
 
+// The same kernel specialised for the reference's window (winsize 15 -> m = 7), with shared-memory layouts that keep
+// its phases free of bank conflicts (the kernel is bound by the L1/shared-memory pipeline, not by HBM): vertical sums
+// as [row][channel][column + column/8] (channel pitch 99 doubles spreads the five channels of a column over distinct
+// banks, row pitch 504 = 8 mod 16), window sums as [row][channel][x + x/8] (pitches 72 and 360).  A half-warp of the
+// horizontal phase = 8 groups of 8 outputs (9 doubles apart) x 2 rows: 16 distinct 64-bit banks.
+// Summation order is that of the generic kernel, so the results are bit-identical to it.
+#define BS7_M 7
+#define BS7_WIN 15
+#define BS7_COLS 64
+#define BS7_ROWS 64                      // rows per strip (one marching segment)
+#define BS7_SPAN (BS7_COLS + 2 * BS7_M)  // 78 strip columns
+#define BS7_VC 99                        // doubles per (row, channel) of vertical sums
+#define BS7_VR 504
+#define BS7_HC 72                        // doubles per (row, channel) of window sums
+#define BS7_HR (5 * BS7_HC)
+#define BS7_SUB 8                        // rows per shared-memory phase (a window of 15 rows = 8 + 7)
+#define BS7_THREADS 416                  // >= 78 * 5 owners, 13 warps
+#ifndef BS7_BLOCKS
+#define BS7_BLOCKS 3
+#endif
+DOFS_D constexpr int bs7_pad(int i) { return i + (i >> 3); }
+
+// horizontal sliding windows and the 2x2 solve for the nb rows whose vertical sums are in s_v (rows yb .. yb+nb-1)
+DOFS_D void bs7_rows(const double* s_v, double* s_h, float2* __restrict__ flow, int pair, int x0, int yb, int nb, int Wk, int Hk,
+                     double scale) {
+    constexpr int m = BS7_M;
+    const int e = threadIdx.x;
+    const int hg = e & 7, hr = (e >> 3) & 7, hc = e >> 6;  // work item = (group of 8 outputs, row, channel), groups fastest
+    __syncthreads();
+    if (hc < 5 && hr < nb) {
+        const double* v = s_v + hr * BS7_VR + hc * BS7_VC + 9 * hg;  // column 8*hg of the strip
+        double* h = s_h + hr * BS7_HR + hc * BS7_HC + 9 * hg;
+        double t = 0, lead[7];  // the first seven columns leave the window one by one: keep them instead of reading them twice
+#pragma unroll
+        for (int i = 0; i < 7; ++i) {
+            lead[i] = v[bs7_pad(i)];
+            t += lead[i];
+        }
+#pragma unroll
+        for (int i = 7; i <= 2 * m; ++i) t += v[bs7_pad(i)];
+        h[0] = t;
+#pragma unroll
+        for (int k = 1; k < 8; ++k) {
+            t += v[bs7_pad(k + 2 * m)] - lead[k - 1];
+            h[k] = t;
+        }
+    }
+    __syncthreads();
+    for (int o = e; o < nb * BS7_COLS; o += BS7_THREADS) {
+        const int tx = o & (BS7_COLS - 1), r = o >> 6;
+        const int x = x0 + tx, y = yb + r;
+        if (x >= Wk) continue;
+        const double* h = s_h + r * BS7_HR + bs7_pad(tx);
+        const double g11 = xdmul(h[0], scale), g12 = xdmul(h[BS7_HC], scale), g22 = xdmul(h[2 * BS7_HC], scale);
+        const double h1 = xdmul(h[3 * BS7_HC], scale), h2 = xdmul(h[4 * BS7_HC], scale);
+        const double idet = xddiv(1.0, xdadd(xdsub(xdmul(g11, g22), xdmul(g12, g12)), 1e-3));
+        const float u = (float)xdmul(xdsub(xdmul(g11, h2), xdmul(g12, h1)), idet);
+        const float w = (float)xdmul(xdsub(xdmul(g22, h1), xdmul(g12, h2)), idet);
+        flow[((size_t)pair * Hk + y) * Wk + x] = make_float2(u, w);
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(BS7_THREADS, BS7_BLOCKS)
+k_box_solve7(const float* __restrict__ M, float2* __restrict__ flow, int Wk, int Hk) {
+    extern __shared__ __align__(16) unsigned char bx7_smem[];
+    double* s_v = reinterpret_cast<double*>(bx7_smem);  // [BS7_SUB][5][BS7_VC] (+ padding to BS7_VR)
+    double* s_h = s_v + BS7_SUB * BS7_VR;               // [BS7_SUB][5][BS7_HC]
+    constexpr int m = BS7_M;
+    const int pair = blockIdx.z;
+    const int x0 = blockIdx.x * BS7_COLS;
+    const int y_begin = blockIdx.y * BS7_ROWS, y_end = min(y_begin + BS7_ROWS, Hk);
+    const float* src = M + (size_t)pair * Wk * Hk * 5;
+    const size_t pitch = (size_t)Wk * 5;
+    const int e = threadIdx.x;
+    const bool owner = e < BS7_SPAN * 5;
+    const float* col = src;
+    int v_at = 0;
+    if (owner) {
+        const int cx = e / 5, c = e - cx * 5;
+        col = src + (size_t)min(max(x0 + cx - m, 0), Wk - 1) * 5 + c;  // replicated border columns
+        v_at = c * BS7_VC + bs7_pad(cx);
+    }
+    double s = 0;
+    if (owner) {
+#pragma unroll
+        for (int j = -m; j <= m; ++j) s += (double)col[(size_t)min(max(y_begin + j, 0), Hk - 1) * pitch];
+    }
+    const double scale = 1.0 / (double)(BS7_WIN * BS7_WIN);
+    for (int yb = y_begin; yb < y_end; yb += BS7_SUB) {
+        const int nb = min(BS7_SUB, y_end - yb);
+        if (owner) {
+            float vin[BS7_SUB], vout[BS7_SUB];
+#pragma unroll
+            for (int r = 0; r < BS7_SUB; ++r) {
+                const int y = yb + r;
+                vin[r] = col[(size_t)min(y + m, Hk - 1) * pitch];
+                vout[r] = col[(size_t)max(y - m - 1, 0) * pitch];
+            }
+#pragma unroll
+            for (int r = 0; r < BS7_SUB; ++r) {
+                if (yb + r != y_begin) s += (double)vin[r] - (double)vout[r];
+                s_v[r * BS7_VR + v_at] = s;
+            }
+        }
+        bs7_rows(s_v, s_h, flow, pair, x0, yb, nb, Wk, Hk, scale);
+    }
+}
+
+#define BS7_SMEM ((size_t)BS7_SUB * (BS7_VR + BS7_HR) * sizeof(double))
+
 inline size_t box_solve_smem(int m) {
     const size_t cols = BS_COLS + 2 * m;
     return (size_t)BS_BATCH * cols * 5 * 8 + (size_t)BS_BATCH * BS_COLS * 5 * 8;
@@ -627,6 +738,8 @@ inline int farneback_run(FlowBuffers& fb, const u8* d_gray0, const u8* d_gray1, 
     static bool attr_set = false;
     if (!attr_set) {
         if (cudaFuncSetAttribute(k_box_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bx_smem) != cudaSuccess)
+            return 3;
+        if (cudaFuncSetAttribute(k_box_solve7, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BS7_SMEM) != cudaSuccess)
             return 3;
         attr_set = true;
     }
@@ -658,7 +771,11 @@ inline int farneback_run(FlowBuffers& fb, const u8* d_gray0, const u8* d_gray1, 
         FLOW_MARK(st, "flow.update_matrices");
         st->launches += 3;
         for (int it = 0; it < fb.cfg.iters; ++it) {
-            k_box_solve<<<g_box, box_solve_threads(m), bx_smem, stream>>>(fb.M, cur, L.w, L.h, m);
+            if (m == BS7_M)
+                k_box_solve7<<<dim3((L.w + BS7_COLS - 1) / BS7_COLS, (L.h + BS7_ROWS - 1) / BS7_ROWS, n), BS7_THREADS, BS7_SMEM,
+                               stream>>>(fb.M, cur, L.w, L.h);
+            else
+                k_box_solve<<<g_box, box_solve_threads(m), bx_smem, stream>>>(fb.M, cur, L.w, L.h, m);
             st->launches++;
             FLOW_MARK(st, k == 0 ? "flow.box_solve.L0" : "flow.box_solve");
             if (it < fb.cfg.iters - 1) {
