@@ -350,11 +350,13 @@ k_pyr_level0(ImageSet imgs, float* __restrict__ I, int W, int H, SmoothTaps taps
 #define PE_TW 32
 #define PE_TH 8
 
+// NT = poly_n at compile time (5 for the reference: loops unrolled, coefficients in registers), 0 = run time
+template <int NT>
 __global__ void __launch_bounds__(PE_TW * PE_TH)
 k_polyexp(const float* __restrict__ I, float* __restrict__ R, int Wk, int Hk, PolyCoef pc) {
     __shared__ float s_row[3][PE_TH][PE_TW + 2 * FLOW_MAX_POLY_N];
     const int img = blockIdx.z;
-    const int n = pc.n;
+    const int n = NT ? NT : pc.n;
     const int x0 = blockIdx.x * PE_TW, y0 = blockIdx.y * PE_TH;
     const float* src = I + (size_t)img * Wk * Hk;
     const int span = PE_TW + 2 * n;
@@ -364,6 +366,7 @@ k_polyexp(const float* __restrict__ I, float* __restrict__ R, int Wk, int Hk, Po
         const int xs = min(max(x0 + cx - n, 0), Wk - 1);
         const float c = src[(size_t)y * Wk + xs];
         float t0 = xfmul(c, pc.g[0]), t1 = 0.f, t2 = 0.f;
+#pragma unroll
         for (int k = 1; k <= n; ++k) {
             const float a = src[(size_t)max(y - k, 0) * Wk + xs];
             const float b = src[(size_t)min(y + k, Hk - 1) * Wk + xs];
@@ -385,6 +388,7 @@ k_polyexp(const float* __restrict__ I, float* __restrict__ R, int Wk, int Hk, Po
     const float* r2 = &s_row[2][ty][tx + n];
     double b1 = (double)xfmul(r0[0], pc.g[0]), b2 = 0, b3 = (double)xfmul(r1[0], pc.g[0]), b4 = 0;
     double b5 = (double)xfmul(r2[0], pc.g[0]), b6 = 0;
+#pragma unroll
     for (int k = 1; k <= n; ++k) {
         const double tg = (double)xfadd(r0[k], r0[-k]);
         const float g0 = pc.g[k];
@@ -765,7 +769,10 @@ inline int farneback_run(FlowBuffers& fb, const u8* d_gray0, const u8* d_gray1, 
         else
             k_pyr_level<<<g_img, blk, 0, stream>>>(imgs, fb.I, fb.W, fb.H, L.w, L.h, L.taps);
         FLOW_MARK(st, "flow.pyramid");
-        k_polyexp<<<g_img, blk, 0, stream>>>(fb.I, fb.R, L.w, L.h, fb.poly);
+        if (fb.poly.n == 5)
+            k_polyexp<5><<<g_img, blk, 0, stream>>>(fb.I, fb.R, L.w, L.h, fb.poly);
+        else
+            k_polyexp<0><<<g_img, blk, 0, stream>>>(fb.I, fb.R, L.w, L.h, fb.poly);
         FLOW_MARK(st, "flow.polyexp");
         k_update_matrices<<<g_pair, blk, 0, stream>>>(fb.R, cur, fb.M, L.w, L.h, ps);
         FLOW_MARK(st, "flow.update_matrices");
