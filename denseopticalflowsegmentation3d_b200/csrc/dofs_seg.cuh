@@ -757,9 +757,9 @@ k_bor_contract(BorState S, int N, int level) {
                 newp[g] = nn;
                 g = nn;
             }
-            S.best[fo + c] = PICK_NONE;
             survives = g == c;
-            if (!survives) S.up[fo + c] = g;
+            if (survives) S.best[fo + c] = PICK_NONE;  // only live roots collect offers in the next level
+            else S.up[fo + c] = g;
         }
         list_append_block(next, &S.n_roots[level * S.F + frame], survives, c);
     }
