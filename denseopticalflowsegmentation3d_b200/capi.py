@@ -8,7 +8,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 
 
 def lib_path():
-    return os.path.join(_HERE, "libdofs3d.so")
+    """The in-tree library; DOFS3D_LIB names another build of the same sources (kernel tuning experiments)."""
+    return os.environ.get("DOFS3D_LIB") or os.path.join(_HERE, "libdofs3d.so")
 
 
 class DofsError(RuntimeError):
