@@ -135,9 +135,7 @@ struct dofs3d_ctx {
     TileAgg *tile_agg = nullptr, *tile_carry = nullptr;
     int tiles_cap = 0;
     int list_cap = 0;
-    int* rsize = nullptr;
-    ushort4* rbbox = nullptr;
-    float2* rflow = nullptr;
+    RootState* rstate = nullptr;
     u64* best_score = nullptr;
     u32* sel_time = nullptr;
     int* sel_box = nullptr;
@@ -375,7 +373,7 @@ int segment_dev(dofs3d_ctx* ctx, const float* d_flow, int already_blurred, int n
     // enqueued, finished frames skip
     BorState& B = ctx->bor;
     const dim3 gS = grid_stride(ctx, n);
-    LAUNCH(ctx, k_bor_init, gS, SEG_THREADS, 0, B, ctx->flow_blur, ctx->rsize, ctx->rbbox, ctx->rflow, ctx->best_score,
+    LAUNCH(ctx, k_bor_init, gS, SEG_THREADS, 0, B, ctx->flow_blur, ctx->rstate, ctx->best_score,
            ctx->sel_time, ctx->sel_box, W, H, N, ctx->seg.neighbors == 8 ? 1 : 0);
     CK(cudaMemsetAsync(ctx->counters, 0, sizeof(int) * CNT_KINDS * F, ctx->stream));
     CK(cudaMemsetAsync(B.n_roots, 0, sizeof(int) * EV_MAX_WAVES * F, ctx->stream));
@@ -473,9 +471,7 @@ int segment_dev(dofs3d_ctx* ctx, const float* d_flow, int already_blurred, int n
     R.ev_key = ev_key;
     R.ev_loser = ev_loser;
     R.wave_start = ctx->wave_start;
-    R.rsize = ctx->rsize;
-    R.rbbox = ctx->rbbox;
-    R.rflow = ctx->rflow;
+    R.rstate = ctx->rstate;
     R.cand = ctx->cand;
     R.n_cand = ctx->counters + CNT_CAND * F;
     R.longest_chain = ctx->counters + CNT_CHAIN * F;
@@ -489,6 +485,8 @@ int segment_dev(dofs3d_ctx* ctx, const float* d_flow, int already_blurred, int n
     R.long_count = ctx->long_count;
     R.list_cap = ctx->list_cap;
     CK(cudaMemsetAsync(ctx->long_count, 0, sizeof(int) * (EV_MAX_WAVES + 1), ctx->stream));
+    R.long_flag = B.mask;  // the edge masks are dead after the Boruvka levels
+    CK(cudaMemsetAsync(R.long_flag, 0, (size_t)n * N, ctx->stream));
     R.ev_op = ctx->ev_op;
     R.ev_inv = ctx->ev_inv;
     R.ev_size = ctx->ev_size;
@@ -500,10 +498,10 @@ int segment_dev(dofs3d_ctx* ctx, const float* d_flow, int already_blurred, int n
     R.tile_carry = ctx->tile_carry;
     R.tiles_cap = ctx->tiles_cap;
     for (int wave = 1; wave <= levels; ++wave) {
+        LAUNCH(ctx, k_replay_short, gS, SEG_THREADS, 0, R, wave);
         LAUNCH(ctx, k_replay_scan, gS, REPLAY_TILE, 0, R, wave);
         LAUNCH(ctx, k_replay_carry, dim3(n), 32, 0, R, wave);
         LAUNCH(ctx, k_replay_operands, gS, SEG_THREADS, 0, R, wave);
-        LAUNCH(ctx, k_replay_serial_short, gS, SEG_THREADS, 0, R, wave);
         LAUNCH(ctx, k_replay_serial_long, dim3(148 * 4), 32 * REPLAY_WARPS, 0, R, wave);
         LAUNCH(ctx, k_replay_gates, gS, SEG_THREADS, 0, R, wave);
     }
@@ -726,9 +724,7 @@ int dofs3d_create(dofs3d_ctx** out, int device, int width, int height, int max_p
     ctx->tiles_cap = (int)((N + REPLAY_TILE - 1) / REPLAY_TILE + 1);
     DA(ctx->tile_agg, F * ctx->tiles_cap);
     DA(ctx->tile_carry, F * ctx->tiles_cap);
-    DA(ctx->rsize, F * N);
-    DA(ctx->rbbox, F * N);
-    DA(ctx->rflow, F * N);
+    DA(ctx->rstate, F * N);
     DA(ctx->best_score, F * N);
     DA(ctx->sel_time, F * N);
     DA(ctx->sel_box, F * N);

@@ -452,6 +452,32 @@ k_prefix_repair_long(RepairArgs A) {
                             // occupancy (32 registers, a few spilled words) beats a spill-free 48-register build by 10 %
 #endif
 
+// Per-root state of Forest::merge (size, mean flow, bounding box) as one 32-byte record = one DRAM sector: the replay
+// gathers the state of absorbed roots at random, and three separate arrays cost three sectors per gather.
+struct __align__(32) RootState {
+    int size;
+    float fx, fy;
+    u32 pad0;
+    ushort4 bbox;  // xmin, ymin, xmax, ymax
+    u32 pad1, pad2;
+};
+DOFS_D RootState root_load(const RootState* p) {
+    const uint4 a = reinterpret_cast<const uint4*>(p)[0];
+    const uint2 b = reinterpret_cast<const uint2*>(p)[2];
+    RootState r;
+    r.size = (int)a.x;
+    r.fx = __uint_as_float(a.y);
+    r.fy = __uint_as_float(a.z);
+    r.pad0 = 0;
+    r.bbox = make_ushort4((u16)(b.x & 0xFFFFu), (u16)(b.x >> 16), (u16)(b.y & 0xFFFFu), (u16)(b.y >> 16));
+    r.pad1 = r.pad2 = 0;
+    return r;
+}
+DOFS_D void root_store(RootState* p, int size, float2 f, ushort4 bb) {
+    reinterpret_cast<uint4*>(p)[0] = make_uint4((u32)size, __float_as_uint(f.x), __float_as_uint(f.y), 0u);
+    reinterpret_cast<uint4*>(p)[1] = make_uint4((u32)bb.x | ((u32)bb.y << 16), (u32)bb.z | ((u32)bb.w << 16), 0u, 0u);
+}
+
 struct BorState {
     u32* comp;       // [F][N] current root of each pixel
     u64* best;       // [F][N] per root: its minimum outgoing edge in this level, as a pick (prefix << 32 | slot)
@@ -519,8 +545,8 @@ DOFS_D void list_append_block(u32* list, int* counter, bool want, u32 value) {
 }
 
 __global__ void __launch_bounds__(SEG_THREADS)
-k_bor_init(BorState S, const float2* __restrict__ flow, int* __restrict__ rsize, ushort4* __restrict__ rbbox,
-           float2* __restrict__ rflow, u64* __restrict__ best_score, u32* __restrict__ sel_time,
+k_bor_init(BorState S, const float2* __restrict__ flow, RootState* __restrict__ rstate, u64* __restrict__ best_score,
+           u32* __restrict__ sel_time,
            int* __restrict__ sel_box, int W, int H, int N, int neighbors8) {
     const int frame = blockIdx.y;
     GRID_STRIDE(p, N) {
@@ -533,9 +559,7 @@ k_bor_init(BorState S, const float2* __restrict__ flow, int* __restrict__ rsize,
         const int y = p / W, x = p - y * W;
         S.mask[g] = (u8)incident_mask(x, y, W, H, neighbors8);
         // Forest::Forest (graph.cpp:129-148): singleton sets
-        rsize[g] = 1;
-        rbbox[g] = make_ushort4((u16)x, (u16)y, (u16)x, (u16)y);
-        rflow[g] = flow[g];
+        root_store(&rstate[g], 1, flow[g], make_ushort4((u16)x, (u16)y, (u16)x, (u16)y));
         best_score[g] = 0ull;
         sel_time[g] = DOFS_INF32;
         sel_box[g] = -1;
@@ -1052,16 +1076,17 @@ k_wave_starts(const u64* __restrict__ ev_key, int* __restrict__ wave_start /* [F
 //
 // A chain = the events won by one root, in time order (contiguous in the sorted event array).  Chains
 // of one wave are independent (every absorbed root has a lower final rank, so its state is final).
-// Only the mean flow is a true recurrence; sizes and boxes are prefix sums / prefix min-max along the
-// chain.  So a wave is five steps:
+//   k_replay_short     every chain of at most REPLAY_SHORT events (almost all of them) is replayed whole by one thread:
+//                      state update and gates in a single pass over its events.  Longer chains are flagged and listed.
+// For the long chains only the mean flow is a true recurrence; sizes and boxes are prefix sums / prefix min-max along
+// the chain.  So they take five steps, each of which skips the events of short chains (and whole tiles without long ones):
 //   k_replay_scan      per event: gather the absorbed root's state; segmented scan (segments = chains)
 //                      of (size, box) inside tiles of 256 events; one aggregate per tile
 //   k_replay_carry     per frame: running (size, box) across the tiles of the wave
 //   k_replay_operands  per event: size before / after, box after, the operands of the recurrence
-//                      (loser_mean*loser_size, float(size_before), 1.0/size_after); chain heads are
-//                      classified short (<= REPLAY_SHORT events) or long (work list)
-//   k_replay_serial_*  the recurrence itself, nothing else: a thread per short chain, a warp per long
-//                      chain (operands stream in coalesced, prefetched, broadcast through shared memory)
+//                      (loser_mean*loser_size, float(size_before), 1.0/size_after)
+//   k_replay_serial_long  the recurrence itself, nothing else: a warp per chain (operands stream in coalesced,
+//                      prefetched, broadcast through shared memory)
 //   k_replay_gates     per event: gates, candidate queue; the last event of a chain stores the root's state
 // The only serial work left is ~10 instructions per event of the longest chain.
 // ---------------------------------------------------------------------------------------------
@@ -1110,9 +1135,7 @@ struct ReplayArgs {
     const u64* ev_key;     // [F][N] sorted
     const u32* ev_loser;   // [F][N] sorted payload
     const int* wave_start; // [F][EV_MAX_WAVES+1]
-    int* rsize;            // [F][N]
-    ushort4* rbbox;        // [F][N]
-    float2* rflow;         // [F][N]
+    RootState* rstate;     // [F][N] size, mean flow and box of every root
     // per event (index = position in the sorted event array)
     float4* ev_op;         // [F][N] (loser mean * loser size).xy, float(size before), float(size after)
     double* ev_inv;        // [F][N] 1.0 / size after
@@ -1127,6 +1150,7 @@ struct ReplayArgs {
     Candidate* cand;       // [F][cand_cap]
     int* n_cand;           // [F]
     int* longest_chain;    // [F]
+    u8* long_flag;         // [F][N] per root: its chain has more than REPLAY_SHORT events (set by k_replay_short; zeroed per call)
     uint2* long_list;      // [list_cap] (frame, index of the chain's first event)
     int* long_count;       // [EV_MAX_WAVES + 1]
     int list_cap;
@@ -1161,6 +1185,68 @@ DOFS_D void push_candidate(const ReplayArgs& A, int frame, u32 root, u32 time, i
 
 #define EV_FLAG_STARTED 0x80000000u  // in ev_size after k_replay_scan: the event's chain started inside its tile
 
+DOFS_D void replay_gate(const ReplayArgs& A, int frame, u32 r, u32 time, int s, float2 f, ushort4 bb) {
+    const int y = (int)r / A.W;
+    if (s >= A.min_size && !(y < A.H / 10)) {                                       // graph.cpp:280, 288
+        const double move = norm2d(f.x, f.y);
+        if (!(move < xddiv((double)(3 * (y + 1)), (double)A.H)))                     // graph.cpp:296
+            push_candidate(A, frame, r, time, s, f, bb);
+    }
+}
+
+// Chains of at most REPLAY_SHORT events — all but a few thousand of the ~2 M of a 1080p frame — are replayed whole by
+// the thread of their first event: Forest::merge's state update (graph.cpp:184-208) and the gates of every merge, one
+// pass over the events instead of five.  The head of a longer chain flags its root and queues the chain for the
+// scan / operands / serial / gates kernels below, which skip everything else.
+__global__ void __launch_bounds__(SEG_THREADS)
+k_replay_short(ReplayArgs A, int wave) {
+    const int frame = blockIdx.y;
+    const int w0 = A.wave_start[frame * (EV_MAX_WAVES + 1) + wave];
+    const int w1 = A.wave_start[frame * (EV_MAX_WAVES + 1) + wave + 1];
+    const size_t fo = (size_t)frame * A.N;
+    const u64* key = A.ev_key + fo;
+    for (int i = w0 + blockIdx.x * blockDim.x + threadIdx.x; i < w1; i += gridDim.x * blockDim.x) {
+        u64 k = key[i];
+        const u64 chain = ev_chain(k, A.eb);
+        if (i > w0 && ev_chain(key[i - 1], A.eb) == chain) continue;  // not a head
+        const u32 r = ev_winner(k, A.eb);
+        if (i + REPLAY_SHORT < w1 && ev_chain(key[i + REPLAY_SHORT], A.eb) == chain) {
+            A.long_flag[fo + r] = 1;
+            const int slot = atomicAdd(&A.long_count[wave], 1);
+            if (slot < A.list_cap) A.long_list[slot] = make_uint2((u32)frame, (u32)i);
+            continue;
+        }
+        const RootState r0 = root_load(&A.rstate[fo + r]);
+        int s = r0.size;
+        float2 f = make_float2(r0.fx, r0.fy);
+        ushort4 bb = r0.bbox;
+        int j = i;
+        for (;;) {
+            const RootState ra = root_load(&A.rstate[fo + A.ev_loser[fo + j]]);
+            const int sa = ra.size;
+            const float2 fa = make_float2(ra.fx, ra.fy);
+            const ushort4 ba = ra.bbox;
+            const float fsa = (float)sa;
+            const int s_after = s + sa;
+            const double inv = xddiv(1.0, (double)s_after);
+            f.x = merge_mean(xfmul(fa.x, fsa), f.x, (float)s, inv);
+            f.y = merge_mean(xfmul(fa.y, fsa), f.y, (float)s, inv);
+            s = s_after;
+            bb.x = min(bb.x, ba.x);
+            bb.y = min(bb.y, ba.y);
+            bb.z = max(bb.z, ba.z);
+            bb.w = max(bb.w, ba.w);
+            replay_gate(A, frame, r, ev_time(k, A.eb), s, f, bb);
+            ++j;
+            if (j >= w1) break;
+            k = key[j];
+            if (ev_chain(k, A.eb) != chain) break;
+        }
+        root_store(&A.rstate[fo + r], s, f, bb);
+        if (j - i > A.longest_chain[frame]) atomicMax(&A.longest_chain[frame], j - i);
+    }
+}
+
 __global__ void __launch_bounds__(REPLAY_TILE)
 k_replay_scan(ReplayArgs A, int wave) {
     __shared__ ScanTuple s_tot[REPLAY_TILE / 32];
@@ -1171,18 +1257,34 @@ k_replay_scan(ReplayArgs A, int wave) {
     const size_t fo = (size_t)frame * A.N;
     const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
     const int n_tiles = (w1 - w0 + REPLAY_TILE - 1) / REPLAY_TILE;
+    if (A.long_count[wave] == 0) return;  // nothing but short chains in this wave (any frame)
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int j = w0 + tile * REPLAY_TILE + threadIdx.x;
         const bool valid = j < w1;
         ScanTuple t = scan_identity();
         bool head = false;
+        u64 key = 0;
+        bool is_long = false;
         if (valid) {
-            const u64 key = A.ev_key[fo + j];
-            const u32 a = A.ev_loser[fo + j];
-            head = j == w0 || ev_chain(A.ev_key[fo + j - 1], A.eb) != ev_chain(key, A.eb);
-            const int sa = A.rsize[fo + a];
-            const float2 fa = A.rflow[fo + a];
-            const ushort4 ba = A.rbbox[fo + a];
+            key = A.ev_key[fo + j];
+            is_long = A.long_flag[fo + ev_winner(key, A.eb)] != 0;
+        }
+        if (!__syncthreads_or(is_long)) {  // a tile without events of long chains: nothing crosses it
+            if (threadIdx.x == 0) {
+                TileAgg g;
+                g.s = 0;
+                g.bb = make_ushort4(65535, 65535, 0, 0);
+                g.has_head = 1;
+                A.tile_agg[(size_t)frame * A.tiles_cap + tile] = g;
+            }
+            continue;
+        }
+        if (valid) head = j == w0 || ev_chain(A.ev_key[fo + j - 1], A.eb) != ev_chain(key, A.eb);
+        if (is_long) {
+            const RootState ra = root_load(&A.rstate[fo + A.ev_loser[fo + j]]);
+            const int sa = ra.size;
+            const float2 fa = make_float2(ra.fx, ra.fy);
+            const ushort4 ba = ra.bbox;
             const float fsa = (float)sa;
             A.ev_prod[fo + j] = make_float2(xfmul(fa.x, fsa), xfmul(fa.y, fsa));
             A.ev_sa[fo + j] = sa;
@@ -1221,7 +1323,7 @@ k_replay_scan(ReplayArgs A, int wave) {
         }
         if (!started) t = scan_combine(c, t);
         started |= c_started;
-        if (valid) {
+        if (is_long) {
             A.ev_size[fo + j] = (int)((u32)t.s | (started ? EV_FLAG_STARTED : 0u));
             A.ev_bbox[fo + j] = make_ushort4((u16)t.x0, (u16)t.y0, (u16)t.x1, (u16)t.y1);
         }
@@ -1240,6 +1342,7 @@ k_replay_scan(ReplayArgs A, int wave) {
 __global__ void __launch_bounds__(32)
 k_replay_carry(ReplayArgs A, int wave) {
     const int frame = blockIdx.x, lane = threadIdx.x;
+    if (A.long_count[wave] == 0) return;
     const int w0 = A.wave_start[frame * (EV_MAX_WAVES + 1) + wave];
     const int w1 = A.wave_start[frame * (EV_MAX_WAVES + 1) + wave + 1];
     const int n_tiles = (w1 - w0 + REPLAY_TILE - 1) / REPLAY_TILE;
@@ -1291,10 +1394,11 @@ k_replay_operands(ReplayArgs A, int wave) {
     const int w0 = A.wave_start[frame * (EV_MAX_WAVES + 1) + wave];
     const int w1 = A.wave_start[frame * (EV_MAX_WAVES + 1) + wave + 1];
     const size_t fo = (size_t)frame * A.N;
+    if (A.long_count[wave] == 0) return;
     for (int j = w0 + blockIdx.x * blockDim.x + threadIdx.x; j < w1; j += gridDim.x * blockDim.x) {
         const u64 key = A.ev_key[fo + j];
-        const u64 chain = ev_chain(key, A.eb);
         const u32 r = ev_winner(key, A.eb);
+        if (A.long_flag[fo + r] == 0) continue;  // replayed by k_replay_short
         const u32 raw = (u32)A.ev_size[fo + j];
         int s = (int)(raw & ~EV_FLAG_STARTED);
         ushort4 bb = A.ev_bbox[fo + j];
@@ -1307,8 +1411,9 @@ k_replay_operands(ReplayArgs A, int wave) {
             bb.w = max(bb.w, c.bb.w);
         }
         // the root's own state before this wave
-        const int s_after = s + A.rsize[fo + r];
-        const ushort4 rb = A.rbbox[fo + r];
+        const RootState rr = root_load(&A.rstate[fo + r]);
+        const int s_after = s + rr.size;
+        const ushort4 rb = rr.bbox;
         bb.x = min(bb.x, rb.x);
         bb.y = min(bb.y, rb.y);
         bb.z = max(bb.z, rb.z);
@@ -1319,38 +1424,6 @@ k_replay_operands(ReplayArgs A, int wave) {
         A.ev_inv[fo + j] = xddiv(1.0, (double)s_after);
         A.ev_size[fo + j] = s_after;
         A.ev_bbox[fo + j] = bb;
-        // long chains go to the warp kernel
-        const bool head = j == w0 || ev_chain(A.ev_key[fo + j - 1], A.eb) != chain;
-        if (head && j + REPLAY_SHORT < w1 && ev_chain(A.ev_key[fo + j + REPLAY_SHORT], A.eb) == chain) {
-            const int slot = atomicAdd(&A.long_count[wave], 1);
-            if (slot < A.list_cap) A.long_list[slot] = make_uint2((u32)frame, (u32)j);
-        }
-    }
-}
-
-// the recurrence of every chain of at most REPLAY_SHORT events: one thread per chain head
-__global__ void __launch_bounds__(SEG_THREADS)
-k_replay_serial_short(ReplayArgs A, int wave) {
-    const int frame = blockIdx.y;
-    const int w0 = A.wave_start[frame * (EV_MAX_WAVES + 1) + wave];
-    const int w1 = A.wave_start[frame * (EV_MAX_WAVES + 1) + wave + 1];
-    const size_t fo = (size_t)frame * A.N;
-    const u64* key = A.ev_key + fo;
-    for (int i = w0 + blockIdx.x * blockDim.x + threadIdx.x; i < w1; i += gridDim.x * blockDim.x) {
-        const u64 chain = ev_chain(key[i], A.eb);
-        if (i > w0 && ev_chain(key[i - 1], A.eb) == chain) continue;                            // not a head
-        if (i + REPLAY_SHORT < w1 && ev_chain(key[i + REPLAY_SHORT], A.eb) == chain) continue;  // long
-        float2 f = A.rflow[fo + ev_winner(key[i], A.eb)];
-        int j = i;
-        for (;;) {
-            const float4 o = A.ev_op[fo + j];
-            const double inv = A.ev_inv[fo + j];
-            f.x = merge_mean(o.x, f.x, o.z, inv);
-            f.y = merge_mean(o.y, f.y, o.z, inv);
-            A.ev_flow[fo + j] = f;
-            ++j;
-            if (j >= w1 || ev_chain(key[j], A.eb) != chain) break;
-        }
     }
 }
 
@@ -1391,7 +1464,11 @@ k_replay_serial_long(ReplayArgs A, int wave) {
         const int w1 = A.wave_start[frame * (EV_MAX_WAVES + 1) + wave + 1];
         const u64 k0 = A.ev_key[fo + i0];
         const u64 chain = ev_chain(k0, A.eb);
-        float2 f = A.rflow[fo + ev_winner(k0, A.eb)];
+        float2 f;
+        {
+            const RootState rr = root_load(&A.rstate[fo + ev_winner(k0, A.eb)]);
+            f = make_float2(rr.fx, rr.fy);
+        }
         int j0 = i0;
         // rounds t+1 and t+2 are in flight while round t is replayed; a load never waits for the chain test of its
         // event (operands of any event position are readable), the test happens when the round is consumed
@@ -1513,22 +1590,17 @@ k_replay_gates(ReplayArgs A, int wave) {
     const int w0 = A.wave_start[frame * (EV_MAX_WAVES + 1) + wave];
     const int w1 = A.wave_start[frame * (EV_MAX_WAVES + 1) + wave + 1];
     const size_t fo = (size_t)frame * A.N;
+    if (A.long_count[wave] == 0) return;
     for (int j = w0 + blockIdx.x * blockDim.x + threadIdx.x; j < w1; j += gridDim.x * blockDim.x) {
         const u64 key = A.ev_key[fo + j];
         const u32 r = ev_winner(key, A.eb);
+        if (A.long_flag[fo + r] == 0) continue;  // replayed by k_replay_short
         const int s = A.ev_size[fo + j];
         const float2 f = A.ev_flow[fo + j];
         const ushort4 bb = A.ev_bbox[fo + j];
-        const int y = (int)r / A.W;
-        if (s >= A.min_size && !(y < A.H / 10)) {                                   // graph.cpp:280, 288
-            const double move = norm2d(f.x, f.y);
-            if (!(move < xddiv((double)(3 * (y + 1)), (double)A.H)))                 // graph.cpp:296
-                push_candidate(A, frame, r, ev_time(key, A.eb), s, f, bb);
-        }
+        replay_gate(A, frame, r, ev_time(key, A.eb), s, f, bb);
         if (j + 1 >= w1 || ev_chain(A.ev_key[fo + j + 1], A.eb) != ev_chain(key, A.eb)) {
-            A.rsize[fo + r] = s;
-            A.rflow[fo + r] = f;
-            A.rbbox[fo + r] = bb;
+            root_store(&A.rstate[fo + r], s, f, bb);
         }
     }
 }
