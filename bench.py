@@ -36,8 +36,8 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=128, help="frame pairs per step per GPU")
-    ap.add_argument("--contexts", type=int, default=4, help="contexts (streams) per GPU; each takes batch/contexts pairs of a step")
+    ap.add_argument("--batch", type=int, default=192, help="frame pairs per step per GPU")
+    ap.add_argument("--contexts", type=int, default=6, help="contexts (streams) per GPU; each takes batch/contexts pairs of a step")
     ap.add_argument("--width", type=int, default=1920)
     ap.add_argument("--height", type=int, default=1080)
     ap.add_argument("--no-cpu-baseline", action="store_true")

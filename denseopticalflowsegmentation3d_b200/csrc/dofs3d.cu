@@ -303,7 +303,7 @@ int build_sorted_edges(dofs3d_ctx* ctx, int n) {
     const int N = ctx->N;
     const int S = (int)ctx->S;
     u32* preA = reinterpret_cast<u32*>(ctx->keysB);  // the prefix buffers live in keysB, which only the fallback needs
-    u32* preB = preA + (size_t)ctx->F * ctx->S;
+    u32* preB = preA + (size_t)n * ctx->S;  // n == 1 (the parity hook): both fit the S u64 of keysB
     LAUNCH(ctx, k_edge_keys, grid1(N, SEG_THREADS, n), SEG_THREADS, 0, ctx->flow_blur, ctx->keysA, preA, ctx->S, ctx->W,
            ctx->H, ctx->seg.neighbors == 8 ? 1 : 0);
     mark(ctx, "edge_keys");
@@ -691,12 +691,15 @@ int dofs3d_create(dofs3d_ctx** out, int device, int width, int height, int max_p
     DA(ctx->flow_in, F * N);
     DA(ctx->flow_tmp, F * N);
     DA(ctx->flow_blur, F * N);
-    DA(ctx->keysA, F * S);
-    DA(ctx->keysB, F * S);
-    DA(ctx->valsA, F * S);
-    DA(ctx->valsB, F * S);
+    // sort buffers: the segmentation needs per frame 3N u64 in keysA (two u32 time-key buffers + two u64 fallback buffers),
+    // 2N u64 in keysB (the 4N u32 prefixes, later the event keys) and N u32 in each payload buffer; the parity hook
+    // dofs3d_edges_sorted sorts all 4N slots of ONE frame (4N u64 / 4N u32 per buffer)
+    DA(ctx->keysA, std::max(S, 3 * F * N));
+    DA(ctx->keysB, std::max(S, 2 * F * N));
+    DA(ctx->valsA, std::max(S, F * N));
+    DA(ctx->valsB, std::max(S, F * N));
     ctx->num_tiles = (int)((S + RS_TILE - 1) / RS_TILE);
-    DA(ctx->tile_hist, F * RS_BINS * ctx->num_tiles);
+    DA(ctx->tile_hist, RS_BINS * std::max<size_t>(ctx->num_tiles, F * ((N + RS_TILE - 1) / RS_TILE)));  // F frames of N, or 1 of 4N
     DA(ctx->digit_tot, F * RS_BINS);
     DA(ctx->sweep_hist, 2 * F * RS_MAX_PASSES * RS_BINS);
     DA(ctx->sweep_ticket, RS_MAX_PASSES + 1);
