@@ -57,7 +57,7 @@ struct SegParams {
 // One merge that passed the size / row / move gates of Forest::new_merge (graph.cpp:280-300).
 struct __align__(16) Candidate {
     u32 root;
-    u32 time;      // position of the merging edge in the sorted edge list
+    u32 time;      // index of the merge in the reference's sequence of accepted edges
     int size;
     float fx, fy;  // mean flow of the merged set
     u16 bbox[4];   // xmin, ymin, xmax, ymax

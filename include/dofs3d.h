@@ -62,7 +62,7 @@ typedef struct {
     int32_t parent_box;  /* index (in this frame's box list) of the smallest box whose pixel set strictly
                             contains this one, or -1; segments nest because they are merge-tree nodes */
     int32_t bbox[4];     /* xmin, ymin, xmax, ymax of the pixel set (Forest::get_bounding_box, graph.cpp:446) */
-    uint32_t time;       /* position of the merging edge in the sorted edge list (snapshot instant) */
+    uint32_t time;       /* index of the merge in the reference's sequence of accepted edges (snapshot instant) */
     float mean_flow[2];  /* Node::flow_value of the root at the snapshot (graph.cpp:184-190) */
     float pad_;
     double score;        /* (w_error + h_error) / 2            graph.cpp:257-260 */
@@ -86,7 +86,7 @@ typedef struct {
     int32_t n_boxes;       /* history entries (roots with a kept snapshot) */
     int32_t longest_chain; /* longest run of merges won by one root (serial depth of the replay) */
     int32_t final_root;    /* root id of the single set the forest ends as (Forest::find of any pixel) */
-    int32_t sort_fallback; /* 1 if the batch needed the full 64-bit radix sort of the edges */
+    int32_t sort_fallback; /* 1 if the merge times of the batch needed the exact 64-bit fallback sort */
     int32_t replay_exact_chunks; /* batch-wide: 32-event chunks of the mean-flow replay whose fast path failed its
                                     exact check and were replayed in double arithmetic */
 } dofs3d_stats;
@@ -94,8 +94,8 @@ typedef struct {
 /* Fills *p with the reference's constants (homographies from get_mat/get_mat_upper, etc.). */
 void dofs3d_default_params(dofs3d_params* p);
 
-/* Context for frames of width x height on GPU `device`; at most max_pairs frame pairs per call.
- * params == NULL selects dofs3d_default_params. */
+/* Context for frames of width x height (2..65535 each, at most 2^26 pixels) on GPU `device`; at most max_pairs frame
+ * pairs per call.  params == NULL selects dofs3d_default_params. */
 int dofs3d_create(dofs3d_ctx** out, int device, int width, int height, int max_pairs, const dofs3d_params* params);
 void dofs3d_destroy(dofs3d_ctx* ctx);
 /* Waits for the context's stream.  After an asynchronous (_dev) segment/process call it also reports that call's
