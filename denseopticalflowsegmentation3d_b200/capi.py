@@ -57,7 +57,7 @@ STATS_DTYPE = np.dtype([(k, "<i4") for k in ("n_edges", "n_merges", "n_levels", 
 
 # every symbol include/dofs3d.h declares
 SYMBOLS = [
-    "dofs3d_default_params", "dofs3d_create", "dofs3d_destroy", "dofs3d_sync", "dofs3d_last_error", "dofs3d_stream",
+    "dofs3d_default_params", "dofs3d_params_for_size", "dofs3d_create", "dofs3d_destroy", "dofs3d_sync", "dofs3d_last_error", "dofs3d_stream",
     "dofs3d_launch_count", "dofs3d_device_bytes", "dofs3d_gray", "dofs3d_gray_dev", "dofs3d_flow", "dofs3d_blur",
     "dofs3d_segment", "dofs3d_paint", "dofs3d_lift", "dofs3d_edges_sorted", "dofs3d_process", "dofs3d_process_dev",
     "dofs3d_segment_dev", "dofs3d_flow_dev", "dofs3d_synth_frames_dev", "dofs3d_set_timing", "dofs3d_get_timing",
@@ -79,6 +79,8 @@ def load_library():
     vp, ip, fp, u8p = C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p
     L.dofs3d_default_params.argtypes = [C.POINTER(Params)]
     L.dofs3d_default_params.restype = None
+    L.dofs3d_params_for_size.argtypes = [C.POINTER(Params), C.c_int, C.c_int]
+    L.dofs3d_params_for_size.restype = None
     L.dofs3d_create.argtypes = [C.POINTER(vp), C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(Params)]
     L.dofs3d_destroy.argtypes = [vp]
     L.dofs3d_destroy.restype = None
@@ -114,6 +116,13 @@ def load_library():
 def default_params():
     p = Params()
     load_library().dofs3d_default_params(C.byref(p))
+    return p
+
+
+def params_for_size(width, height):
+    """default_params with the reference's 640x360 calibration quads rescaled to width x height."""
+    p = Params()
+    load_library().dofs3d_params_for_size(C.byref(p), width, height)
     return p
 
 

@@ -611,20 +611,32 @@ int check_batch(dofs3d_ctx* ctx, int n) {
 // =================================================================================================
 extern "C" {
 
-void dofs3d_default_params(dofs3d_params* p) {
-    if (!p) return;
-    memset(p, 0, sizeof *p);
+// the reference's calibration quads are pixel coordinates of a 640x360 frame; (sx, sy) rescales them to another frame size
+static void calibration(dofs3d_params* p, double sx, double sy) {
     // get_mat (lifting_3d.cpp:482-514): image quad <-> bird's-eye-view rectangle
-    const double img[4][2] = {{215, 265}, {90, 121}, {294, 120}, {625, 265}};
+    const double img[4][2] = {{215 * sx, 265 * sy}, {90 * sx, 121 * sy}, {294 * sx, 120 * sy}, {625 * sx, 265 * sy}};
     const double bev[4][2] = {{100, 13000}, {100, 6000}, {800, 6000}, {800, 13000}};
     perspective_transform(img, bev, p->persp);
     perspective_transform(bev, img, p->inv);
     // get_mat_upper (lifting_3d.cpp:441-480): the same BEV rectangle to the roof-height image quads
     const double roof_y[3][2] = {{176, 85}, {185, 80}, {140, 55}};
     for (int c = 0; c < 3; ++c) {
-        const double roof[4][2] = {{215, roof_y[c][0]}, {90, roof_y[c][1]}, {294, roof_y[c][1]}, {625, roof_y[c][0]}};
+        const double roof[4][2] = {{215 * sx, roof_y[c][0] * sy}, {90 * sx, roof_y[c][1] * sy}, {294 * sx, roof_y[c][1] * sy},
+                                   {625 * sx, roof_y[c][0] * sy}};
         perspective_transform(bev, roof, p->inv_upper[c]);
     }
+}
+
+void dofs3d_params_for_size(dofs3d_params* p, int width, int height) {
+    if (!p) return;
+    dofs3d_default_params(p);
+    if (width > 0 && height > 0) calibration(p, width / 640.0, height / 360.0);
+}
+
+void dofs3d_default_params(dofs3d_params* p) {
+    if (!p) return;
+    memset(p, 0, sizeof *p);
+    calibration(p, 1.0, 1.0);
     p->pyr_scale = 0.5;
     p->levels = 3;
     p->winsize = 15;

@@ -21,6 +21,9 @@ std::vector<Solution> get_bottom_variants_batch(const std::vector<cv::Point2f>& 
                                                 const std::vector<int>& cls);
 std::pair<cv::Matx33f, cv::Matx33f> get_mat();  // lifting_3d.cpp:482-514
 cv::Matx33f get_mat_upper(int cls);             // lifting_3d.cpp:441-480
+// The same calibration for a width x height frame of the same view (the reference's quads are 640x360 pixel coordinates).
+std::pair<cv::Matx33f, cv::Matx33f> get_mat(int width, int height);
+cv::Matx33f get_mat_upper(int cls, int width, int height);
 // Intersection of lines a1a2 and b1b2 in float; (NaN, NaN) for parallel lines (lifting_3d.cpp:63-88).  Setup-sized
 // scalar helper, evaluated on the host.
 cv::Point2f get_intersect(cv::Point2f a1, cv::Point2f a2, cv::Point2f b1, cv::Point2f b2);

@@ -304,6 +304,24 @@ std::pair<cv::Matx33f, cv::Matx33f> get_mat() {
     return {a, b};
 }
 
+std::pair<cv::Matx33f, cv::Matx33f> get_mat(int width, int height) {
+    dofs3d_params p;
+    dofs3d_params_for_size(&p, width, height);
+    cv::Matx33f a, b;
+    std::memcpy(a.val, p.persp, sizeof p.persp);
+    std::memcpy(b.val, p.inv, sizeof p.inv);
+    return {a, b};
+}
+
+cv::Matx33f get_mat_upper(int cls, int width, int height) {
+    if (cls < 0 || cls > 2) throw std::invalid_argument("get_mat_upper: cls must be 0, 1 or 2");
+    dofs3d_params p;
+    dofs3d_params_for_size(&p, width, height);
+    cv::Matx33f a;
+    std::memcpy(a.val, p.inv_upper[cls], sizeof p.inv_upper[cls]);
+    return a;
+}
+
 cv::Matx33f get_mat_upper(int cls) {
     if (cls < 0 || cls > 2) throw std::invalid_argument("get_mat_upper: cls must be 0, 1 or 2");
     dofs3d_params p;

@@ -93,6 +93,11 @@ typedef struct {
 
 /* Fills *p with the reference's constants (homographies from get_mat/get_mat_upper, etc.). */
 void dofs3d_default_params(dofs3d_params* p);
+/* The same constants with the calibration quads of get_mat / get_mat_upper (pixel coordinates of the reference's
+ * 640x360 camera, lifting_3d.cpp:441-514) rescaled to a width x height frame of the same view: the homographies then map
+ * that frame to the same bird's-eye-view rectangle.  The pixel-valued gates (min_size, the motion threshold) are left
+ * as the reference has them.  ("calibration generalised to arbitrary resolution".) */
+void dofs3d_params_for_size(dofs3d_params* p, int width, int height);
 
 /* Context for frames of width x height (2..65535 each, at most 2^26 pixels) on GPU `device`; at most max_pairs frame
  * pairs per call.  params == NULL selects dofs3d_default_params. */

@@ -48,6 +48,28 @@ def test_default_params_are_the_reference_constants(port):
     assert list(p.cls_min_convexity) == [3.0 / 4.0, 1.0 / 2.0, 20.0 / 29.0]  # graph.cpp:328-339
 
 
+def test_params_for_size_rescales_the_calibration():
+    """dofs3d_params_for_size: at 640x360 it is the reference's calibration bit for bit; at another size the image-side
+    coordinates scale and the bird's-eye-view side stays."""
+    from denseopticalflowsegmentation3d_b200 import capi
+    ref = dofs.default_params()
+    same = capi.params_for_size(640, 360)
+    assert bytes(same) == bytes(ref)
+    big = capi.params_for_size(1920, 1080)
+
+    def apply(m, x, y):
+        v = np.array(m, np.float64).reshape(3, 3) @ np.array([x, y, 1.0])
+        return v[:2] / v[2]
+
+    for x, y in [(215, 265), (90, 121), (400, 200), (625, 265)]:
+        assert np.allclose(apply(big.persp, 3 * x, 3 * y), apply(ref.persp, x, y), rtol=0, atol=0.5)  # same BEV point
+    for bx, by in [(100, 13000), (800, 6000), (450, 9000)]:
+        assert np.allclose(apply(big.inv, bx, by), 3 * apply(ref.inv, bx, by), rtol=0, atol=2e-2)
+        for c in range(3):
+            assert np.allclose(apply(big.inv_upper[c], bx, by), 3 * apply(ref.inv_upper[c], bx, by), rtol=0, atol=2e-2)
+    assert (big.min_size, big.winsize, big.neighbors) == (ref.min_size, ref.winsize, ref.neighbors)
+
+
 def test_no_cpu_fallback_without_gpu():
     import torch
     if torch.cuda.is_available():
