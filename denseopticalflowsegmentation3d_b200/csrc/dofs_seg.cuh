@@ -666,7 +666,10 @@ k_bor_pixel(BorState S, const u32* __restrict__ prefix, size_t prefix_stride, co
 // (up to) eight incident edges — its four back-edges and the back-edges of the four neighbours that point at it.
 // k_bor_level0_pick stores that pick in `best`; k_bor_level0_root applies the same mutual-pick rule as k_bor_root (the
 // edge's `end` side survives a tie; the pixel owning the slot is `start`).
-__global__ void __launch_bounds__(SEG_THREADS)
+#ifndef BOR_LEVEL0_BLOCKS
+#define BOR_LEVEL0_BLOCKS 6
+#endif
+__global__ void __launch_bounds__(SEG_THREADS, BOR_LEVEL0_BLOCKS)
 k_bor_level0_pick(BorState S, const u32* __restrict__ prefix, size_t prefix_stride, const float2* __restrict__ flow, int W,
                   int H, int N) {
     const int frame = blockIdx.y;
@@ -1198,7 +1201,10 @@ DOFS_D void replay_gate(const ReplayArgs& A, int frame, u32 r, u32 time, int s, 
 // the thread of their first event: Forest::merge's state update (graph.cpp:184-208) and the gates of every merge, one
 // pass over the events instead of five.  The head of a longer chain flags its root and queues the chain for the
 // scan / operands / serial / gates kernels below, which skip everything else.
-__global__ void __launch_bounds__(SEG_THREADS)
+#ifndef REPLAY_SHORT_BLOCKS
+#define REPLAY_SHORT_BLOCKS 8  // bound by the latency of the random state gathers: full occupancy (32 registers)
+#endif
+__global__ void __launch_bounds__(SEG_THREADS, REPLAY_SHORT_BLOCKS)
 k_replay_short(ReplayArgs A, int wave) {
     const int frame = blockIdx.y;
     const int w0 = A.wave_start[frame * (EV_MAX_WAVES + 1) + wave];
