@@ -596,7 +596,7 @@ __device__ __noinline__ void bor_pixel_settle(u64* best, const u32* __restrict__
         for (int e = 0; e < 8; ++e) {
             if (!((out >> e) & 1u)) continue;
             const u32 slot = incident_slot(p, e, W);
-            pick_offer(b, make_pick(pre[slot], slot), *reinterpret_cast<volatile u64*>(b), f, W);
+            if (pre[slot] != EDGE_PREFIX_INVALID) pick_offer(b, make_pick(pre[slot], slot), *reinterpret_cast<volatile u64*>(b), f, W);
         }
     }
 }
@@ -641,7 +641,7 @@ k_bor_pixel(BorState S, const u32* __restrict__ prefix, size_t prefix_stride, co
         for (int k = 0; k < 8; ++k) {
             constexpr int order[8] = {6, 0, 1, 2, 3, 4, 7, 5};
             const int e = order[k];
-            if ((out >> e) & 1u) {
+            if (((out >> e) & 1u) && pr[e] != EDGE_PREFIX_INVALID) {  // (a NaN / infinite weight is no edge)
                 same += pr[e] == pmin ? 1u : 0u;
                 if (pr[e] < pmin) {
                     pmin = pr[e];
@@ -650,6 +650,7 @@ k_bor_pixel(BorState S, const u32* __restrict__ prefix, size_t prefix_stride, co
                 }
             }
         }
+        if (pmin == EDGE_PREFIX_INVALID) continue;
         const u64 mine = make_pick(pmin, smin);
         u32 flags = (same != 0 && pmin != 0u) ? PIX_TIE_LOCAL : 0u;
         u64 seen = seen0;

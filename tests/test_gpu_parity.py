@@ -366,6 +366,20 @@ def test_process_end_to_end(dofs, port, golden_synth):
         compare_boxes(staged["boxes"][i], box_pixel_sets(staged["labels"][i], staged["boxes"][i]), res["entries"], W)
 
 
+def test_non_finite_flow_is_reported_not_fatal(dofs):
+    """A NaN / infinite flow vector gives its edges no weight (the reference's comparator is undefined there): the frame
+    cannot be joined into one set, which the call reports as an error instead of hanging or reading out of bounds."""
+    W, H = 64, 48
+    f = random_flow(5, W, H)
+    f[10:14, 20:24] = np.nan
+    f[30, 40] = np.inf
+    with dofs.Context(W, H) as c:
+        with pytest.raises(dofs.DofsError):
+            c.segment(f, already_blurred=True)
+        ok = c.segment(random_flow(6, W, H), already_blurred=True)  # the context stays usable
+        assert ok["stats"][0]["final_root"] >= 0
+
+
 def test_argument_errors(dofs):
     with dofs.Context(64, 48, max_pairs=2) as c:
         f = np.zeros((3, 48, 64, 2), np.float32)
