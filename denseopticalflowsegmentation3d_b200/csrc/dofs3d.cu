@@ -373,7 +373,7 @@ int segment_dev(dofs3d_ctx* ctx, const float* d_flow, int already_blurred, int n
     // enqueued, finished frames skip
     BorState& B = ctx->bor;
     const dim3 gS = grid_stride(ctx, n);
-    LAUNCH(ctx, k_bor_init, gS, SEG_THREADS, 0, B, ctx->flow_blur, ctx->rstate, ctx->best_score,
+    LAUNCH(ctx, k_bor_init, gS, SEG_THREADS, 0, B, ctx->best_score,
            ctx->sel_time, ctx->sel_box, W, H, N, ctx->seg.neighbors == 8 ? 1 : 0);
     CK(cudaMemsetAsync(ctx->counters, 0, sizeof(int) * CNT_KINDS * F, ctx->stream));
     CK(cudaMemsetAsync(B.n_roots, 0, sizeof(int) * EV_MAX_WAVES * F, ctx->stream));
@@ -472,6 +472,8 @@ int segment_dev(dofs3d_ctx* ctx, const float* d_flow, int already_blurred, int n
     R.ev_loser = ev_loser;
     R.wave_start = ctx->wave_start;
     R.rstate = ctx->rstate;
+    R.flow = ctx->flow_blur;
+    R.lvl = B.lvl;
     R.cand = ctx->cand;
     R.n_cand = ctx->counters + CNT_CAND * F;
     R.longest_chain = ctx->counters + CNT_CHAIN * F;

@@ -545,8 +545,7 @@ DOFS_D void list_append_block(u32* list, int* counter, bool want, u32 value) {
 }
 
 __global__ void __launch_bounds__(SEG_THREADS)
-k_bor_init(BorState S, const float2* __restrict__ flow, RootState* __restrict__ rstate, u64* __restrict__ best_score,
-           u32* __restrict__ sel_time,
+k_bor_init(BorState S, u64* __restrict__ best_score, u32* __restrict__ sel_time,
            int* __restrict__ sel_box, int W, int H, int N, int neighbors8) {
     const int frame = blockIdx.y;
     GRID_STRIDE(p, N) {
@@ -558,8 +557,7 @@ k_bor_init(BorState S, const float2* __restrict__ flow, RootState* __restrict__ 
         S.lvl[g] = 0;
         const int y = p / W, x = p - y * W;
         S.mask[g] = (u8)incident_mask(x, y, W, H, neighbors8);
-        // Forest::Forest (graph.cpp:129-148): singleton sets
-        root_store(&rstate[g], 1, flow[g], make_ushort4((u16)x, (u16)y, (u16)x, (u16)y));
+        // (Forest::Forest's singleton sets, graph.cpp:129-148, are never materialised: see root_initial)
         best_score[g] = 0ull;
         sel_time[g] = DOFS_INF32;
         sel_box[g] = -1;
@@ -1139,7 +1137,9 @@ struct ReplayArgs {
     const u64* ev_key;     // [F][N] sorted
     const u32* ev_loser;   // [F][N] sorted payload
     const int* wave_start; // [F][EV_MAX_WAVES+1]
-    RootState* rstate;     // [F][N] size, mean flow and box of every root
+    RootState* rstate;     // [F][N] size, mean flow and box of every root that has won a merge (written when its chain ends)
+    const float2* flow;    // [F][N] blurred flow: the state of a root that never won is its pixel (Forest::Forest, graph.cpp:129-148)
+    const u8* lvl;         // [F][N] final rank of every root: 0 = never won a merge
     // per event (index = position in the sorted event array)
     float4* ev_op;         // [F][N] (loser mean * loser size).xy, float(size before), float(size after)
     double* ev_inv;        // [F][N] 1.0 / size after
@@ -1187,6 +1187,26 @@ DOFS_D void push_candidate(const ReplayArgs& A, int frame, u32 root, u32 time, i
     A.cand[(size_t)frame * A.cand_cap + slot] = c;
 }
 
+// State of root c before its own chain: the singleton set of pixel c.  A root wins merges only in the wave of its
+// final rank — all of them in one chain — so this is also its state at the head of that chain.
+DOFS_D RootState root_initial(const ReplayArgs& A, size_t fo, u32 c) {
+    RootState r;
+    const float2 f = A.flow[fo + c];
+    const int y = (int)c / A.W, x = (int)c - y * A.W;
+    r.size = 1;
+    r.fx = f.x;
+    r.fy = f.y;
+    r.pad0 = r.pad1 = r.pad2 = 0;
+    r.bbox = make_ushort4((u16)x, (u16)y, (u16)x, (u16)y);
+    return r;
+}
+// State of an absorbed root: final (stored when its chain ended, in an earlier wave) if it ever won, else its pixel.
+// In wave 1 every absorbed root has rank 0.
+DOFS_D RootState root_absorbed(const ReplayArgs& A, size_t fo, u32 a, int wave) {
+    if (wave == 1 || A.lvl[fo + a] == 0) return root_initial(A, fo, a);
+    return root_load(&A.rstate[fo + a]);
+}
+
 #define EV_FLAG_STARTED 0x80000000u  // in ev_size after k_replay_scan: the event's chain started inside its tile
 
 DOFS_D void replay_gate(const ReplayArgs& A, int frame, u32 r, u32 time, int s, float2 f, ushort4 bb) {
@@ -1223,13 +1243,13 @@ k_replay_short(ReplayArgs A, int wave) {
             if (slot < A.list_cap) A.long_list[slot] = make_uint2((u32)frame, (u32)i);
             continue;
         }
-        const RootState r0 = root_load(&A.rstate[fo + r]);
+        const RootState r0 = root_initial(A, fo, r);
         int s = r0.size;
         float2 f = make_float2(r0.fx, r0.fy);
         ushort4 bb = r0.bbox;
         int j = i;
         for (;;) {
-            const RootState ra = root_load(&A.rstate[fo + A.ev_loser[fo + j]]);
+            const RootState ra = root_absorbed(A, fo, A.ev_loser[fo + j], wave);
             const int sa = ra.size;
             const float2 fa = make_float2(ra.fx, ra.fy);
             const ushort4 ba = ra.bbox;
@@ -1288,7 +1308,7 @@ k_replay_scan(ReplayArgs A, int wave) {
         }
         if (valid) head = j == w0 || ev_chain(A.ev_key[fo + j - 1], A.eb) != ev_chain(key, A.eb);
         if (is_long) {
-            const RootState ra = root_load(&A.rstate[fo + A.ev_loser[fo + j]]);
+            const RootState ra = root_absorbed(A, fo, A.ev_loser[fo + j], wave);
             const int sa = ra.size;
             const float2 fa = make_float2(ra.fx, ra.fy);
             const ushort4 ba = ra.bbox;
@@ -1418,7 +1438,7 @@ k_replay_operands(ReplayArgs A, int wave) {
             bb.w = max(bb.w, c.bb.w);
         }
         // the root's own state before this wave
-        const RootState rr = root_load(&A.rstate[fo + r]);
+        const RootState rr = root_initial(A, fo, r);
         const int s_after = s + rr.size;
         const ushort4 rb = rr.bbox;
         bb.x = min(bb.x, rb.x);
@@ -1473,8 +1493,7 @@ k_replay_serial_long(ReplayArgs A, int wave) {
         const u64 chain = ev_chain(k0, A.eb);
         float2 f;
         {
-            const RootState rr = root_load(&A.rstate[fo + ev_winner(k0, A.eb)]);
-            f = make_float2(rr.fx, rr.fy);
+            f = A.flow[fo + ev_winner(k0, A.eb)];  // the root's own pixel (root_initial)
         }
         int j0 = i0;
         // rounds t+1 and t+2 are in flight while round t is replayed; a load never waits for the chain test of its
