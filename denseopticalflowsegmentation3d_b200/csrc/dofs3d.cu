@@ -373,15 +373,18 @@ int segment_dev(dofs3d_ctx* ctx, const float* d_flow, int already_blurred, int n
     // enqueued, finished frames skip
     BorState& B = ctx->bor;
     const dim3 gS = grid_stride(ctx, n);
-    LAUNCH(ctx, k_bor_init, gS, SEG_THREADS, 0, B, ctx->best_score,
-           ctx->sel_time, ctx->sel_box, W, H, N, ctx->seg.neighbors == 8 ? 1 : 0);
+    // per-root selection state: no score yet (0), no snapshot time (INF), no box (-1); everything else per root is written
+    // by the level-0 kernels
+    CK(cudaMemsetAsync(ctx->best_score, 0, sizeof(u64) * (size_t)n * N, ctx->stream));
+    CK(cudaMemsetAsync(ctx->sel_time, 0xFF, sizeof(u32) * (size_t)n * N, ctx->stream));
+    CK(cudaMemsetAsync(ctx->sel_box, 0xFF, sizeof(int) * (size_t)n * N, ctx->stream));
     CK(cudaMemsetAsync(ctx->counters, 0, sizeof(int) * CNT_KINDS * F, ctx->stream));
     CK(cudaMemsetAsync(B.n_roots, 0, sizeof(int) * EV_MAX_WAVES * F, ctx->stream));
     const int levels = ctx->max_levels;
     for (int level = 0; level < levels; ++level) {
         if (level == 0) {
             LAUNCH(ctx, k_bor_level0_pick, gS, SEG_THREADS, 0, B, prefix, ctx->S, ctx->flow_blur, W, H, N);
-            LAUNCH(ctx, k_bor_level0_root, gS, SEG_THREADS, 0, B, W, N);
+            LAUNCH(ctx, k_bor_level0_root, gS, SEG_THREADS, 0, B, W, H, N, ctx->seg.neighbors == 8 ? 1 : 0);
         } else {
             LAUNCH(ctx, k_bor_pixel, gS, SEG_THREADS, 0, B, prefix, ctx->S, ctx->flow_blur, W, N, level);
             LAUNCH(ctx, k_bor_root, gS, SEG_THREADS, 0, B, W, N, level);

@@ -544,26 +544,6 @@ DOFS_D void list_append_block(u32* list, int* counter, bool want, u32 value) {
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(SEG_THREADS)
-k_bor_init(BorState S, u64* __restrict__ best_score, u32* __restrict__ sel_time,
-           int* __restrict__ sel_box, int W, int H, int N, int neighbors8) {
-    const int frame = blockIdx.y;
-    GRID_STRIDE(p, N) {
-        const size_t g = (size_t)frame * N + p;
-        S.comp[g] = (u32)p;
-        S.newp[g] = (u32)p;
-        S.loss_time[g] = DOFS_INF32;
-        S.up[g] = (u32)p;
-        S.lvl[g] = 0;
-        const int y = p / W, x = p - y * W;
-        S.mask[g] = (u8)incident_mask(x, y, W, H, neighbors8);
-        // (Forest::Forest's singleton sets, graph.cpp:129-148, are never materialised: see root_initial)
-        best_score[g] = 0ull;
-        sel_time[g] = DOFS_INF32;
-        sel_box[g] = -1;
-    }
-}
-
 // Every pixel offers the smallest of its (up to eight) incident edges that leave its component to ITS OWN component:
 // one atomic per boundary pixel, and neighbouring pixels mostly address the same word.  Pixels are visited in image
 // order (neighbouring component ids share cache lines); a pixel whose incident edges have all become internal costs
@@ -702,20 +682,31 @@ k_bor_level0_pick(BorState S, const u32* __restrict__ prefix, size_t prefix_stri
     }
 }
 
+// Also the only initialisation the per-root arrays get: every pixel is a root here, so hook target, loss slot, rank
+// and edge mask are written for all of them (no separate init pass); `up` and `comp` follow in the level-0 contraction
+// and relabel.
 __global__ void __launch_bounds__(SEG_THREADS)
-k_bor_level0_root(BorState S, int W, int N) {
+k_bor_level0_root(BorState S, int W, int H, int N, int neighbors8) {
     const int frame = blockIdx.y;
     const size_t fo = (size_t)frame * N;
     GRID_STRIDE(p, N) {
+        const int y = p / W, x = p - y * W;
+        S.mask[fo + p] = (u8)incident_mask(x, y, W, H, neighbors8);
+        S.lvl[fo + p] = 0;
         const u64 t = S.best[fo + p];
-        if (t == PICK_NONE) continue;  // a frame of one pixel
-        const u32 slot = (u32)t;
-        const int s = (int)(slot >> 2), e = edge_other(s, (int)(slot & 3u), W);
-        const int q = s == p ? e : s;
-        const bool mutual = S.best[fo + q] == t;
-        if (mutual && p == e) continue;  // rank tie: the `end` side survives (graph.cpp:177-182, 210-213); newp[p] is p
-        S.newp[fo + p] = (u32)q;
-        S.loss_time[fo + p] = slot;
+        u32 hook = (u32)p, loss = DOFS_INF32;
+        if (t != PICK_NONE) {  // (PICK_NONE: a pixel without a finite-weight edge)
+            const u32 slot = (u32)t;
+            const int s = (int)(slot >> 2), e = edge_other(s, (int)(slot & 3u), W);
+            const int q = s == p ? e : s;
+            const bool mutual = S.best[fo + q] == t;
+            if (!(mutual && p == e)) {  // rank tie: the `end` side survives (graph.cpp:177-182, 210-213)
+                hook = (u32)q;
+                loss = slot;
+            }
+        }
+        S.newp[fo + p] = hook;
+        S.loss_time[fo + p] = loss;
     }
 }
 
@@ -786,7 +777,7 @@ k_bor_contract(BorState S, int N, int level) {
             }
             survives = g == c;
             if (survives) S.best[fo + c] = PICK_NONE;  // only live roots collect offers in the next level
-            else S.up[fo + c] = g;
+            if (!survives || level == 0) S.up[fo + c] = g;  // (level 0 initialises `up`: a survivor points at itself)
         }
         list_append_block(next, &S.n_roots[level * S.F + frame], survives, c);
     }
@@ -798,6 +789,10 @@ k_bor_relabel(BorState S, int N, int level) {
     const int frame = blockIdx.y;
     if (bor_done(S, level, frame)) return;
     const size_t fo = (size_t)frame * N;
+    if (level == 0) {  // every pixel is its own component: this is where `comp` is first written
+        GRID_STRIDE(p, N) S.comp[fo + p] = S.up[fo + p];
+        return;
+    }
     GRID_STRIDE(p, N) {
         const u32 c = S.comp[fo + p];
         const u32 g = S.up[fo + c];
