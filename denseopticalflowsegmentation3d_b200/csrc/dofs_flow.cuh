@@ -408,19 +408,16 @@ k_polyexp(const float* __restrict__ I, float* __restrict__ R, int Wk, int Hk, Po
 }
 
 // ---------------------------------------------------------------------------------------------
-// K3  flow of the next finer level: resize(prev_flow, size, INTER_LINEAR) * (1 / pyr_scale)
+// K3  flow of the next finer level: resize(prev_flow, size, INTER_LINEAR) * (1 / pyr_scale) — evaluated inside the
+// first k_update_matrices of the level, never stored
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-k_flow_upsample(const float2* __restrict__ prev, float2* __restrict__ flow, int Wp, int Hp, int Wk, int Hk, double mul) {
-    const int pair = blockIdx.z;
-    const int x = blockIdx.x * 32 + (threadIdx.x & 31);
-    const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
-    if (x >= Wk || y >= Hk) return;
+// one pixel of resize(prev_flow, (Wk, Hk), INTER_LINEAR) * mul
+DOFS_D float2 flow_upsampled(const float2* __restrict__ src /* [Hp][Wp] of the pair */, int x, int y, int Wp, int Hp, int Wk,
+                             int Hk, double mul) {
     int sx, sy;
     float fx, fy;
     flow_linear_coord(x, (double)Wp / Wk, Wp, &sx, &fx);
     flow_linear_coord(y, (double)Hp / Hk, Hp, &sy, &fy);
-    const float2* src = prev + (size_t)pair * Wp * Hp;
     const int sx1 = min(sx + 1, Wp - 1), sy1 = min(sy + 1, Hp - 1);
     const float2 a = src[(size_t)sy * Wp + sx], b = src[(size_t)sy * Wp + sx1];
     const float2 c = src[(size_t)sy1 * Wp + sx], d = src[(size_t)sy1 * Wp + sx1];
@@ -428,7 +425,7 @@ k_flow_upsample(const float2* __restrict__ prev, float2* __restrict__ flow, int 
     const float tx = xfadd(xfmul(a.x, wx0), xfmul(b.x, fx)), ty = xfadd(xfmul(a.y, wx0), xfmul(b.y, fx));
     const float bx = xfadd(xfmul(c.x, wx0), xfmul(d.x, fx)), by = xfadd(xfmul(c.y, wx0), xfmul(d.y, fx));
     const float vx = xfadd(xfmul(tx, wy0), xfmul(bx, fy)), vy = xfadd(xfmul(ty, wy0), xfmul(by, fy));
-    flow[((size_t)pair * Hk + y) * Wk + x] = make_float2((float)xdmul((double)vx, mul), (float)xdmul((double)vy, mul));
+    return make_float2((float)xdmul((double)vx, mul), (float)xdmul((double)vy, mul));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -449,9 +446,19 @@ DOFS_D float flow_border_scale(int x, int y, int w, int h) {
     return s;
 }
 
+// The flow a level starts from — zero at the coarsest level, the upsampled flow of the coarser level otherwise — is only
+// ever read here (the first box filter + solve overwrites it), so the first launch of a level forms it on the fly.
+struct FlowStart {
+    const float2* prev;  // flow of the coarser level, or nullptr: the level starts from zero
+    int Wp, Hp;
+    double mul;
+};
+enum { UM_FLOW = 0, UM_START = 1 };
+
+template <int MODE>
 __global__ void __launch_bounds__(256)
 k_update_matrices(const float* __restrict__ R, const float2* __restrict__ flow, float* __restrict__ M, int Wk, int Hk,
-                  PairSlots ps) {
+                  PairSlots ps, FlowStart fs) {
     const int pair = blockIdx.z;
     const int x = blockIdx.x * 32 + (threadIdx.x & 31);
     const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
@@ -459,7 +466,10 @@ k_update_matrices(const float* __restrict__ R, const float2* __restrict__ flow, 
     const size_t npx = (size_t)Wk * Hk;
     const float* R0 = R + ((size_t)(pair + ps.first0) * npx + (size_t)y * Wk + x) * 5;
     const float* R1 = R + (size_t)(pair + ps.first1) * npx * 5;
-    const float2 d = flow[(size_t)pair * npx + (size_t)y * Wk + x];
+    float2 d;
+    if (MODE == UM_FLOW) d = flow[(size_t)pair * npx + (size_t)y * Wk + x];
+    else if (fs.prev) d = flow_upsampled(fs.prev + (size_t)pair * fs.Wp * fs.Hp, x, y, fs.Wp, fs.Hp, Wk, Hk, fs.mul);
+    else d = make_float2(0.f, 0.f);
     const float dx = d.x, dy = d.y;
     float fx = xfadd((float)x, dx), fy = xfadd((float)y, dy);
     const int x1 = (int)floorf(fx), y1 = (int)floorf(fy);
@@ -757,13 +767,11 @@ inline int farneback_run(FlowBuffers& fb, const u8* d_gray0, const u8* d_gray1, 
         const dim3 g_pair((L.w + 31) / 32, (L.h + 7) / 8, n);
         const dim3 g_box((L.w + BS_COLS - 1) / BS_COLS, (L.h + BS_ROWS - 1) / BS_ROWS, n);
         cur = (k == 0) ? d_flow_out : (prev == fb.flowA ? fb.flowB : fb.flowA);
-        if (!prev) {
-            if (cudaMemsetAsync(cur, 0, (size_t)n * L.w * L.h * sizeof(float2), stream) != cudaSuccess) return 3;
-        } else {
-            k_flow_upsample<<<g_pair, blk, 0, stream>>>(prev, cur, Wp, Hp, L.w, L.h, 1.0 / fb.cfg.pyr_scale);
-            st->launches++;
-        }
-        FLOW_MARK(st, "flow.init");
+        FlowStart start;
+        start.prev = prev;
+        start.Wp = Wp;
+        start.Hp = Hp;
+        start.mul = 1.0 / fb.cfg.pyr_scale;
         if (L.w == fb.W && L.h == fb.H && L.taps.radius == 1)
             k_pyr_level0<<<g_img, blk, 0, stream>>>(imgs, fb.I, fb.W, fb.H, L.taps);
         else
@@ -774,7 +782,7 @@ inline int farneback_run(FlowBuffers& fb, const u8* d_gray0, const u8* d_gray1, 
         else
             k_polyexp<0><<<g_img, blk, 0, stream>>>(fb.I, fb.R, L.w, L.h, fb.poly);
         FLOW_MARK(st, "flow.polyexp");
-        k_update_matrices<<<g_pair, blk, 0, stream>>>(fb.R, cur, fb.M, L.w, L.h, ps);
+        k_update_matrices<UM_START><<<g_pair, blk, 0, stream>>>(fb.R, cur, fb.M, L.w, L.h, ps, start);
         FLOW_MARK(st, "flow.update_matrices");
         st->launches += 3;
         for (int it = 0; it < fb.cfg.iters; ++it) {
@@ -786,7 +794,7 @@ inline int farneback_run(FlowBuffers& fb, const u8* d_gray0, const u8* d_gray1, 
             st->launches++;
             FLOW_MARK(st, k == 0 ? "flow.box_solve.L0" : "flow.box_solve");
             if (it < fb.cfg.iters - 1) {
-                k_update_matrices<<<g_pair, blk, 0, stream>>>(fb.R, cur, fb.M, L.w, L.h, ps);
+                k_update_matrices<UM_FLOW><<<g_pair, blk, 0, stream>>>(fb.R, cur, fb.M, L.w, L.h, ps, start);
                 st->launches++;
                 FLOW_MARK(st, "flow.update_matrices");
             }
