@@ -111,10 +111,17 @@ k_blur_fused(const float2* __restrict__ src, float2* __restrict__ dst, int W, in
     const int x0 = blockIdx.x * FB_T, y0 = blockIdx.y * FB_T;
     const float2* img = src + (size_t)frame * W * H;
     const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
-    for (int ry = wrp; ry < C; ry += 8) {
-        const int yy = reflect101(y0 + ry - R, H);
-        const float2* row = img + (size_t)yy * W;
-        for (int cx = lane; cx < C; cx += 32) s_in[ry][cx] = row[reflect101(x0 + cx - R, W)];
+    if (x0 >= R && y0 >= R && x0 + FB_T + R <= W && y0 + FB_T + R <= H) {  // no border in reach: plain rows (block-uniform)
+        for (int ry = wrp; ry < C; ry += 8) {
+            const float2* row = img + (size_t)(y0 + ry - R) * W + (x0 - R);
+            for (int cx = lane; cx < C; cx += 32) s_in[ry][cx] = row[cx];
+        }
+    } else {
+        for (int ry = wrp; ry < C; ry += 8) {
+            const int yy = reflect101(y0 + ry - R, H);
+            const float2* row = img + (size_t)yy * W;
+            for (int cx = lane; cx < C; cx += 32) s_in[ry][cx] = row[reflect101(x0 + cx - R, W)];
+        }
     }
     __syncthreads();
     // rows: (tile row, group of 4 columns)
