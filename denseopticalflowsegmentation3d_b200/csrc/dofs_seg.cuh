@@ -124,52 +124,41 @@ k_blur_fused(const float2* __restrict__ src, float2* __restrict__ dst, int W, in
         }
     }
     __syncthreads();
-    // rows: (tile row, group of 4 columns), rows fastest (row pitch C+1 = 9 mod 16 float2: a half-warp reads 16 distinct
-    // 64-bit banks).  Every sample is loaded once and fed to the (up to) four outputs it belongs to — for each output the
-    // taps still arrive in ascending order, so the sums are those of k_blur_rows bit for bit, with 4 accumulators live
-    // instead of a 28-sample window (the kernel is bound by load latency: registers are occupancy).
+    // rows: (tile row, group of 4 columns)
     for (int w = threadIdx.x; w < C * (FB_T / 4); w += 256) {
-        const int ry = w % C, g = w / C;
-        float2 acc[4];
+        const int ry = w / (FB_T / 4), g = w % (FB_T / 4);
+        float2 v[2 * R + 4];
 #pragma unroll
-        for (int o = 0; o < 4; ++o) acc[o] = make_float2(0.f, 0.f);
+        for (int i = 0; i < 2 * R + 4; ++i) v[i] = s_in[ry][4 * g + i];
 #pragma unroll
-        for (int i = 0; i < 2 * R + 4; ++i) {
-            const float2 v = s_in[ry][4 * g + i];
+        for (int o = 0; o < 4; ++o) {
+            float sx = 0.f, sy = 0.f;
 #pragma unroll
-            for (int o = 0; o < 4; ++o) {
-                if (i - o >= 0 && i - o <= 2 * R) {
-                    acc[o].x = fmaf(taps.k[i - o], v.x, acc[o].x);
-                    acc[o].y = fmaf(taps.k[i - o], v.y, acc[o].y);
-                }
+            for (int k = 0; k <= 2 * R; ++k) {
+                sx = fmaf(taps.k[k], v[o + k].x, sx);
+                sy = fmaf(taps.k[k], v[o + k].y, sy);
             }
+            s_h[ry][4 * g + o] = make_float2(sx, sy);
         }
-#pragma unroll
-        for (int o = 0; o < 4; ++o) s_h[ry][4 * g + o] = acc[o];
     }
     __syncthreads();
     // columns: (tile column, group of 4 rows)
     {
         const int tx = threadIdx.x & 31, g = threadIdx.x >> 5;  // 8 groups of 4 rows
-        float2 acc[4];
+        float2 v[2 * R + 4];
 #pragma unroll
-        for (int o = 0; o < 4; ++o) acc[o] = make_float2(0.f, 0.f);
-#pragma unroll
-        for (int i = 0; i < 2 * R + 4; ++i) {
-            const float2 v = s_h[4 * g + i][tx];
-#pragma unroll
-            for (int o = 0; o < 4; ++o) {
-                if (i - o >= 0 && i - o <= 2 * R) {
-                    acc[o].x = fmaf(taps.k[i - o], v.x, acc[o].x);
-                    acc[o].y = fmaf(taps.k[i - o], v.y, acc[o].y);
-                }
-            }
-        }
+        for (int i = 0; i < 2 * R + 4; ++i) v[i] = s_h[4 * g + i][tx];
         const int x = x0 + tx;
 #pragma unroll
         for (int o = 0; o < 4; ++o) {
+            float sx = 0.f, sy = 0.f;
+#pragma unroll
+            for (int k = 0; k <= 2 * R; ++k) {
+                sx = fmaf(taps.k[k], v[o + k].x, sx);
+                sy = fmaf(taps.k[k], v[o + k].y, sy);
+            }
             const int y = y0 + 4 * g + o;
-            if (x < W && y < H) dst[(size_t)frame * W * H + (size_t)y * W + x] = acc[o];
+            if (x < W && y < H) dst[(size_t)frame * W * H + (size_t)y * W + x] = make_float2(sx, sy);
         }
     }
 }
