@@ -2,18 +2,22 @@
 //
 // The reference (cpp/src/graph.cpp) is a strictly sequential Kruskal loop with union by rank, a
 // running float mean per set and a per-merge scoring hook.  This file computes the SAME merge
-// sequence and per-merge state in parallel, using one structural fact (checked against the reference
+// sequence and per-merge state in parallel, using two structural facts (checked against the reference
 // in tests/ and tools/proto_parallel.py):
 //
-//   Boruvka levels on the (weight, insertion-order)-ranked edges are exactly the union-by-rank ranks.
-//   In level k every current component S (all have rank k) picks its minimum outgoing edge m_k(S).
-//     * a pick that is not mutual: S loses at time m_k(S) to whatever component holds the other
-//       endpoint at that time (it has rank > k);
-//     * a mutual pick (S and S' pick the same edge): a rank tie; the component holding `edge.end`
-//       survives (graph.cpp:177-182) and becomes a level k+1 component.
-//   So every root id loses exactly once, at loss_time[c] (position of its edge in the sorted list),
-//   and `up[c]` = root of the next-level component it is contracted into.  The root of any pixel's
-//   set at time t is found by climbing `up` while loss_time < t (<= max rank hops).
+//   1. The loop only acts on the edges it accepts, and those are the minimum spanning forest under the strict
+//      order (weight, insertion sequence) whatever else is in the sorted list.  So the 4N edge slots are never
+//      sorted here: Boruvka compares edges directly, and only the <= N-1 accepted edges are ordered afterwards
+//      (their positions are the merge times).
+//   2. Boruvka levels under that order are exactly the union-by-rank ranks.
+//      In level k every current component S (all have rank k) picks its minimum outgoing edge m_k(S).
+//        * a pick that is not mutual: S loses at m_k(S) to whatever component holds the other
+//          endpoint at that time (it has rank > k);
+//        * a mutual pick (S and S' pick the same edge): a rank tie; the component holding `edge.end`
+//          survives (graph.cpp:177-182) and becomes a level k+1 component.
+//      So every root id loses exactly once, at the time of its edge, and `up[c]` = root of the next-level
+//      component it is contracted into.  The root of any pixel's set at time t is found by climbing `up`
+//      while loss time < t (<= max rank hops).
 //
 // Merge events are then grouped into per-root chains ordered by time, and the chains are replayed
 // in waves of increasing final rank (a chain only absorbs roots of strictly lower final rank), which

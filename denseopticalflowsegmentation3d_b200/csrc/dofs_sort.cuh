@@ -1,12 +1,11 @@
 // Stable LSD radix sort of (key, u32 payload) pairs, batched over frames (blockIdx.y = frame), for
 // 32-bit and 64-bit keys.
 //
-// Reproduces the order of the reference's std::multiset edge container (graph.cpp:55-60): ascending
-// f64 weight (non-negative doubles order like their bit patterns), equal weights in insertion order —
-// i.e. a STABLE sort of the insertion sequence by weight.  The edge list is ordered in two steps
-// (dofs_seg.cuh: 4 passes on an order-preserving 32-bit prefix of the weight, then an exact in-place
-// repair of the short runs that share a prefix); the full 64-bit sort is the fallback of that scheme and
-// the sort of the merge events by (wave, winner root, time).
+// Used for the merge times (dofs_seg.cuh: the <= N-1 accepted edges on a 32-bit key, 4 passes, then an exact repair of
+// the short runs that share a prefix), for the merge events by (wave, winner root, time) (64-bit keys), for the exact
+// 64-bit fallback of the merge times, and — parity hook dofs3d_edges_sorted only — for the reference's whole edge list
+// in std::multiset order (graph.cpp:55-60): ascending f64 weight (non-negative doubles order like their bit patterns),
+// equal weights in insertion order, i.e. a STABLE sort of the insertion sequence by weight.
 //
 // One 8-bit digit per pass, three kernels per pass:
 //   k_radix_hist     per-tile digit histogram             reads keys
