@@ -151,3 +151,54 @@ def test_port_equals_ref_random(port, ref, seed, W, H, n8):
 def test_get_mats_port_equals_ref(port, ref):
     for a, b in zip(port.get_mats(), ref.get_mats()):
         assert np.array_equal(a, b)
+
+
+# ---------------------------------------------------------------------------------------------------
+# The structural fact the CUDA segmentation rests on (csrc/dofs_seg.cuh K8): the merge loop only
+# acts on the edges it accepts, so ordering THOSE edges — on one 32-bit key (the slot for a zero weight, else an
+# order-preserving 32-bit prefix of the weight) with ties of a prefix broken by (weight, slot) — reproduces the order in
+# which the reference accepts them.  Checked here on the CPU against the port's merge trace.
+def _edge_prefix(w):
+    """csrc/dofs_seg.cuh edge_prefix: exponent rebased to 2^-200, top 23 mantissa bits."""
+    bits = np.ascontiguousarray(w, np.float64).view(np.uint64)
+    base = np.uint64((1023 - 200) << 52)
+    k = np.where(bits > base, bits - base, np.uint64(0))
+    return np.minimum(k >> np.uint64(29), np.uint64(0xFFFFFFFE)).astype(np.uint64)
+
+
+def _near_tie_columns(W, H, seed=0):
+    rng = np.random.default_rng(seed)
+    f = np.zeros((H, W, 2), np.float32)
+    f[..., 1] = np.arange(H, dtype=np.float32)[:, None] + 1000.0 * np.arange(W, dtype=np.float32)[None, :]
+    f[..., 0] = (rng.random((H, W)) * 3e-4).astype(np.float32)
+    return f
+
+
+@pytest.mark.parametrize("field", ["random", "zero", "near_tie"])
+def test_merge_times_from_accepted_edges_only(port, field):
+    W, H = 64, 40
+    if field == "random":
+        fb = random_flow(7, W, H)  # smooth field with exactly-flat patches (zero-weight ties)
+    elif field == "zero":
+        fb = np.zeros((H, W, 2), np.float32)
+    else:
+        fb = _near_tie_columns(W, H)  # thousands of accepted edges of weight 1 + O(1e-8): one prefix, different weights
+    persp, inv, up = port.get_mats()
+    start, end, w = port.build_graph(fb, True)
+    tr = port.segment(fb, persp, inv, up, trace=True)["trace"]
+    pos = tr["edge_pos"].astype(np.int64)  # positions of the accepted edges in the reference's sorted list, in merge order
+    assert len(pos) == W * H - 1 and np.all(np.diff(pos) > 0)
+    s, e, wa = start[pos].astype(np.int64), end[pos].astype(np.int64), w[pos]
+    # slot = 4 * start + direction (0 left, 1 up, 2 up-left, 3 down-left) = the reference's insertion sequence number
+    d = np.select([e == s - 1, e == s - W, e == s - W - 1, e == s + W - 1], [0, 1, 2, 3], -1)
+    assert np.all(d >= 0)
+    slot = 4 * s + d
+    prefix = _edge_prefix(wa)
+    assert np.all((prefix == 0) == (wa == 0)) and np.all(prefix[wa > 0] >= 0x19800000) and 4 * W * H < 0x19800000
+    key = np.where(prefix == 0, slot.astype(np.uint64), prefix)
+    # order by (key, weight, slot) — what the 4-pass radix sort + the repair of equal-prefix runs produce
+    order = np.lexsort((slot, wa.view(np.uint64), key))
+    assert np.array_equal(order, np.arange(len(pos))), "merge times from the accepted edges alone differ from the reference order"
+    if field == "near_tie":
+        runs = np.unique(key, return_counts=True)[1]
+        assert runs.max() > 2048  # the case the exact fallback sort exists for
