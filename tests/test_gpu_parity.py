@@ -413,7 +413,7 @@ def test_full_size_1080p_properties_and_oracle(dofs, port):
     psets = box_pixel_sets(labels, boxes)
     assert len(boxes) > 0
     for b, px in zip(boxes, psets):
-        assert len(px) == b["size"] and int(b["root"]) in set(px.tolist()[:0]) or True
+        assert len(px) == b["size"]
         assert b["root"] in px                      # every root pixel is a member of its own set
         if b["parent_box"] >= 0:                    # nesting: a child's set is inside its parent's
             assert np.isin(px, psets[b["parent_box"]]).all()
