@@ -55,8 +55,31 @@ class Stats(C.Structure):
 STATS_DTYPE = np.dtype([(k, "<i4") for k in ("n_edges", "n_merges", "n_levels", "n_candidates", "n_scored",
                                              "n_boxes", "longest_chain", "final_root", "sort_fallback", "replay_exact_chunks")])
 
+class Run(C.Structure):
+    _fields_ = [("start", C.c_uint32), ("label", C.c_int32)]
+
+
+RUN_DTYPE = np.dtype([("start", "<u4"), ("label", "<i4")])
+LABELS_I32, LABELS_U16, LABELS_RLE = 0, 1, 2
+
+
+class Outputs(C.Structure):
+    """dofs3d_outputs: where the results of one call go (host or device addresses, depending on the entry point)."""
+    _fields_ = [("label_format", C.c_int), ("labels", C.c_void_p), ("n_runs", C.c_void_p), ("max_runs", C.c_int),
+                ("boxes", C.c_void_p), ("n_boxes", C.c_void_p), ("max_boxes", C.c_int), ("stats", C.c_void_p)]
+
+
+def runs_to_labels(runs, n_runs, n_pixels):
+    """Dense int32 label image of one frame from its run-length form."""
+    r = runs[:n_runs]
+    ends = np.append(r["start"][1:], n_pixels).astype(np.int64)
+    return np.repeat(r["label"], ends - r["start"].astype(np.int64)).astype(np.int32)
+
+
 # every symbol include/dofs3d.h declares
 SYMBOLS = [
+    "dofs3d_process_ex", "dofs3d_process_ex_dev", "dofs3d_segment_ex", "dofs3d_stream_begin", "dofs3d_stream_submit",
+    "dofs3d_stream_collect", "dofs3d_node_state", "dofs3d_scored_merges", "dofs3d_pinned_alloc", "dofs3d_pinned_free",
     "dofs3d_default_params", "dofs3d_params_for_size", "dofs3d_create", "dofs3d_destroy", "dofs3d_sync", "dofs3d_last_error", "dofs3d_stream",
     "dofs3d_launch_count", "dofs3d_device_bytes", "dofs3d_gray", "dofs3d_gray_dev", "dofs3d_flow", "dofs3d_blur",
     "dofs3d_segment", "dofs3d_paint", "dofs3d_lift", "dofs3d_edges_sorted", "dofs3d_process", "dofs3d_process_dev",
@@ -107,6 +130,18 @@ def load_library():
     L.dofs3d_process.argtypes = [vp, u8p, C.c_int, ip, vp, ip, C.c_int, vp]
     L.dofs3d_process_dev.argtypes = [vp, u8p, C.c_int, ip, vp, ip, C.c_int, vp]
     L.dofs3d_synth_frames_dev.argtypes = [vp, C.c_uint32, C.c_int, C.c_int, C.c_int, u8p]
+    L.dofs3d_process_ex.argtypes = [vp, u8p, C.c_int, C.POINTER(Outputs)]
+    L.dofs3d_process_ex_dev.argtypes = [vp, u8p, C.c_int, C.POINTER(Outputs)]
+    L.dofs3d_segment_ex.argtypes = [vp, fp, C.c_int, C.c_int, C.POINTER(Outputs)]
+    L.dofs3d_stream_begin.argtypes = [vp]
+    L.dofs3d_stream_submit.argtypes = [vp, u8p, C.c_int, C.POINTER(Outputs)]
+    L.dofs3d_stream_collect.argtypes = [vp, C.POINTER(C.c_int)]
+    L.dofs3d_node_state.argtypes = [vp, C.c_int, C.c_int, ip, fp, ip]
+    L.dofs3d_scored_merges.argtypes = [vp, C.c_int, C.c_int, ip, ip, vp, u8p]
+    L.dofs3d_pinned_alloc.argtypes = [C.c_size_t]
+    L.dofs3d_pinned_alloc.restype = C.c_void_p
+    L.dofs3d_pinned_free.argtypes = [vp]
+    L.dofs3d_pinned_free.restype = None
     L.dofs3d_set_timing.argtypes = [vp, C.c_int]
     L.dofs3d_get_timing.argtypes = [vp, C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.POINTER(C.c_int), C.c_int]
     _lib = L
@@ -137,6 +172,7 @@ class Context:
         self.L = load_library()
         self.W, self.H, self.N, self.max_pairs = width, height, width * height, max_pairs
         self.h = C.c_void_p()
+        self._stream_pending = []
         rc = self.L.dofs3d_create(C.byref(self.h), device, width, height, max_pairs,
                                   C.byref(params) if params is not None else None)
         if rc != 0:
@@ -240,9 +276,107 @@ class Context:
         return {"labels": labels, "boxes": [boxes[i, :n_boxes[i]] for i in range(n)], "n_boxes": n_boxes,
                 "stats": stats}
 
+    # ---- compact result formats ------------------------------------------------------------
+    def _host_outputs(self, n, label_format, max_boxes, max_runs):
+        if label_format == LABELS_RLE:
+            labels = np.zeros((n, max_runs), RUN_DTYPE)
+        else:
+            labels = np.empty((n, self.H, self.W), np.uint16 if label_format == LABELS_U16 else np.int32)
+        arr = dict(labels=labels, n_runs=np.zeros(n, np.int32), boxes=np.zeros((n, max_boxes), BOX_DTYPE),
+                   n_boxes=np.zeros(n, np.int32), stats=np.zeros(n, STATS_DTYPE))
+        o = Outputs(label_format, labels.ctypes.data, arr["n_runs"].ctypes.data, max_runs, arr["boxes"].ctypes.data,
+                    arr["n_boxes"].ctypes.data, max_boxes, arr["stats"].ctypes.data)
+        return arr, o
+
+    @staticmethod
+    def _finish_outputs(arr, n=None):
+        n = len(arr["n_boxes"]) if n is None else n
+        return {"labels": arr["labels"][:n], "n_runs": arr["n_runs"][:n], "n_boxes": arr["n_boxes"][:n],
+                "boxes": [arr["boxes"][i, :arr["n_boxes"][i]] for i in range(n)], "stats": arr["stats"][:n]}
+
+    def process_ex(self, bgr_frames, label_format=LABELS_U16, max_boxes=1024, max_runs=65536):
+        """dofs3d_process_ex: whole path with u16 / run-length / int32 labels."""
+        fr = np.ascontiguousarray(bgr_frames, np.uint8).reshape(-1, self.H, self.W, 3)
+        arr, o = self._host_outputs(fr.shape[0] - 1, label_format, max_boxes, max_runs)
+        self._ck(self.L.dofs3d_process_ex(self.h, _ptr(fr), fr.shape[0], C.byref(o)))
+        return self._finish_outputs(arr)
+
+    def segment_ex(self, flow, already_blurred=False, label_format=LABELS_U16, max_boxes=1024, max_runs=65536):
+        f = np.ascontiguousarray(flow, np.float32).reshape(-1, self.H, self.W, 2)
+        arr, o = self._host_outputs(f.shape[0], label_format, max_boxes, max_runs)
+        self._ck(self.L.dofs3d_segment_ex(self.h, _ptr(f), 1 if already_blurred else 0, f.shape[0], C.byref(o)))
+        return self._finish_outputs(arr)
+
+    # ---- streaming ------------------------------------------------------------------------
+    def stream_begin(self):
+        self._ck(self.L.dofs3d_stream_begin(self.h))
+        self._stream_pending = []
+
+    def stream_submit(self, bgr_frames, label_format=LABELS_U16, max_boxes=1024, max_runs=65536):
+        """Asynchronous; the chunk's arrays are kept alive here until stream_collect returns them."""
+        fr = np.ascontiguousarray(bgr_frames, np.uint8).reshape(-1, self.H, self.W, 3)
+        arr, o = self._host_outputs(self.max_pairs, label_format, max_boxes, max_runs)
+        self._ck(self.L.dofs3d_stream_submit(self.h, _ptr(fr), fr.shape[0], C.byref(o)))
+        self._stream_pending.append((fr, arr, o))
+
+    def stream_collect(self):
+        n = C.c_int(0)
+        self._ck(self.L.dofs3d_stream_collect(self.h, C.byref(n)))
+        _, arr, _ = self._stream_pending.pop(0)
+        return self._finish_outputs(arr, n.value)
+
+    def process_stream(self, bgr_frames, chunk_pairs=None, **kw):
+        """A whole clip [n+1][H][W][3] through the streaming entry points in chunks; concatenated results."""
+        fr = np.ascontiguousarray(bgr_frames, np.uint8).reshape(-1, self.H, self.W, 3)
+        ch = chunk_pairs or self.max_pairs
+        self.stream_begin()
+        outs, pos, inflight = [], 0, 0
+        while pos < fr.shape[0]:
+            nf = min(ch + 1 if pos == 0 else ch, fr.shape[0] - pos)
+            if inflight == 2:
+                outs.append(self.stream_collect())
+                inflight -= 1
+            self.stream_submit(fr[pos:pos + nf], **kw)
+            inflight += 1
+            pos += nf
+        while inflight:
+            outs.append(self.stream_collect())
+            inflight -= 1
+        return {"labels": np.concatenate([o["labels"] for o in outs]), "n_runs": np.concatenate([o["n_runs"] for o in outs]),
+                "n_boxes": np.concatenate([o["n_boxes"] for o in outs]), "boxes": [b for o in outs for b in o["boxes"]],
+                "stats": np.concatenate([o["stats"] for o in outs])}
+
+    # ---- per-node state of the last call ----------------------------------------------------
+    def node_state(self, pair, node):
+        size = C.c_int32(0)
+        flow = np.zeros(2, np.float32)
+        bbox = np.zeros(4, np.int32)
+        self._ck(self.L.dofs3d_node_state(self.h, pair, node, C.byref(size), _ptr(flow), _ptr(bbox)))
+        return {"size": size.value, "mean_flow": flow, "bbox": bbox}
+
+    def scored_merges(self, pair):
+        n = self._ck(self.L.dofs3d_scored_merges(self.h, pair, 0, None, None, None, None))
+        root, time = np.zeros(n, np.int32), np.zeros(n, np.uint32)
+        score, kept = np.zeros(n, np.float64), np.zeros(n, np.uint8)
+        if n:
+            self._ck(self.L.dofs3d_scored_merges(self.h, pair, n, _ptr(root), _ptr(time), _ptr(score), _ptr(kept)))
+        return {"root": root, "time": time, "score": score, "kept": kept.astype(bool)}
+
+    def last_scores(self, pair):
+        """Forest::get_segment_best_score for every root that has one: {root: score of its latest scored merge}."""
+        m = self.scored_merges(pair)
+        out, when = {}, {}
+        for r, t, s in zip(m["root"].tolist(), m["time"].tolist(), m["score"].tolist()):
+            if r not in when or when[r] < t:
+                when[r], out[r] = t, s
+        return out
+
     # ---- raw device-pointer entry points (ints are device addresses, e.g. torch.Tensor.data_ptr()) ----
     def synth_frames_dev(self, seed, n_objects, first_frame, n_frames, d_bgr_ptr):
         self._ck(self.L.dofs3d_synth_frames_dev(self.h, seed, n_objects, first_frame, n_frames, C.c_void_p(d_bgr_ptr)))
+
+    def process_ex_dev(self, d_bgr_ptr, n_frames, outputs):
+        self._ck(self.L.dofs3d_process_ex_dev(self.h, C.c_void_p(d_bgr_ptr), n_frames, C.byref(outputs)))
 
     def process_dev(self, d_bgr_ptr, n_frames, d_labels=None, d_boxes=None, d_n_boxes=None, max_boxes=0, d_stats=None):
         v = lambda p: None if p is None else C.c_void_p(p)  # noqa: E731

@@ -143,13 +143,32 @@ struct dofs3d_ctx {
     double* cand_score = nullptr;
     int cand_cap = 0, box_cap = 0;
     int* counters = nullptr;    // [6][F]: n_cand, longest_chain, n_scored, n_boxes, n_roots, final_root
-    dofs3d_stats* h_stats = nullptr;  // pinned copy of the stats of the last call
     int max_levels = 0;               // guaranteed bound of Boruvka levels for this frame size
     bool force_time_fallback = false; // test knob (DOFS3D_FORCE_TIME_FALLBACK=1): always take the exact 64-bit fallback of K8
-    int pending_pairs = 0, pending_max_boxes = -1;  // last asynchronous call, validated by dofs3d_sync
     dofs3d_box *boxes_tmp = nullptr, *boxes = nullptr;
-    int32_t* labels = nullptr;
+    int32_t* labels = nullptr;        // [F][N] int32, or [F][N] u16 in the same buffer (labels_fmt of the last call)
+    int labels_fmt = DOFS3D_LABELS_I32;
+    int* run_count = nullptr;         // [F][run_blocks] label runs starting in every block of 256 pixels, then their scan
+    int* n_runs = nullptr;            // [F]
+    int run_blocks = 0;
+    dofs3d_run* runs = nullptr;       // [F][runs_cap], allocated on the first run-length call
+    int runs_cap = 0;
     dofs3d_stats* stats = nullptr;
+    int* sticky = nullptr;            // device: STICKY_* bits of every call since the last dofs3d_sync
+    int* h_sticky = nullptr;          // pinned copy, refreshed after every call
+
+    // streaming (dofs3d_stream_*): copy stream, two staging buffers, the outstanding chunks
+    cudaStream_t copy_stream = nullptr;
+    u8* stage[2] = {nullptr, nullptr};
+    cudaEvent_t stage_free[2] = {nullptr, nullptr};   // recorded when the gray conversion has consumed the buffer
+    cudaEvent_t stage_ready[2] = {nullptr, nullptr};  // recorded when the upload has landed
+    struct Chunk {
+        int n_pairs;
+        cudaEvent_t done;
+    };
+    std::vector<Chunk> chunks;        // outstanding, oldest first (at most 2)
+    long long chunks_submitted = 0;
+    bool have_carry = false;          // gray slot 0 and fb.R_carry hold the last frame of the previous chunk
 
     // flow buffers
     FlowBuffers fb;
@@ -353,7 +372,17 @@ void blur_launch(dofs3d_ctx* ctx, const float2* src, float2* dst, int n) {
 }
 
 // get_segmented_array (segment.cpp:34-72) for n frames whose (unblurred or blurred) flow is at d_flow.
-int segment_dev(dofs3d_ctx* ctx, const float* d_flow, int already_blurred, int n) {
+// what a call must leave in the context for export_results: label format, run-length capacity, the box capacity the
+// caller announced (for the deferred overflow check)
+struct OutSpec {
+    int fmt = DOFS3D_LABELS_I32;
+    int max_runs = 0;
+    int max_boxes = -1;
+};
+
+int ensure_runs(dofs3d_ctx* ctx, int max_runs);
+
+int segment_dev(dofs3d_ctx* ctx, const float* d_flow, int already_blurred, int n, const OutSpec& spec = OutSpec()) {
     const int N = ctx->N, W = ctx->W, H = ctx->H, F = ctx->F;
     const dim3 gN = grid1(N, SEG_THREADS, n);
     const float2* src = reinterpret_cast<const float2*>(d_flow);
@@ -535,62 +564,142 @@ int segment_dev(dofs3d_ctx* ctx, const float* d_flow, int already_blurred, int n
            ctx->sel_box, N);
     LAUNCH(ctx, k_box_parents<dofs3d_box>, gB, SEG_THREADS, 0, ctx->boxes, A.n_boxes, ctx->box_cap, BT.loss_time,
            ctx->win, ctx->sel_time, ctx->sel_box, N);
-    LAUNCH(ctx, k_labels, gN, SEG_THREADS, 0, ctx->labels, BT.loss_time, ctx->win, ctx->sel_time, ctx->sel_box, N);
+    ctx->labels_fmt = spec.fmt == DOFS3D_LABELS_I32 ? DOFS3D_LABELS_I32 : DOFS3D_LABELS_U16;
+    if (spec.fmt == DOFS3D_LABELS_I32) {
+        LAUNCH(ctx, k_labels<int>, gN, SEG_THREADS, 0, ctx->labels, BT.loss_time, ctx->win, ctx->sel_time, ctx->sel_box, N,
+               (int*)nullptr, 0);
+    } else {
+        const bool rle = spec.fmt == DOFS3D_LABELS_RLE;
+        if (rle) {
+            int rc = ensure_runs(ctx, spec.max_runs);
+            if (rc) return rc;
+        }
+        u16* lab16 = reinterpret_cast<u16*>(ctx->labels);
+        LAUNCH(ctx, k_labels<u16>, gN, SEG_THREADS, 0, lab16, BT.loss_time, ctx->win, ctx->sel_time, ctx->sel_box, N,
+               rle ? ctx->run_count : (int*)nullptr, ctx->run_blocks);
+        if (rle) {
+            LAUNCH(ctx, k_run_scan, dim3(n), 1024, 0, ctx->run_count, ctx->run_blocks, ctx->n_runs, spec.max_runs, ctx->sticky);
+            LAUNCH(ctx, (k_run_write<u16, dofs3d_run>), gN, SEG_THREADS, 0, lab16, ctx->run_count, ctx->run_blocks, ctx->runs,
+                   ctx->runs_cap, N);
+        }
+    }
     mark(ctx, "labels");
 
     // counters -> stats record, on the device; a copy lands in pinned host memory for the host-pointer entry points
     LAUNCH(ctx, k_stats<dofs3d_stats>, dim3((n + 63) / 64), 64, 0, ctx->stats, B, ctx->counters + CNT_CAND * F,
            ctx->counters + CNT_SCORED * F, ctx->counters + CNT_BOXES * F, ctx->counters + CNT_CHAIN * F, n, N,
            n_edges_of(W, H, ctx->seg.neighbors), levels, ctx->repair_flags + 1, ctx->long_count,
-           ctx->sweep_ticket + RS_MAX_PASSES);
-    CK(cudaMemcpyAsync(ctx->h_stats, ctx->stats, sizeof(dofs3d_stats) * n, cudaMemcpyDeviceToHost, ctx->stream));
+           ctx->sweep_ticket + RS_MAX_PASSES, ctx->sticky, ctx->cand_cap, ctx->box_cap, spec.max_boxes);
+    CK(cudaMemcpyAsync(ctx->h_sticky, ctx->sticky, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     return 0;
 }
 
-// after a stream synchronisation: did every frame of the last call fit the queues / converge?
-int check_last_call(dofs3d_ctx* ctx, int n, int max_boxes) {
-    for (int f = 0; f < n; ++f) {
-        const dofs3d_stats& st = ctx->h_stats[f];
-        if (st.final_root < 0) {
-            ctx->err = "internal: Boruvka did not converge or a sort look-back timed out";
-            return DOFS3D_ERR_INTERNAL;
+// run-length buffers, allocated (or grown) on the first call that asks for them
+int ensure_runs(dofs3d_ctx* ctx, int max_runs) {
+    if (max_runs < 1) {
+        ctx->err = "max_runs must be positive for the run-length label format";
+        return DOFS3D_ERR_ARG;
+    }
+    if (!ctx->run_count) {
+        ctx->run_blocks = (ctx->N + SEG_THREADS - 1) / SEG_THREADS;
+        DA(ctx->run_count, (size_t)ctx->F * ctx->run_blocks);
+        DA(ctx->n_runs, (size_t)ctx->F);
+    }
+    if (max_runs > ctx->runs_cap) {
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (ctx->runs) {
+            cudaFree(ctx->runs);
+            ctx->allocs.erase(std::find(ctx->allocs.begin(), ctx->allocs.end(), (void*)ctx->runs));
+            ctx->bytes -= (long long)sizeof(dofs3d_run) * ctx->F * ctx->runs_cap;
+            ctx->runs = nullptr;
         }
-        if (st.n_candidates > ctx->cand_cap) {
-            ctx->err = "candidate queue overflow";
-            return DOFS3D_ERR_OVERFLOW;
-        }
-        if (st.n_boxes > ctx->box_cap || (max_boxes >= 0 && st.n_boxes > max_boxes)) {
-            ctx->err = "more boxes than max_boxes";
-            return DOFS3D_ERR_OVERFLOW;
-        }
+        DA(ctx->runs, (size_t)ctx->F * max_runs);
+        ctx->runs_cap = max_runs;
     }
     return 0;
+}
+
+// the deferred conditions of every call since the last check, from the pinned copy of the sticky bits (the stream must
+// have been synchronised); clears them
+int check_sticky(dofs3d_ctx* ctx) {
+    const int bits = *ctx->h_sticky;
+    if (!bits) return 0;
+    *ctx->h_sticky = 0;
+    CK(cudaMemsetAsync(ctx->sticky, 0, sizeof(int), ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (bits & STICKY_INTERNAL) {
+        ctx->err = "internal: Boruvka did not converge (non-finite flow?) or a sort look-back timed out";
+        return DOFS3D_ERR_INTERNAL;
+    }
+    ctx->err = bits & STICKY_CANDIDATES ? "candidate queue overflow"
+               : bits & STICKY_BOXES    ? "more boxes than max_boxes"
+                                        : "more label runs than max_runs";
+    return DOFS3D_ERR_OVERFLOW;
 }
 
 // copy results of the last segment_dev to caller memory (kind = cudaMemcpyDeviceToHost / DeviceToDevice); asynchronous
-int export_results(dofs3d_ctx* ctx, int n, int32_t* labels_out, dofs3d_box* boxes_out, int32_t* n_boxes_out,
-                   int max_boxes, dofs3d_stats* stats_out, cudaMemcpyKind kind) {
+int export_results(dofs3d_ctx* ctx, int n, const dofs3d_outputs& o, cudaMemcpyKind kind) {
     const int F = ctx->F;
-    if (labels_out)
-        CK(cudaMemcpyAsync(labels_out, ctx->labels, (size_t)n * ctx->N * sizeof(int32_t), kind, ctx->stream));
-    if (boxes_out && max_boxes > 0) {
-        const int cols = std::min(max_boxes, ctx->box_cap);
-        CK(cudaMemcpy2DAsync(boxes_out, (size_t)max_boxes * sizeof(dofs3d_box), ctx->boxes,
+    if (o.labels) {
+        if (o.label_format == DOFS3D_LABELS_RLE) {
+            const int cols = std::min(o.max_runs, ctx->runs_cap);
+            CK(cudaMemcpy2DAsync(o.labels, (size_t)o.max_runs * sizeof(dofs3d_run), ctx->runs,
+                                 (size_t)ctx->runs_cap * sizeof(dofs3d_run), (size_t)cols * sizeof(dofs3d_run), n, kind,
+                                 ctx->stream));
+        } else {
+            const size_t el = o.label_format == DOFS3D_LABELS_U16 ? sizeof(u16) : sizeof(int32_t);
+            CK(cudaMemcpyAsync(o.labels, ctx->labels, (size_t)n * ctx->N * el, kind, ctx->stream));
+        }
+    }
+    if (o.n_runs && o.label_format == DOFS3D_LABELS_RLE)
+        CK(cudaMemcpyAsync(o.n_runs, ctx->n_runs, sizeof(int) * n, kind, ctx->stream));
+    if (o.boxes && o.max_boxes > 0) {
+        const int cols = std::min(o.max_boxes, ctx->box_cap);
+        CK(cudaMemcpy2DAsync(o.boxes, (size_t)o.max_boxes * sizeof(dofs3d_box), ctx->boxes,
                              (size_t)ctx->box_cap * sizeof(dofs3d_box), (size_t)cols * sizeof(dofs3d_box), n, kind,
                              ctx->stream));
     }
-    if (n_boxes_out)
-        CK(cudaMemcpyAsync(n_boxes_out, ctx->counters + CNT_BOXES * F, sizeof(int) * n, kind, ctx->stream));
-    if (stats_out) CK(cudaMemcpyAsync(stats_out, ctx->stats, sizeof(dofs3d_stats) * n, kind, ctx->stream));
+    if (o.n_boxes) CK(cudaMemcpyAsync(o.n_boxes, ctx->counters + CNT_BOXES * F, sizeof(int) * n, kind, ctx->stream));
+    if (o.stats) CK(cudaMemcpyAsync(o.stats, ctx->stats, sizeof(dofs3d_stats) * n, kind, ctx->stream));
     return 0;
 }
 
+int check_outputs(dofs3d_ctx* ctx, const dofs3d_outputs* o, OutSpec* spec) {
+    if (!o) {
+        ctx->err = "null dofs3d_outputs";
+        return DOFS3D_ERR_ARG;
+    }
+    if (o->label_format < DOFS3D_LABELS_I32 || o->label_format > DOFS3D_LABELS_RLE || o->max_boxes < 0 ||
+        (o->label_format == DOFS3D_LABELS_RLE && o->labels && o->max_runs < 1)) {
+        ctx->err = "bad dofs3d_outputs (label_format / max_boxes / max_runs)";
+        return DOFS3D_ERR_ARG;
+    }
+    // run-length output the caller does not collect is not computed
+    spec->fmt = (o->label_format == DOFS3D_LABELS_RLE && !o->labels) ? DOFS3D_LABELS_U16 : o->label_format;
+    spec->max_runs = o->max_runs;
+    spec->max_boxes = o->boxes ? o->max_boxes : -1;
+    return 0;
+}
+
+dofs3d_outputs legacy_outputs(int32_t* labels, dofs3d_box* boxes, int32_t* n_boxes, int max_boxes, dofs3d_stats* stats) {
+    dofs3d_outputs o;
+    memset(&o, 0, sizeof o);
+    o.label_format = DOFS3D_LABELS_I32;
+    o.labels = labels;
+    o.boxes = boxes;
+    o.n_boxes = n_boxes;
+    o.max_boxes = max_boxes;
+    o.stats = stats;
+    return o;
+}
+
 // cvtColor + Farneback for n pairs out of n+1 consecutive gray frames already in ctx->gray
-int flow_dev(dofs3d_ctx* ctx, const u8* d_gray0, const u8* d_gray1, int n, float2* d_flow_out) {
+int flow_dev(dofs3d_ctx* ctx, const u8* d_gray0, const u8* d_gray1, int n, float2* d_flow_out, bool carry_in = false,
+             bool carry_out = false) {
     FlowLaunchStats st;
     st.mark = [](void* u, const char* name) { mark(static_cast<dofs3d_ctx*>(u), name); };
     st.user = ctx;
-    int rc = farneback_run(ctx->fb, d_gray0, d_gray1, n, d_flow_out, ctx->stream, &st);
+    int rc = farneback_run(ctx->fb, d_gray0, d_gray1, n, d_flow_out, ctx->stream, &st, carry_in, carry_out);
     ctx->launches += st.launches;
     if (rc) {
         ctx->err = "farneback_run failed";
@@ -766,7 +875,10 @@ int dofs3d_create(dofs3d_ctx** out, int device, int width, int height, int max_p
         if (v >= 1 && v < ctx->max_levels) ctx->max_levels = v;
     }
     if (const char* e = getenv("DOFS3D_FORCE_TIME_FALLBACK")) ctx->force_time_fallback = atoi(e) != 0;
-    CK(cudaMallocHost(&ctx->h_stats, sizeof(dofs3d_stats) * F));
+    CK(cudaMallocHost(&ctx->h_sticky, sizeof(int)));
+    *ctx->h_sticky = 0;
+    DA(ctx->sticky, 1);
+    CK(cudaMemsetAsync(ctx->sticky, 0, sizeof(int), ctx->stream));
     DA(ctx->boxes_tmp, F * ctx->box_cap);
     DA(ctx->boxes, F * ctx->box_cap);
     DA(ctx->labels, F * N);
@@ -796,7 +908,7 @@ static int ensure_flow(dofs3d_ctx* ctx) {
         ctx->bytes += (long long)fbytes;
         if (rc) {
             ctx->err = farneback_error(rc);
-            return rc == 1 ? DOFS3D_ERR_ARG : DOFS3D_ERR_NOMEM;
+            return rc == 1 ? DOFS3D_ERR_ARG : rc == 3 ? DOFS3D_ERR_CUDA : DOFS3D_ERR_NOMEM;
         }
     }
     DA(ctx->flow_raw, F * N);
@@ -809,7 +921,14 @@ void dofs3d_destroy(dofs3d_ctx* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (void* p : ctx->allocs) cudaFree(p);
     farneback_free(&ctx->fb);
-    if (ctx->h_stats) cudaFreeHost(ctx->h_stats);
+    if (ctx->h_sticky) cudaFreeHost(ctx->h_sticky);
+    for (int i = 0; i < 2; ++i) {
+        if (ctx->stage[i]) cudaFree(ctx->stage[i]);
+        if (ctx->stage_free[i]) cudaEventDestroy(ctx->stage_free[i]);
+        if (ctx->stage_ready[i]) cudaEventDestroy(ctx->stage_ready[i]);
+    }
+    for (auto& c : ctx->chunks) cudaEventDestroy(c.done);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     for (auto& m : ctx->timer.marks) cudaEventDestroy(m.second);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -817,13 +936,9 @@ void dofs3d_destroy(dofs3d_ctx* ctx) {
 
 int dofs3d_sync(dofs3d_ctx* ctx) {
     if (!ctx) return DOFS3D_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->stream));
-    if (ctx->pending_pairs > 0) {  // an asynchronous segment/process call has finished: report overflow / non-convergence
-        const int n = ctx->pending_pairs;
-        ctx->pending_pairs = 0;
-        return check_last_call(ctx, n, ctx->pending_max_boxes);
-    }
-    return 0;
+    return check_sticky(ctx);  // deferred overflow / non-convergence of every asynchronous call since the last sync
 }
 
 const char* dofs3d_last_error(const dofs3d_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
@@ -933,35 +1048,47 @@ int dofs3d_segment_dev(dofs3d_ctx* ctx, const float* d_flow, int already_blurred
     if (rc) return rc;
     if (!d_flow || max_boxes < 0) return DOFS3D_ERR_ARG;
     if (n_pairs == 0) return 0;
+    const dofs3d_outputs o = legacy_outputs(d_labels_out, d_boxes_out, d_n_boxes_out, max_boxes, d_stats_out);
+    OutSpec spec;
+    if ((rc = check_outputs(ctx, &o, &spec))) return rc;
     timer_begin(ctx);
-    rc = segment_dev(ctx, d_flow, already_blurred, n_pairs);
+    rc = segment_dev(ctx, d_flow, already_blurred, n_pairs, spec);
     if (rc) return rc;
-    rc = export_results(ctx, n_pairs, d_labels_out, d_boxes_out, d_n_boxes_out, max_boxes, d_stats_out,
-                        cudaMemcpyDeviceToDevice);
+    rc = export_results(ctx, n_pairs, o, cudaMemcpyDeviceToDevice);
     CK(cudaGetLastError());
-    ctx->pending_pairs = n_pairs;
-    ctx->pending_max_boxes = d_boxes_out ? max_boxes : -1;
     return rc;
+}
+
+int dofs3d_segment_ex(dofs3d_ctx* ctx, const float* flow, int already_blurred, int n_pairs, const dofs3d_outputs* out) {
+    int rc = check_batch(ctx, n_pairs);
+    if (rc) return rc;
+    OutSpec spec;
+    if (!flow) return DOFS3D_ERR_ARG;
+    if ((rc = check_outputs(ctx, out, &spec))) return rc;
+    if (n_pairs == 0) return 0;
+    const size_t px = (size_t)ctx->N * n_pairs;
+    CK(cudaMemcpyAsync(ctx->flow_in, flow, px * sizeof(float2), cudaMemcpyHostToDevice, ctx->stream));
+    timer_begin(ctx);
+    rc = segment_dev(ctx, reinterpret_cast<const float*>(ctx->flow_in), already_blurred, n_pairs, spec);
+    if (rc) return rc;
+    if ((rc = export_results(ctx, n_pairs, *out, cudaMemcpyDeviceToHost))) return rc;
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaGetLastError());
+    return check_sticky(ctx);
 }
 
 int dofs3d_segment(dofs3d_ctx* ctx, const float* flow, int already_blurred, int n_pairs, int32_t* labels_out,
                    dofs3d_box* boxes_out, int32_t* n_boxes_out, int max_boxes, dofs3d_stats* stats_out,
                    float* flow_blurred_out) {
-    int rc = check_batch(ctx, n_pairs);
-    if (rc) return rc;
-    if (!flow || max_boxes < 0) return DOFS3D_ERR_ARG;
-    if (n_pairs == 0) return 0;
-    const size_t px = (size_t)ctx->N * n_pairs;
-    CK(cudaMemcpyAsync(ctx->flow_in, flow, px * sizeof(float2), cudaMemcpyHostToDevice, ctx->stream));
-    timer_begin(ctx);
-    rc = segment_dev(ctx, reinterpret_cast<const float*>(ctx->flow_in), already_blurred, n_pairs);
-    if (rc) return rc;
-    rc = export_results(ctx, n_pairs, labels_out, boxes_out, n_boxes_out, max_boxes, stats_out, cudaMemcpyDeviceToHost);
-    if (flow_blurred_out)
-        CK(cudaMemcpyAsync(flow_blurred_out, ctx->flow_blur, px * sizeof(float2), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    CK(cudaGetLastError());
-    return check_last_call(ctx, n_pairs, boxes_out ? max_boxes : -1);
+    if (!ctx || max_boxes < 0) return DOFS3D_ERR_ARG;
+    const dofs3d_outputs o = legacy_outputs(labels_out, boxes_out, n_boxes_out, max_boxes, stats_out);
+    int rc = dofs3d_segment_ex(ctx, flow, already_blurred, n_pairs, &o);
+    if (flow_blurred_out && n_pairs > 0 && (rc == 0 || rc == DOFS3D_ERR_OVERFLOW)) {
+        CK(cudaMemcpyAsync(flow_blurred_out, ctx->flow_blur, (size_t)ctx->N * n_pairs * sizeof(float2), cudaMemcpyDeviceToHost,
+                           ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    return rc;
 }
 
 // ------------------------------------------------------------------------------------- paint
@@ -978,8 +1105,12 @@ int dofs3d_paint(dofs3d_ctx* ctx, int n_pairs, double min_score, int32_t* painte
         d_bgr = ctx->bgr;
         CK(cudaMemcpyAsync(d_bgr, bgr_inout, px * 3, cudaMemcpyHostToDevice, ctx->stream));
     }
-    LAUNCH(ctx, k_paint<dofs3d_box>, grid1(ctx->N, SEG_THREADS, n_pairs), SEG_THREADS, 0, ctx->labels, ctx->boxes, ctx->box_cap,
-           ctx->N, min_score, d_painted, d_bgr);
+    if (ctx->labels_fmt == DOFS3D_LABELS_I32)
+        LAUNCH(ctx, (k_paint<dofs3d_box, int>), grid1(ctx->N, SEG_THREADS, n_pairs), SEG_THREADS, 0, ctx->labels, ctx->boxes,
+               ctx->box_cap, ctx->N, min_score, d_painted, d_bgr);
+    else
+        LAUNCH(ctx, (k_paint<dofs3d_box, u16>), grid1(ctx->N, SEG_THREADS, n_pairs), SEG_THREADS, 0,
+               reinterpret_cast<const u16*>(ctx->labels), ctx->boxes, ctx->box_cap, ctx->N, min_score, d_painted, d_bgr);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(painted_out, d_painted, px * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
     if (bgr_inout) CK(cudaMemcpyAsync(bgr_inout, d_bgr, px * 3, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1053,51 +1184,222 @@ long long dofs3d_edges_sorted(dofs3d_ctx* ctx, const float* flow_blurred, int32_
 }
 
 // ------------------------------------------------------------------------------------- whole path
-int dofs3d_process_dev(dofs3d_ctx* ctx, const uint8_t* d_bgr_frames, int n_frames, int32_t* d_labels_out,
-                       dofs3d_box* d_boxes_out, int32_t* d_n_boxes_out, int max_boxes, dofs3d_stats* d_stats_out) {
+static int process_frames_dev(dofs3d_ctx* ctx, const u8* d_bgr, int n_frames, const OutSpec& spec) {
+    const int n = n_frames - 1;
+    const size_t N = ctx->N;
+    LAUNCH(ctx, k_bgr2gray, grid1(N * n_frames / 4 + 1, 256, 1), 256, 0, d_bgr, ctx->gray, N * n_frames);
+    mark(ctx, "gray");
+    int rc = flow_dev(ctx, ctx->gray, ctx->gray + N, n, ctx->flow_raw);  // pair i = frames (i, i+1)
+    if (rc) return rc;
+    return segment_dev(ctx, reinterpret_cast<const float*>(ctx->flow_raw), 0, n, spec);
+}
+
+int dofs3d_process_ex_dev(dofs3d_ctx* ctx, const uint8_t* d_bgr_frames, int n_frames, const dofs3d_outputs* d_out) {
     if (!ctx || !d_bgr_frames || n_frames < 1) return DOFS3D_ERR_ARG;
     const int n = n_frames - 1;
     int rc = check_batch(ctx, n);
     if (rc) return rc;
+    OutSpec spec;
+    if ((rc = check_outputs(ctx, d_out, &spec))) return rc;
     if (n == 0) return 0;
     if ((rc = ensure_flow(ctx))) return rc;
+    ctx->have_carry = false;
     timer_begin(ctx);
-    const size_t N = ctx->N;
-    LAUNCH(ctx, k_bgr2gray, grid1(N * n_frames / 4 + 1, 256, 1), 256, 0, d_bgr_frames, ctx->gray, N * n_frames);
-    mark(ctx, "gray");
-    rc = flow_dev(ctx, ctx->gray, ctx->gray + N, n, ctx->flow_raw);  // pair i = frames (i, i+1)
-    if (rc) return rc;
-    rc = segment_dev(ctx, reinterpret_cast<const float*>(ctx->flow_raw), 0, n);
-    if (rc) return rc;
-    rc = export_results(ctx, n, d_labels_out, d_boxes_out, d_n_boxes_out, max_boxes, d_stats_out, cudaMemcpyDeviceToDevice);
+    if ((rc = process_frames_dev(ctx, d_bgr_frames, n_frames, spec))) return rc;
+    rc = export_results(ctx, n, *d_out, cudaMemcpyDeviceToDevice);
     CK(cudaGetLastError());
-    ctx->pending_pairs = n;
-    ctx->pending_max_boxes = d_boxes_out ? max_boxes : -1;
     return rc;
 }
 
-int dofs3d_process(dofs3d_ctx* ctx, const uint8_t* bgr_frames, int n_frames, int32_t* labels_out, dofs3d_box* boxes_out,
-                   int32_t* n_boxes_out, int max_boxes, dofs3d_stats* stats_out) {
+int dofs3d_process_dev(dofs3d_ctx* ctx, const uint8_t* d_bgr_frames, int n_frames, int32_t* d_labels_out,
+                       dofs3d_box* d_boxes_out, int32_t* d_n_boxes_out, int max_boxes, dofs3d_stats* d_stats_out) {
+    if (max_boxes < 0) return DOFS3D_ERR_ARG;
+    const dofs3d_outputs o = legacy_outputs(d_labels_out, d_boxes_out, d_n_boxes_out, max_boxes, d_stats_out);
+    return dofs3d_process_ex_dev(ctx, d_bgr_frames, n_frames, &o);
+}
+
+int dofs3d_process_ex(dofs3d_ctx* ctx, const uint8_t* bgr_frames, int n_frames, const dofs3d_outputs* out) {
     if (!ctx || !bgr_frames || n_frames < 1) return DOFS3D_ERR_ARG;
     const int n = n_frames - 1;
     int rc = check_batch(ctx, n);
     if (rc) return rc;
+    OutSpec spec;
+    if ((rc = check_outputs(ctx, out, &spec))) return rc;
     if (n == 0) return 0;
     if ((rc = ensure_flow(ctx))) return rc;
+    ctx->have_carry = false;
     const size_t N = ctx->N;
     CK(cudaMemcpyAsync(ctx->bgr, bgr_frames, N * 3 * n_frames, cudaMemcpyHostToDevice, ctx->stream));
     timer_begin(ctx);
-    LAUNCH(ctx, k_bgr2gray, grid1(N * n_frames / 4 + 1, 256, 1), 256, 0, ctx->bgr, ctx->gray, N * n_frames);
-    mark(ctx, "gray");
-    rc = flow_dev(ctx, ctx->gray, ctx->gray + N, n, ctx->flow_raw);
-    if (rc) return rc;
-    rc = segment_dev(ctx, reinterpret_cast<const float*>(ctx->flow_raw), 0, n);
-    if (rc) return rc;
-    rc = export_results(ctx, n, labels_out, boxes_out, n_boxes_out, max_boxes, stats_out, cudaMemcpyDeviceToHost);
-    if (rc) return rc;
+    if ((rc = process_frames_dev(ctx, ctx->bgr, n_frames, spec))) return rc;
+    if ((rc = export_results(ctx, n, *out, cudaMemcpyDeviceToHost))) return rc;
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaGetLastError());
-    return check_last_call(ctx, n, boxes_out ? max_boxes : -1);
+    return check_sticky(ctx);
+}
+
+int dofs3d_process(dofs3d_ctx* ctx, const uint8_t* bgr_frames, int n_frames, int32_t* labels_out, dofs3d_box* boxes_out,
+                   int32_t* n_boxes_out, int max_boxes, dofs3d_stats* stats_out) {
+    if (max_boxes < 0) return DOFS3D_ERR_ARG;
+    const dofs3d_outputs o = legacy_outputs(labels_out, boxes_out, n_boxes_out, max_boxes, stats_out);
+    return dofs3d_process_ex(ctx, bgr_frames, n_frames, &o);
+}
+
+// ------------------------------------------------------------------------------------- streaming
+int dofs3d_stream_begin(dofs3d_ctx* ctx) {
+    if (!ctx) return DOFS3D_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    if (!ctx->chunks.empty()) {
+        ctx->err = "dofs3d_stream_begin with chunks outstanding: collect them first";
+        return DOFS3D_ERR_ARG;
+    }
+    ctx->have_carry = false;
+    return 0;
+}
+
+int dofs3d_stream_submit(dofs3d_ctx* ctx, const uint8_t* bgr_frames, int n_frames, const dofs3d_outputs* out) {
+    if (!ctx || !bgr_frames || n_frames < 1) return DOFS3D_ERR_ARG;
+    const int n = ctx->have_carry ? n_frames : n_frames - 1;  // pairs of this chunk
+    int rc = check_batch(ctx, n);
+    if (rc) return rc;
+    OutSpec spec;
+    if ((rc = check_outputs(ctx, out, &spec))) return rc;
+    if (ctx->chunks.size() >= 2) {
+        ctx->err = "two chunks are already outstanding: collect one first";
+        return DOFS3D_ERR_ARG;
+    }
+    if ((rc = ensure_flow(ctx))) return rc;
+    const size_t N = ctx->N;
+    if (!ctx->copy_stream) {
+        CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            CK(cudaMalloc(&ctx->stage[i], (size_t)(ctx->F + 1) * N * 3));
+            ctx->bytes += (long long)(ctx->F + 1) * N * 3;
+            CK(cudaEventCreateWithFlags(&ctx->stage_free[i], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&ctx->stage_ready[i], cudaEventDisableTiming));
+        }
+    }
+    const int b = (int)(ctx->chunks_submitted & 1);
+    // upload on the copy stream, under the kernels of the previous chunk; the buffer is free once the gray conversion
+    // of the chunk that used it last has run
+    if (ctx->chunks_submitted >= 2) CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->stage_free[b], 0));
+    CK(cudaMemcpyAsync(ctx->stage[b], bgr_frames, N * 3 * n_frames, cudaMemcpyHostToDevice, ctx->copy_stream));
+    CK(cudaEventRecord(ctx->stage_ready[b], ctx->copy_stream));
+    CK(cudaStreamWaitEvent(ctx->stream, ctx->stage_ready[b], 0));
+    timer_begin(ctx);
+    // gray slot 0 holds the carried frame; the chunk's frames follow it
+    u8* gray_dst = ctx->gray + (ctx->have_carry ? N : 0);
+    LAUNCH(ctx, k_bgr2gray, grid1(N * n_frames / 4 + 1, 256, 1), 256, 0, ctx->stage[b], gray_dst, N * n_frames);
+    CK(cudaEventRecord(ctx->stage_free[b], ctx->stream));
+    mark(ctx, "gray");
+    ctx->chunks_submitted++;
+    cudaEvent_t done;
+    CK(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
+    if (n > 0) {
+        if ((rc = flow_dev(ctx, ctx->gray, ctx->gray + N, n, ctx->flow_raw, ctx->have_carry, true))) return rc;
+        if ((rc = segment_dev(ctx, reinterpret_cast<const float*>(ctx->flow_raw), 0, n, spec))) return rc;
+        if ((rc = export_results(ctx, n, *out, cudaMemcpyDeviceToHost))) return rc;
+        // the last frame becomes frame 0 of the next chunk
+        CK(cudaMemcpyAsync(ctx->gray, ctx->gray + (size_t)n * N, N, cudaMemcpyDeviceToDevice, ctx->stream));
+        ctx->have_carry = true;
+    } else {
+        // a first chunk of one frame: nothing to pair yet; it is expanded with the next chunk (gray slot 0 already holds it,
+        // but its polynomial expansion does not exist yet, so the next chunk treats it as a fresh frame)
+        ctx->err = "the first chunk of a stream needs at least two frames";
+        cudaEventDestroy(done);
+        return DOFS3D_ERR_ARG;
+    }
+    CK(cudaEventRecord(done, ctx->stream));
+    CK(cudaGetLastError());
+    ctx->chunks.push_back({n, done});
+    return 0;
+}
+
+int dofs3d_stream_collect(dofs3d_ctx* ctx, int* n_pairs_out) {
+    if (!ctx) return DOFS3D_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->chunks.empty()) {
+        ctx->err = "no chunk outstanding";
+        return DOFS3D_ERR_ARG;
+    }
+    const dofs3d_ctx::Chunk c = ctx->chunks.front();
+    ctx->chunks.erase(ctx->chunks.begin());
+    CK(cudaEventSynchronize(c.done));
+    cudaEventDestroy(c.done);
+    if (n_pairs_out) *n_pairs_out = c.n_pairs;
+    // the sticky bits copied after this chunk's kernels are on the host now (a later chunk may add to them; it reports then)
+    const int bits = *ctx->h_sticky;
+    if (bits) {
+        CK(cudaStreamSynchronize(ctx->stream));
+        return check_sticky(ctx);
+    }
+    return 0;
+}
+
+void* dofs3d_pinned_alloc(size_t bytes) {
+    void* p = nullptr;
+    return cudaMallocHost(&p, bytes ? bytes : 1) == cudaSuccess ? p : nullptr;
+}
+void dofs3d_pinned_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
+// ------------------------------------------------------------------------------------- per-node state
+int dofs3d_node_state(dofs3d_ctx* ctx, int pair, int node, int32_t* size_out, float* mean_flow2_out, int32_t* bbox4_out) {
+    if (!ctx || pair < 0 || pair >= ctx->F || node < 0 || node >= ctx->N) return DOFS3D_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    const size_t g = (size_t)pair * ctx->N + node;
+    u8 lvl = 0;
+    CK(cudaMemcpyAsync(&lvl, ctx->bor.lvl + g, 1, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (lvl == 0) {  // never won a merge: the singleton it started as (Forest::Forest, graph.cpp:143-147)
+        float2 f;
+        CK(cudaMemcpyAsync(&f, ctx->flow_blur + g, sizeof f, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        const int x = node % ctx->W, y = node / ctx->W;
+        if (size_out) *size_out = 1;
+        if (mean_flow2_out) mean_flow2_out[0] = f.x, mean_flow2_out[1] = f.y;
+        if (bbox4_out) bbox4_out[0] = x, bbox4_out[1] = y, bbox4_out[2] = x, bbox4_out[3] = y;
+        return 0;
+    }
+    RootState r;
+    CK(cudaMemcpyAsync(&r, ctx->rstate + g, sizeof r, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (size_out) *size_out = r.size;
+    if (mean_flow2_out) mean_flow2_out[0] = r.fx, mean_flow2_out[1] = r.fy;
+    if (bbox4_out) bbox4_out[0] = r.bbox.x, bbox4_out[1] = r.bbox.y, bbox4_out[2] = r.bbox.z, bbox4_out[3] = r.bbox.w;
+    return 0;
+}
+
+int dofs3d_scored_merges(dofs3d_ctx* ctx, int pair, int cap, int32_t* root_out, uint32_t* time_out, double* score_out,
+                         uint8_t* kept_out) {
+    if (!ctx || pair < 0 || pair >= ctx->F || cap < 0) return DOFS3D_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    int n_cand = 0;
+    CK(cudaMemcpyAsync(&n_cand, ctx->counters + CNT_CAND * ctx->F + pair, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    n_cand = std::min(n_cand, ctx->cand_cap);
+    std::vector<Candidate> cand((size_t)n_cand);
+    std::vector<double> score((size_t)n_cand);
+    if (n_cand) {
+        CK(cudaMemcpyAsync(cand.data(), ctx->cand + (size_t)pair * ctx->cand_cap, sizeof(Candidate) * n_cand,
+                           cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(score.data(), ctx->cand_score + (size_t)pair * ctx->cand_cap, sizeof(double) * n_cand,
+                           cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    int m = 0;
+    for (int i = 0; i < n_cand; ++i) {
+        if (score[i] == -1.0) continue;  // no class produced a rectangle (graph.cpp:318-322)
+        if (m < cap) {
+            if (root_out) root_out[m] = (int32_t)cand[i].root;
+            if (time_out) time_out[m] = cand[i].time;
+            if (score_out) score_out[m] = score[i];
+            if (kept_out) kept_out[m] = (cand[i].pad & CAND_KEPT) ? 1 : 0;
+        }
+        ++m;
+    }
+    return m;
 }
 
 // ------------------------------------------------------------------------------------- synthetic video

@@ -4,7 +4,7 @@
 // reference tree and not version-pinned by it (cpp/CMakeLists.txt:14); the arithmetic below restates
 // the published algorithm of OpenCV 4.x modules/video/src/optflowgf.cpp (polynomial expansion,
 // update-matrices, box-filtered 2x2 solve, coarse-to-fine over a Gaussian pyramid) and is checked
-// against cv2 4.13 with an end-point-error tolerance (tests/test_flow.py).
+// against cv2 4.13 with an end-point-error tolerance (tests/test_gpu_parity.py, tests/test_gpu_fullsize.py).
 //
 // Layout in HBM (all row-major, one image after the other):
 //   gray   u8  [image][H][W]
@@ -86,6 +86,8 @@ struct FlowBuffers {
     float* M = nullptr;      // [F][N][5]
     float2* flowA = nullptr; // [F][N]
     float2* flowB = nullptr; // [F][N]
+    float* R_carry = nullptr;            // polynomial expansion of ONE frame at every level (streaming: the last frame of a chunk)
+    size_t carry_off[FLOW_MAX_LEVELS];   // float offset of level k in R_carry
 };
 
 struct FlowLaunchStats {
@@ -160,8 +162,14 @@ inline void flow_poly_coef(int n, double sigma, PolyCoef* pc) {
 }
 
 inline const char* farneback_error(int rc) {
-    return rc == 1 ? "unsupported Farneback parameters" : rc == 2 ? "device allocation failed (flow buffers)" : "flow error";
+    return rc == 1 ? "unsupported Farneback parameters" : rc == 2 ? "device allocation failed (flow buffers)"
+                   : rc == 3 ? "cudaFuncSetAttribute failed (box filter shared memory)" : "flow error";
 }
+
+// Dynamic shared-memory opt-in of the box-filter kernels (above 48 KB).  Function attributes are per device, so every
+// context sets them after cudaSetDevice, when it allocates its flow buffers; the generic kernel gets the size of the
+// largest window the configuration check admits, so contexts with different windows can share a device.
+inline int farneback_set_attributes();
 
 inline int farneback_alloc(FlowBuffers* fb, int W, int H, int F, const FlowConfig& cfg, size_t* bytes) {
     fb->W = W;
@@ -205,8 +213,14 @@ inline int farneback_alloc(FlowBuffers* fb, int W, int H, int F, const FlowConfi
         !alloc((void**)&fb->M, F * N * 5 * sizeof(float)) || !alloc((void**)&fb->flowA, F * N * sizeof(float2)) ||
         !alloc((void**)&fb->flowB, F * N * sizeof(float2)))
         return 2;
+    size_t carry = 0;
+    for (int l = 0; l < fb->n_levels; ++l) {
+        fb->carry_off[l] = carry;
+        carry += (size_t)fb->level[l].w * fb->level[l].h * 5;
+    }
+    if (!alloc((void**)&fb->R_carry, carry * sizeof(float))) return 2;
     if (bytes) *bytes = total;
-    return 0;
+    return farneback_set_attributes();
 }
 
 inline void farneback_free(FlowBuffers* fb) {
@@ -215,6 +229,8 @@ inline void farneback_free(FlowBuffers* fb) {
     cudaFree(fb->M);
     cudaFree(fb->flowA);
     cudaFree(fb->flowB);
+    cudaFree(fb->R_carry);
+    fb->R_carry = nullptr;
     fb->I = fb->R = fb->M = nullptr;
     fb->flowA = fb->flowB = nullptr;
 }
@@ -730,13 +746,22 @@ inline size_t box_solve_smem(int m) {
 }
 inline int box_solve_threads(int m) { return (((BS_COLS + 2 * m) * 5 + 31) / 32) * 32; }
 
+inline int farneback_set_attributes() {
+    if (cudaFuncSetAttribute(k_box_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)box_solve_smem(63 / 2)) != cudaSuccess)
+        return 3;
+    if (cudaFuncSetAttribute(k_box_solve7, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BS7_SMEM) != cudaSuccess) return 3;
+    return 0;
+}
+
 // ---------------------------------------------------------------------------------------------
 // driver: n pairs; images of pair p are gray0 + p*N and gray1 + p*N.  When gray1 == gray0 + N the
 // batch is a video (pair p = frames p, p+1) and every frame is expanded once instead of twice.
+// Streaming (video batches only): carry_in = frame 0 was the last frame of the previous batch and its polynomial
+// expansion is in R_carry (it is not expanded again); carry_out = keep the expansion of the last frame in R_carry.
 // Returns 0, or non-zero after a launch error.
 // ---------------------------------------------------------------------------------------------
 inline int farneback_run(FlowBuffers& fb, const u8* d_gray0, const u8* d_gray1, int n, float2* d_flow_out,
-                         cudaStream_t stream, FlowLaunchStats* st) {
+                         cudaStream_t stream, FlowLaunchStats* st, bool carry_in = false, bool carry_out = false) {
     const size_t N = (size_t)fb.W * fb.H;
     const bool video = d_gray1 == d_gray0 + N;
     ImageSet imgs;
@@ -749,21 +774,22 @@ inline int farneback_run(FlowBuffers& fb, const u8* d_gray0, const u8* d_gray1, 
     ps.first1 = video ? 1 : n;
     const int m = fb.cfg.winsize / 2;
     const size_t bx_smem = box_solve_smem(m);
-    static bool attr_set = false;
-    if (!attr_set) {
-        if (cudaFuncSetAttribute(k_box_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bx_smem) != cudaSuccess)
-            return 3;
-        if (cudaFuncSetAttribute(k_box_solve7, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BS7_SMEM) != cudaSuccess)
-            return 3;
-        attr_set = true;
-    }
+    if ((carry_in || carry_out) && !video) return 3;
+    const int skip = carry_in ? 1 : 0;  // images not expanded here
+    ImageSet fresh = imgs;
+    fresh.base0 = imgs.base0 + (size_t)skip * N;
+    fresh.split -= skip;
+    fresh.count -= skip;
     float2* cur = nullptr;   // flow of the level being refined
     float2* prev = nullptr;  // flow of the coarser level
     int Wp = 0, Hp = 0;
     for (int k = fb.n_levels - 1; k >= 0; --k) {
         const FlowLevel& L = fb.level[k];
         const dim3 blk(256);
-        const dim3 g_img((L.w + 31) / 32, (L.h + 7) / 8, imgs.count);
+        const dim3 g_img((L.w + 31) / 32, (L.h + 7) / 8, fresh.count);
+        const size_t npx = (size_t)L.w * L.h;
+        float* I_fresh = fb.I + (size_t)skip * npx;
+        float* R_fresh = fb.R + (size_t)skip * npx * 5;
         const dim3 g_pair((L.w + 31) / 32, (L.h + 7) / 8, n);
         const dim3 g_box((L.w + BS_COLS - 1) / BS_COLS, (L.h + BS_ROWS - 1) / BS_ROWS, n);
         cur = (k == 0) ? d_flow_out : (prev == fb.flowA ? fb.flowB : fb.flowA);
@@ -773,14 +799,19 @@ inline int farneback_run(FlowBuffers& fb, const u8* d_gray0, const u8* d_gray1, 
         start.Hp = Hp;
         start.mul = 1.0 / fb.cfg.pyr_scale;
         if (L.w == fb.W && L.h == fb.H && L.taps.radius == 1)
-            k_pyr_level0<<<g_img, blk, 0, stream>>>(imgs, fb.I, fb.W, fb.H, L.taps);
+            k_pyr_level0<<<g_img, blk, 0, stream>>>(fresh, I_fresh, fb.W, fb.H, L.taps);
         else
-            k_pyr_level<<<g_img, blk, 0, stream>>>(imgs, fb.I, fb.W, fb.H, L.w, L.h, L.taps);
+            k_pyr_level<<<g_img, blk, 0, stream>>>(fresh, I_fresh, fb.W, fb.H, L.w, L.h, L.taps);
         FLOW_MARK(st, "flow.pyramid");
         if (fb.poly.n == 5)
-            k_polyexp<5><<<g_img, blk, 0, stream>>>(fb.I, fb.R, L.w, L.h, fb.poly);
+            k_polyexp<5><<<g_img, blk, 0, stream>>>(I_fresh, R_fresh, L.w, L.h, fb.poly);
         else
-            k_polyexp<0><<<g_img, blk, 0, stream>>>(fb.I, fb.R, L.w, L.h, fb.poly);
+            k_polyexp<0><<<g_img, blk, 0, stream>>>(I_fresh, R_fresh, L.w, L.h, fb.poly);
+        if (carry_in)
+            cudaMemcpyAsync(fb.R, fb.R_carry + fb.carry_off[k], npx * 5 * sizeof(float), cudaMemcpyDeviceToDevice, stream);
+        if (carry_out)
+            cudaMemcpyAsync(fb.R_carry + fb.carry_off[k], fb.R + (size_t)n * npx * 5, npx * 5 * sizeof(float),
+                            cudaMemcpyDeviceToDevice, stream);
         FLOW_MARK(st, "flow.polyexp");
         k_update_matrices<UM_START><<<g_pair, blk, 0, stream>>>(fb.R, cur, fb.M, L.w, L.h, ps, start);
         FLOW_MARK(st, "flow.update_matrices");

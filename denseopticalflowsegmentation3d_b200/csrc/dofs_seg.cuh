@@ -1640,11 +1640,20 @@ k_replay_gates(ReplayArgs A, int wave) {
 // ---------------------------------------------------------------------------------------------
 // K11 + K12  lifting of the queued merges, per-root first-maximum selection, box records, labels
 // ---------------------------------------------------------------------------------------------
+// Scores are compared through an order-preserving map of the double to u64 (any admissible score, negative ones included,
+// maps above 0, which stands for "no score yet": segment_history starts at -1 and keeps any score above the caller's
+// threshold, graph.cpp:348-352).
+DOFS_D u64 score_key(double s) {
+    const u64 b = (u64)__double_as_longlong(s);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+#define CAND_KEPT 1u  // Candidate::pad bit 0: passed the convexity and score gates (graph.cpp:341-346)
+
 struct SelectArgs {
-    const Candidate* cand;  // [F][cand_cap]
+    Candidate* cand;        // [F][cand_cap]
     const int* n_cand;      // [F]
-    double* cand_score;     // [F][cand_cap]  score if the merge passed every gate, else -1
-    u64* best_score;        // [F][N] bit pattern of the best score per root (0 = none)
+    double* cand_score;     // [F][cand_cap]  get_score of the merge (-1: no rectangle), whatever the later gates say
+    u64* best_score;        // [F][N] score_key of the best kept score per root (0 = none)
     u32* sel_time;          // [F][N] time of the first merge reaching the best score
     int* sel_box;           // [F][N] index of the root's box in the sorted box list
     int* n_scored;          // [F]
@@ -1666,15 +1675,15 @@ k_lift_score(SelectArgs A, SegParams P) {
     const double convexity = xddiv((double)c.size, rect_area);
     LiftSolution sol;
     const double score = lift_get_score(c.fx, c.fy, xmin, ymin, xmax, ymax, P, &sol);
-    double kept = -1.0;
+    bool kept = false;
     if (score != -1.0) {
         const double min_convexity = P.cls_min_convexity[sol.cls];
-        if (!(convexity < min_convexity) && score > P.score_threshold) kept = score;
+        kept = !(convexity < min_convexity) && score > P.score_threshold;
     }
-    A.cand_score[(size_t)frame * A.cand_cap + i] = kept;
-    if (kept > 0.0) {
-        atomicMax((unsigned long long*)&A.best_score[(size_t)frame * A.N + c.root],
-                  (unsigned long long)__double_as_longlong(kept));
+    A.cand_score[(size_t)frame * A.cand_cap + i] = score;
+    A.cand[(size_t)frame * A.cand_cap + i].pad = kept ? CAND_KEPT : 0u;
+    if (kept) {
+        atomicMax((unsigned long long*)&A.best_score[(size_t)frame * A.N + c.root], (unsigned long long)score_key(score));
         atomicAdd(&A.n_scored[frame], 1);
     }
 }
@@ -1686,10 +1695,10 @@ k_select_time(SelectArgs A) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int n = min(A.n_cand[frame], A.cand_cap);
     if (i >= n) return;
-    const double sc = A.cand_score[(size_t)frame * A.cand_cap + i];
-    if (!(sc > 0.0)) return;
     const Candidate c = A.cand[(size_t)frame * A.cand_cap + i];
-    if ((u64)__double_as_longlong(sc) == A.best_score[(size_t)frame * A.N + c.root])
+    if (!(c.pad & CAND_KEPT)) return;
+    const double sc = A.cand_score[(size_t)frame * A.cand_cap + i];
+    if (score_key(sc) == A.best_score[(size_t)frame * A.N + c.root])
         atomicMin(&A.sel_time[(size_t)frame * A.N + c.root], c.time);
 }
 
@@ -1735,11 +1744,11 @@ k_emit_boxes(SelectArgs A, SegParams P, Box* __restrict__ tmp_boxes, int box_cap
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int n = min(A.n_cand[frame], A.cand_cap);
     if (i >= n) return;
-    const double sc = A.cand_score[(size_t)frame * A.cand_cap + i];
-    if (!(sc > 0.0)) return;
     const Candidate c = A.cand[(size_t)frame * A.cand_cap + i];
+    if (!(c.pad & CAND_KEPT)) return;
+    const double sc = A.cand_score[(size_t)frame * A.cand_cap + i];
     const size_t g = (size_t)frame * A.N + c.root;
-    if ((u64)__double_as_longlong(sc) != A.best_score[g] || c.time != A.sel_time[g]) return;
+    if (score_key(sc) != A.best_score[g] || c.time != A.sel_time[g]) return;
     const int slot = atomicAdd(&A.n_boxes[frame], 1);
     if (slot >= box_cap) return;
     LiftSolution sol;
@@ -1799,14 +1808,114 @@ k_box_parents(Box* __restrict__ boxes, const int* __restrict__ n_boxes, int box_
     b->parent_box = first_box_above(loss_time + fo, win + fo, sel_time + fo, sel_box + fo, (u32)b->root, false);
 }
 
+// Label image: the smallest kept snapshot containing each pixel.  T = int32 (-1: none) or u16 (0xFFFF: none; a frame has
+// fewer than 4096 boxes).  When run_count is given, every block also counts the label runs that start in its 256 pixels
+// (a run starts where the label differs from the previous pixel's, in raster order) for the run-length output.
+template <typename T>
+DOFS_D T label_cast(int box) { return (T)box; }  // -1 -> 0xFFFF for u16
+
+template <typename T>
 __global__ void __launch_bounds__(SEG_THREADS)
-k_labels(int* __restrict__ labels, const u32* __restrict__ loss_time, const u32* __restrict__ win,
-         const u32* __restrict__ sel_time, const int* __restrict__ sel_box, int N) {
+k_labels(T* __restrict__ labels, const u32* __restrict__ loss_time, const u32* __restrict__ win,
+         const u32* __restrict__ sel_time, const int* __restrict__ sel_box, int N, int* __restrict__ run_count, int run_blocks) {
+    __shared__ int s_cnt[SEG_THREADS / 32];
     const int frame = blockIdx.y;
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= N) return;
     const size_t fo = (size_t)frame * N;
-    labels[fo + p] = first_box_above(loss_time + fo, win + fo, sel_time + fo, sel_box + fo, (u32)p, true);
+    int lab = -2;
+    if (p < N) {
+        lab = first_box_above(loss_time + fo, win + fo, sel_time + fo, sel_box + fo, (u32)p, true);
+        labels[fo + p] = label_cast<T>(lab);
+    }
+    if (!run_count) return;
+    const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+    int prev = __shfl_up_sync(0xffffffffu, lab, 1);
+    if (lane == 0) prev = (p > 0 && p < N) ? first_box_above(loss_time + fo, win + fo, sel_time + fo, sel_box + fo, (u32)(p - 1), true) : -2;
+    const bool start = p < N && (p == 0 || prev != lab);
+    const unsigned m = __ballot_sync(0xffffffffu, start);
+    if (lane == 0) s_cnt[wrp] = __popc(m);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int w = 0; w < SEG_THREADS / 32; ++w) t += s_cnt[w];
+        run_count[(size_t)frame * run_blocks + blockIdx.x] = t;
+    }
+}
+
+// per frame: exclusive scan of the per-block run counts (in place) and the frame's number of runs
+__global__ void __launch_bounds__(1024)
+k_run_scan(int* __restrict__ run_count, int run_blocks, int* __restrict__ n_runs, int max_runs, int* __restrict__ sticky) {
+    __shared__ int s_w[32];
+    __shared__ int s_carry;
+    const int frame = blockIdx.x;
+    int* c = run_count + (size_t)frame * run_blocks;
+    const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (int base = 0; base < run_blocks; base += 1024) {
+        const int i = base + threadIdx.x;
+        const int v = i < run_blocks ? c[i] : 0;
+        int x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) s_w[wrp] = x;
+        __syncthreads();
+        if (wrp == 0) {
+            int t = s_w[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int y = __shfl_up_sync(0xffffffffu, t, o);
+                if (lane >= o) t += y;
+            }
+            s_w[lane] = t;
+        }
+        __syncthreads();
+        const int carry = s_carry;
+        const int incl = x + (wrp ? s_w[wrp - 1] : 0);
+        if (i < run_blocks) c[i] = carry + incl - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = carry + incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        n_runs[frame] = s_carry;
+        if (s_carry > max_runs) atomicOr(sticky, 8 /* STICKY_RUNS */);
+    }
+}
+
+// run i of a frame = {first pixel, label}; it ends where run i+1 starts (the last one at W*H).  Runs are in raster order.
+template <typename T, typename Run>
+__global__ void __launch_bounds__(SEG_THREADS)
+k_run_write(const T* __restrict__ labels, const int* __restrict__ run_base, int run_blocks, Run* __restrict__ runs, int max_runs,
+            int N) {
+    __shared__ int s_cnt[SEG_THREADS / 32];
+    const int frame = blockIdx.y;
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t fo = (size_t)frame * N;
+    const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+    T lab = 0, prev = 0;
+    if (p < N) {
+        lab = labels[fo + p];
+        if (p > 0) prev = labels[fo + p - 1];
+    }
+    const bool start = p < N && (p == 0 || prev != lab);
+    const unsigned m = __ballot_sync(0xffffffffu, start);
+    if (lane == 0) s_cnt[wrp] = __popc(m);
+    __syncthreads();
+    int before = 0;
+    for (int w = 0; w < wrp; ++w) before += s_cnt[w];
+    if (start) {
+        const int pos = run_base[(size_t)frame * run_blocks + blockIdx.x] + before + __popc(m & ((1u << lane) - 1u));
+        if (pos < max_runs) {
+            Run r;
+            r.start = (u32)p;
+            r.label = sizeof(T) == 2 ? (lab == (T)0xFFFF ? -1 : (int)lab) : (int)lab;
+            runs[(size_t)frame * max_runs + pos] = r;
+        }
+    }
 }
 
 // dofs3d_lift: get_bottom_variants for n independent problems
@@ -1836,13 +1945,18 @@ k_lift_problems(const float2* __restrict__ dir, const int4* __restrict__ bbox, c
     if (!s.has_rect) out[i].cls = c;
 }
 
+#define STICKY_INTERNAL 1    // Boruvka did not converge (non-finite flow) or a sort look-back timed out
+#define STICKY_CANDIDATES 2  // candidate queue overflow
+#define STICKY_BOXES 4       // more boxes than the caller's max_boxes / the box list
+#define STICKY_RUNS 8        // more label runs than the caller's max_runs
+
 // per-frame work counters -> the public stats record (include/dofs3d.h), on the device so that the
 // whole call stays asynchronous
 template <typename StatsT>
 __global__ void k_stats(StatsT* __restrict__ out, BorState S, const int* __restrict__ n_cand, const int* __restrict__ n_scored,
                         const int* __restrict__ n_boxes, const int* __restrict__ longest_chain, int n_frames, int N,
                         int n_edges, int max_levels, const int* __restrict__ need_full, const int* __restrict__ replay_redone,
-                        const int* __restrict__ sweep_timeout) {
+                        const int* __restrict__ sweep_timeout, int* __restrict__ sticky, int cand_cap, int box_cap, int max_boxes) {
     const int f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= n_frames) return;
     const int levels = S.levels[f];
@@ -1859,20 +1973,28 @@ __global__ void k_stats(StatsT* __restrict__ out, BorState S, const int* __restr
     st.sort_fallback = *need_full;
     st.replay_exact_chunks = *replay_redone;
     out[f] = st;
+    // deferred failures of asynchronous calls accumulate here until dofs3d_sync reports them (several calls may be
+    // enqueued before one sync)
+    int bad = 0;
+    if (st.final_root < 0) bad |= STICKY_INTERNAL;
+    if (st.n_candidates > cand_cap) bad |= STICKY_CANDIDATES;
+    if (st.n_boxes > box_cap || (max_boxes >= 0 && st.n_boxes > max_boxes)) bad |= STICKY_BOXES;
+    if (bad) atomicOr(sticky, bad);
 }
 
 // What the reference's display loop leaves in every pixel (draw.cpp:120-147): segments are painted in ascending root
 // order when score > min_score, later ones over earlier ones — i.e. the containing box with the largest index wins.
 // painted[p] = that box index or -1; bgr (optional) = the class colour draw.cpp uses (cls 0/2 (0,255,255), cls 1 (0,255,0)).
-template <typename Box>
+template <typename Box, typename T>
 __global__ void __launch_bounds__(SEG_THREADS)
-k_paint(const int* __restrict__ labels, const Box* __restrict__ boxes, int box_cap, int N, double min_score,
+k_paint(const T* __restrict__ labels, const Box* __restrict__ boxes, int box_cap, int N, double min_score,
         int* __restrict__ painted, u8* __restrict__ bgr) {
     const int frame = blockIdx.y;
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= N) return;
     const Box* bx = boxes + (size_t)frame * box_cap;
-    int b = labels[(size_t)frame * N + p], best = -1;
+    const T raw = labels[(size_t)frame * N + p];
+    int b = sizeof(T) == 2 ? (raw == (T)0xFFFF ? -1 : (int)raw) : (int)raw, best = -1;
     while (b >= 0) {
         if (bx[b].score > min_score && b > best) best = b;
         b = bx[b].parent_box;

@@ -82,9 +82,12 @@ public:
     std::vector<SegmentData> get_best_segments();
     // Only the kept entries, as (root id, data) in ascending root order — what callers iterate for.
     std::vector<std::pair<int, SegmentData>> get_best_segments_sparse() const;
-    // Bounding box {(xmin,ymin),(xmax,ymax)} of a kept root's best snapshot (graph.cpp:446-452).
+    // bboxes[node_id] of the finished forest (graph.cpp:446-452): Forest::merge clears the box of every absorbed root
+    // (graph.cpp:207), so this is the whole frame for the final root and empty for every other node.
     std::vector<cv::Point2i> get_bounding_box(int node_id) const;
-    // Score of a kept root's best snapshot, -1 otherwise.
+    // segment_scores[node_id] (graph.cpp:386-389): the score of the node's LATEST merge whose get_score produced a
+    // rectangle, written before the convexity and threshold gates (graph.cpp:326); 0.0 if it never had one.
+    // (Forests returned by process_video carry no per-merge scores: 0.0.)
     double get_segment_best_score(int node_id) const;
     // merge / new_merge (graph.cpp:170-218, 272-384) are not callable one at a time: the loop runs on the device.
     int merge(int a, int b);

@@ -21,8 +21,13 @@ Forest get_segmented_array(const cv::Mat& flow, const cv::Mat& bev, const cv::Ma
 // (segment.cpp:97-101): two CV_8UC3 frames in, CV_32FC2 flow out.
 cv::Mat dense_flow(const cv::Mat& frame1_bgr, const cv::Mat& frame2_bgr);
 
-// Whole path for a video (main1, segment.cpp:209-269): frames[i], frames[i+1] -> one Forest per pair, one batch on the device.
+// Whole path for a video (main1, segment.cpp:209-269): frames[i], frames[i+1] -> one Forest per pair.  The clip is streamed
+// through the device in chunks of at most chunk_pairs pairs (dofs3d_stream_*): the boundary frame of a chunk stays on the
+// device (prev_frame, segment.cpp:268), uploads overlap the kernels of the previous chunk, memory is bounded by the chunk.
 std::vector<Forest> process_video(const std::vector<cv::Mat>& frames_bgr, const cv::Matx33f& persp_mat,
                                   const cv::Matx33f& inv_mat, const std::vector<cv::Matx33f>& inv_mat_upper,
-                                  int neighbor = 8);
+                                  int neighbor = 8, int chunk_pairs = 32);
+
+// GPU the shim's contexts are created on (default: environment variable DOFS3D_DEVICE, else 0).
+void set_device(int device);
 #endif

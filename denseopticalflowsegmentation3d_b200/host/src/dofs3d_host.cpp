@@ -7,9 +7,11 @@
 // score -1).  Device failures have no sentinel in that vocabulary, so they throw std::runtime_error.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <stdexcept>
 #include <string>
@@ -25,17 +27,26 @@ bool debug = false;
 namespace {
 
 struct CtxKey {
-    int w, h, n, neighbors;
+    int w, h, n, neighbors, device;
     float mats[45];
     bool operator<(const CtxKey& o) const {
-        if (std::tie(w, h, n, neighbors) != std::tie(o.w, o.h, o.n, o.neighbors))
-            return std::tie(w, h, n, neighbors) < std::tie(o.w, o.h, o.n, o.neighbors);
+        if (std::tie(w, h, n, neighbors, device) != std::tie(o.w, o.h, o.n, o.neighbors, o.device))
+            return std::tie(w, h, n, neighbors, device) < std::tie(o.w, o.h, o.n, o.neighbors, o.device);
         return std::memcmp(mats, o.mats, sizeof mats) < 0;
     }
 };
 
+// Contexts are reused across calls (allocation is the expensive part).  A context serves one call at a time: every
+// shim function holds the entry's mutex for its whole duration, so concurrent callers with the same key queue up
+// instead of racing on one stream and one set of buffers (the reference functions are re-entrant).
+struct CtxEntry {
+    dofs3d_ctx* c = nullptr;
+    std::mutex mu;
+};
+
 std::mutex g_mu;
-std::map<CtxKey, dofs3d_ctx*> g_ctx;  // contexts are reused across calls (allocation is the expensive part)
+std::map<CtxKey, std::unique_ptr<CtxEntry>> g_ctx;
+int g_device = -1;  // -1: DOFS3D_DEVICE from the environment, else 0
 
 [[noreturn]] void fail(dofs3d_ctx* c, int rc, const char* what) {
     throw std::runtime_error(std::string(what) + ": dofs3d status " + std::to_string(rc) + " (" +
@@ -48,7 +59,13 @@ void fill_mats(dofs3d_params& p, const cv::Matx33f& persp, const cv::Matx33f& in
     for (size_t c = 0; c < 3 && c < up.size(); ++c) std::memcpy(p.inv_upper[c], up[c].val, sizeof p.inv_upper[c]);
 }
 
-dofs3d_ctx* context_for(int w, int h, int n, const dofs3d_params& p) {
+int device_index() {
+    if (g_device >= 0) return g_device;
+    const char* e = std::getenv("DOFS3D_DEVICE");
+    return e ? std::atoi(e) : 0;
+}
+
+CtxEntry* context_for(int w, int h, int n, const dofs3d_params& p) {
     CtxKey k;
     k.w = w;
     k.h = h;
@@ -57,18 +74,22 @@ dofs3d_ctx* context_for(int w, int h, int n, const dofs3d_params& p) {
     std::memcpy(k.mats, p.persp, sizeof p.persp);
     std::memcpy(k.mats + 9, p.inv, sizeof p.inv);
     std::memcpy(k.mats + 18, p.inv_upper, sizeof p.inv_upper);
+    k.device = device_index();
     std::lock_guard<std::mutex> lock(g_mu);
     auto it = g_ctx.find(k);
-    if (it != g_ctx.end()) return it->second;
+    if (it != g_ctx.end()) return it->second.get();
     dofs3d_ctx* c = nullptr;
-    int rc = dofs3d_create(&c, 0, w, h, n, &p);
+    int rc = dofs3d_create(&c, k.device, w, h, n, &p);
     if (rc != 0) {
         std::string msg = c ? dofs3d_last_error(c) : "no CUDA device";
         if (c) dofs3d_destroy(c);
         throw std::runtime_error("dofs3d_create failed (" + msg + "); there is no CPU fallback");
     }
-    g_ctx[k] = c;
-    return c;
+    auto e = std::make_unique<CtxEntry>();
+    e->c = c;
+    CtxEntry* out = e.get();
+    g_ctx[k] = std::move(e);
+    return out;
 }
 
 std::vector<cv::Point2f> points4(const float* p) {
@@ -99,6 +120,22 @@ struct Forest::Result {
     std::vector<dofs3d_box> boxes;
     std::vector<int32_t> labels;
     dofs3d_stats stats;
+    // segment_scores of the reference (graph.cpp:326): the score of the LATEST merge of every root whose get_score
+    // was not -1, whatever the convexity / threshold gates said afterwards
+    std::map<int, std::pair<uint32_t, double>> last_score;
+    void fetch_scores(dofs3d_ctx* c, int pair_index) {
+        int n = dofs3d_scored_merges(c, pair_index, 0, nullptr, nullptr, nullptr, nullptr);
+        if (n < 0) fail(c, n, "Forest (scored merges)");
+        std::vector<int32_t> root((size_t)n);
+        std::vector<uint32_t> time((size_t)n);
+        std::vector<double> score((size_t)n);
+        if (n) n = dofs3d_scored_merges(c, pair_index, n, root.data(), time.data(), score.data(), nullptr);
+        if (n < 0) fail(c, n, "Forest (scored merges)");
+        for (int i = 0; i < n; ++i) {
+            auto it = last_score.find(root[i]);
+            if (it == last_score.end() || it->second.first < time[i]) last_score[root[i]] = {time[i], score[i]};
+        }
+    }
     // pixel sets, built on first use
     std::vector<std::set<int>> sets;
     bool sets_built = false;
@@ -127,7 +164,9 @@ std::vector<Edge> build_graph(const cv::Mat& img, int width, int height, const D
     dofs3d_params p;
     dofs3d_default_params(&p);
     p.neighbors = neighborhood_8 ? 8 : 4;
-    dofs3d_ctx* c = context_for(width, height, 1, p);
+    CtxEntry* ent = context_for(width, height, 1, p);
+    std::lock_guard<std::mutex> call(ent->mu);
+    dofs3d_ctx* c = ent->c;
     const size_t slots = 4 * (size_t)width * height;
     std::vector<int32_t> s(slots), e(slots);
     std::vector<uint64_t> w(slots);
@@ -162,7 +201,9 @@ static Forest run_segment(const cv::Mat& flow, int already_blurred, const cv::Ma
     p.neighbors = neighbors;
     fill_mats(p, persp_mat, inv_mat, inv_mat_upper);
     const int W = flow.cols, H = flow.rows;
-    dofs3d_ctx* c = context_for(W, H, 1, p);
+    CtxEntry* ent = context_for(W, H, 1, p);
+    std::lock_guard<std::mutex> call(ent->mu);
+    dofs3d_ctx* c = ent->c;
     auto res = std::make_shared<Forest::Result>();
     const int cap = 4096;
     res->boxes.resize(cap);
@@ -174,6 +215,7 @@ static Forest run_segment(const cv::Mat& flow, int already_blurred, const cv::Ma
     res->n_boxes = nb;
     res->boxes.resize(nb);
     res->final_root = res->stats.final_root;
+    res->fetch_scores(c, 0);
     Forest f;
     f.num_sets = W * H - res->stats.n_merges;
     f.width = W;
@@ -193,6 +235,17 @@ Forest segment_graph(const cv::Mat& flow, const std::vector<Edge>& graph_edges, 
     const long long e8 = 4 * W * H - 3 * W - 3 * H + 2, e4 = 2 * W * H - W - H;
     const long long n = (long long)graph_edges.size();
     if (n != e8 && n != e4) throw std::invalid_argument("segment_graph: graph_edges was not built from this flow field");
+    // the device rebuilds the list from `flow`: a list that was re-weighted or re-ordered by the caller would be silently
+    // ignored, so a few entries are checked against the reference's weight function (segment.cpp:20-32) and order
+    check_flow(flow, "segment_graph");
+    const long long probes[5] = {0, n / 4, n / 2, (3 * n) / 4, n - 1};
+    for (long long i : probes) {
+        const Edge& ed = graph_edges[(size_t)i];
+        if (ed.start < 0 || ed.start >= W * H || ed.end < 0 || ed.end >= W * H ||
+            !(diff(flow, ed.start % (int)W, ed.start / (int)W, ed.end % (int)W, ed.end / (int)W) == ed.weight) ||
+            (i > 0 && graph_edges[(size_t)i - 1].weight > ed.weight))
+            throw std::invalid_argument("segment_graph: graph_edges is not build_graph(flow) (weights or order differ)");
+    }
     return run_segment(flow, 1, bev, persp_mat, inv_mat, inv_mat_upper, n == e8 ? 8 : 4, nullptr);
 }
 
@@ -232,19 +285,23 @@ std::vector<SegmentData> Forest::get_best_segments() {
     return hist;
 }
 
+// graph.cpp:446-452 returns bboxes[node_id], and Forest::merge clears the box of every absorbed root (graph.cpp:207):
+// after the full Kruskal pass only the final root still has one — the whole frame.  Every other node: empty.
+// (The box a segment had at its best snapshot is SegmentData::sol / dofs3d_box::bbox; the state a node had when it was
+// absorbed is dofs3d_node_state.)
 std::vector<cv::Point2i> Forest::get_bounding_box(int node_id) const {
-    if (result)
-        for (const dofs3d_box& b : result->boxes)
-            if (b.root == node_id) return {cv::Point2i(b.bbox[0], b.bbox[1]), cv::Point2i(b.bbox[2], b.bbox[3])};
-    if (result && node_id == result->final_root) return {cv::Point2i(0, 0), cv::Point2i(width - 1, height - 1)};
+    if (!result) return {};
+    if (node_id < 0 || node_id >= width * height) throw std::out_of_range("Forest::get_bounding_box: node id");
+    if (node_id == result->final_root) return {cv::Point2i(0, 0), cv::Point2i(width - 1, height - 1)};
     return {};
 }
 
+// graph.cpp:386-389: segment_scores[node_id] — the score of the node's latest merge that produced a rectangle
+// (graph.cpp:326, written before the convexity and threshold gates), 0.0 if there was none.
 double Forest::get_segment_best_score(int node_id) const {
-    if (result)
-        for (const dofs3d_box& b : result->boxes)
-            if (b.root == node_id) return b.score;
-    return -1.0;
+    if (!result) return 0.0;
+    auto it = result->last_score.find(node_id);
+    return it == result->last_score.end() ? 0.0 : it->second.second;
 }
 
 int Forest::merge(int, int) { throw std::logic_error("Forest::merge: the merge loop runs on the device as a whole (segment_graph)"); }
@@ -263,7 +320,9 @@ std::vector<Solution> get_bottom_variants_batch(const std::vector<cv::Point2f>& 
     dofs3d_params p;
     dofs3d_default_params(&p);
     fill_mats(p, mat, inv_mat, inv_matrix_upper);
-    dofs3d_ctx* c = context_for(64, 64, 1, p);
+    CtxEntry* ent = context_for(64, 64, 1, p);
+    std::lock_guard<std::mutex> call(ent->mu);
+    dofs3d_ctx* c = ent->c;
     std::vector<float> d(2 * n);
     std::vector<int32_t> b(4 * n), k(n);
     for (size_t i = 0; i < n; ++i) {
@@ -349,7 +408,9 @@ cv::Mat dense_flow(const cv::Mat& f1, const cv::Mat& f2) {
     const int W = f1.cols, H = f1.rows;
     dofs3d_params p;
     dofs3d_default_params(&p);
-    dofs3d_ctx* c = context_for(W, H, 1, p);
+    CtxEntry* ent = context_for(W, H, 1, p);
+    std::lock_guard<std::mutex> call(ent->mu);
+    dofs3d_ctx* c = ent->c;
     const size_t N = (size_t)W * H;
     std::vector<uint8_t> bgr(2 * N * 3), gray(2 * N);
     std::memcpy(bgr.data(), f1.ptr<uint8_t>(), N * 3);
@@ -362,46 +423,115 @@ cv::Mat dense_flow(const cv::Mat& f1, const cv::Mat& f2) {
     return flow;
 }
 
+void set_device(int device) { g_device = device; }
+
+// main1 (segment.cpp:174-275) over the streaming entry points: the clip goes through the device in chunks of at most
+// `chunk_pairs` pairs; the last frame of a chunk is carried on the device (prev_frame, segment.cpp:268), the upload of
+// chunk k+1 runs under the kernels of chunk k, and device memory is bounded by the chunk size whatever the clip length.
 std::vector<Forest> process_video(const std::vector<cv::Mat>& frames, const cv::Matx33f& persp_mat, const cv::Matx33f& inv_mat,
-                                  const std::vector<cv::Matx33f>& inv_mat_upper, int neighbor) {
+                                  const std::vector<cv::Matx33f>& inv_mat_upper, int neighbor, int chunk_pairs) {
     std::vector<Forest> out;
     if (frames.size() < 2) return out;
     if (neighbor != 4 && neighbor != 8) neighbor = 4;
     const int W = frames[0].cols, H = frames[0].rows, n = (int)frames.size() - 1;
     const size_t N = (size_t)W * H;
+    const int CH = std::max(1, std::min(chunk_pairs, n));
     dofs3d_params p;
     dofs3d_default_params(&p);
     p.neighbors = neighbor;
     fill_mats(p, persp_mat, inv_mat, inv_mat_upper);
-    dofs3d_ctx* c = context_for(W, H, n, p);
-    std::vector<uint8_t> bgr((size_t)(n + 1) * N * 3);
-    for (int i = 0; i <= n; ++i) {
-        if (frames[i].type() != CV_8UC3 || frames[i].cols != W || frames[i].rows != H)
-            throw std::invalid_argument("process_video: CV_8UC3 frames of equal size expected");
-        std::memcpy(bgr.data() + (size_t)i * N * 3, frames[i].ptr<uint8_t>(), N * 3);
-    }
+    CtxEntry* ent = context_for(W, H, CH, p);
+    std::lock_guard<std::mutex> call(ent->mu);
+    dofs3d_ctx* c = ent->c;
+    for (const cv::Mat& f : frames)
+        if (f.type() != CV_8UC3 || f.cols != W || f.rows != H || !f.isContinuous())
+            throw std::invalid_argument("process_video: continuous CV_8UC3 frames of equal size expected");
     const int cap = 1024;
-    std::vector<int32_t> labels((size_t)n * N), nb(n);
-    std::vector<dofs3d_box> boxes((size_t)n * cap);
-    std::vector<dofs3d_stats> stats(n);
-    int rc = dofs3d_process(c, bgr.data(), n + 1, labels.data(), boxes.data(), nb.data(), cap, stats.data());
-    if (rc != 0) fail(c, rc, "process_video");
-    for (int i = 0; i < n; ++i) {
-        auto res = std::make_shared<Forest::Result>();
-        res->n_boxes = nb[i];
-        res->boxes.assign(boxes.begin() + (size_t)i * cap, boxes.begin() + (size_t)i * cap + nb[i]);
-        res->labels.assign(labels.begin() + (size_t)i * N, labels.begin() + (size_t)(i + 1) * N);
-        res->stats = stats[i];
-        res->final_root = stats[i].final_root;
-        Forest f;
-        f.num_sets = (int)N - stats[i].n_merges;
-        f.width = W;
-        f.height = H;
-        f.persp_mat = persp_mat;
-        f.inv_mat = inv_mat;
-        f.inv_mat_upper = inv_mat_upper;
-        f.result = res;
-        out.push_back(f);
+    struct Slot {  // two chunks are in flight: pinned staging for the frames going in and the results coming out
+        uint8_t* bgr = nullptr;
+        uint16_t* labels = nullptr;
+        dofs3d_box* boxes = nullptr;
+        int32_t* nb = nullptr;
+        dofs3d_stats* stats = nullptr;
+        int first_pair = 0;
+    } slot[2];
+    auto release = [&]() {
+        for (Slot& sl : slot) {
+            dofs3d_pinned_free(sl.bgr);
+            dofs3d_pinned_free(sl.labels);
+            dofs3d_pinned_free(sl.boxes);
+            dofs3d_pinned_free(sl.nb);
+            dofs3d_pinned_free(sl.stats);
+        }
+    };
+    for (Slot& sl : slot) {
+        sl.bgr = static_cast<uint8_t*>(dofs3d_pinned_alloc((size_t)(CH + 1) * N * 3));
+        sl.labels = static_cast<uint16_t*>(dofs3d_pinned_alloc((size_t)CH * N * sizeof(uint16_t)));
+        sl.boxes = static_cast<dofs3d_box*>(dofs3d_pinned_alloc((size_t)CH * cap * sizeof(dofs3d_box)));
+        sl.nb = static_cast<int32_t*>(dofs3d_pinned_alloc((size_t)CH * sizeof(int32_t)));
+        sl.stats = static_cast<dofs3d_stats*>(dofs3d_pinned_alloc((size_t)CH * sizeof(dofs3d_stats)));
+        if (!sl.bgr || !sl.labels || !sl.boxes || !sl.nb || !sl.stats) {
+            release();
+            throw std::runtime_error("process_video: pinned host allocation failed");
+        }
     }
+    auto collect = [&](Slot& sl) {
+        int got = 0;
+        int rc = dofs3d_stream_collect(c, &got);
+        if (rc != 0) {
+            release();
+            fail(c, rc, "process_video");
+        }
+        for (int i = 0; i < got; ++i) {
+            auto res = std::make_shared<Forest::Result>();
+            res->n_boxes = sl.nb[i];
+            res->boxes.assign(sl.boxes + (size_t)i * cap, sl.boxes + (size_t)i * cap + sl.nb[i]);
+            res->labels.resize(N);
+            const uint16_t* lab = sl.labels + (size_t)i * N;
+            for (size_t px = 0; px < N; ++px) res->labels[px] = lab[px] == 0xFFFF ? -1 : (int32_t)lab[px];
+            res->stats = sl.stats[i];
+            res->final_root = sl.stats[i].final_root;
+            Forest f;
+            f.num_sets = (int)N - sl.stats[i].n_merges;
+            f.width = W;
+            f.height = H;
+            f.persp_mat = persp_mat;
+            f.inv_mat = inv_mat;
+            f.inv_mat_upper = inv_mat_upper;
+            f.result = res;
+            out.push_back(f);
+        }
+    };
+    int rc = dofs3d_stream_begin(c);
+    if (rc != 0) {
+        release();
+        fail(c, rc, "process_video");
+    }
+    int next_frame = 0, submitted = 0, collected = 0;
+    while (next_frame <= n) {
+        const bool first = next_frame == 0;
+        const int nf = std::min(first ? CH + 1 : CH, n + 1 - next_frame);
+        if (nf < 1 || (first && nf < 2)) break;
+        Slot& sl = slot[submitted & 1];
+        if (submitted - collected == 2) collect(slot[collected++ & 1]);
+        for (int i = 0; i < nf; ++i) std::memcpy(sl.bgr + (size_t)i * N * 3, frames[next_frame + i].ptr<uint8_t>(), N * 3);
+        dofs3d_outputs o;
+        std::memset(&o, 0, sizeof o);
+        o.label_format = DOFS3D_LABELS_U16;
+        o.labels = sl.labels;
+        o.boxes = sl.boxes;
+        o.n_boxes = sl.nb;
+        o.max_boxes = cap;
+        o.stats = sl.stats;
+        rc = dofs3d_stream_submit(c, sl.bgr, nf, &o);
+        if (rc != 0) {
+            release();
+            fail(c, rc, "process_video");
+        }
+        ++submitted;
+        next_frame += nf;
+    }
+    while (collected < submitted) collect(slot[collected++ & 1]);
+    release();
     return out;
 }

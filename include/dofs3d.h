@@ -16,6 +16,7 @@
 #ifndef DOFS3D_H
 #define DOFS3D_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -162,6 +163,80 @@ long long dofs3d_edges_sorted(dofs3d_ctx* ctx, const float* flow_blurred, int32_
  * segmentation, lifting.  Outputs as dofs3d_segment with n = n_frames - 1. */
 int dofs3d_process(dofs3d_ctx* ctx, const uint8_t* bgr_frames, int n_frames, int32_t* labels_out,
                    dofs3d_box* boxes_out, int32_t* n_boxes_out, int max_boxes, dofs3d_stats* stats_out);
+
+/* ---- compact results ("a compact on-wire result format (labels RLE + boxes)") ------------------
+ * What the reference's consumers take from a frame's segments is which pixels each kept segment covers (draw.cpp:120-147
+ * paints them) and the Solution of each (draw.cpp:85-100 draws its cube).  The int32 label image above carries the pixel
+ * sets at 4 bytes per pixel; the two formats below carry the same information in 2 bytes per pixel or in a few KB. */
+typedef enum {
+    DOFS3D_LABELS_I32 = 0, /* int32 [n][H][W], -1 = no box (the format of dofs3d_segment / dofs3d_process) */
+    DOFS3D_LABELS_U16 = 1, /* uint16 [n][H][W], 0xFFFF = no box (a frame has fewer than 4096 boxes) */
+    DOFS3D_LABELS_RLE = 2  /* dofs3d_run [n][max_runs]: the label image as runs in raster order */
+} dofs3d_label_format;
+
+/* One run of equal labels in raster order: pixels start .. (start of the next run of the frame) - 1, the last run of a
+ * frame ends at W*H - 1.  label = box index or -1.  Every pixel belongs to exactly one run (background runs included). */
+typedef struct {
+    uint32_t start;
+    int32_t label;
+} dofs3d_run;
+
+/* Where the results of one call go; every pointer is optional (NULL to skip).  Host pointers for the host entry points,
+ * device pointers for the _dev ones. */
+typedef struct {
+    int label_format;     /* dofs3d_label_format */
+    void* labels;         /* I32 / U16: the dense image; RLE: dofs3d_run [n][max_runs] */
+    int32_t* n_runs;      /* RLE: [n] number of runs of each frame */
+    int max_runs;         /* RLE: capacity per frame; a frame with more runs fails with DOFS3D_ERR_OVERFLOW */
+    dofs3d_box* boxes;    /* [n][max_boxes] */
+    int32_t* n_boxes;     /* [n] */
+    int max_boxes;
+    dofs3d_stats* stats;  /* [n] */
+} dofs3d_outputs;
+
+/* dofs3d_process / dofs3d_segment with the result formats above. */
+int dofs3d_process_ex(dofs3d_ctx* ctx, const uint8_t* bgr_frames, int n_frames, const dofs3d_outputs* out);
+int dofs3d_process_ex_dev(dofs3d_ctx* ctx, const uint8_t* d_bgr_frames, int n_frames, const dofs3d_outputs* d_out);
+int dofs3d_segment_ex(dofs3d_ctx* ctx, const float* flow, int already_blurred, int n_pairs, const dofs3d_outputs* out);
+
+/* ---- streaming (the video loop of main1, segment.cpp:174-275: prev_frame is the only state carried, :268) ------------
+ * A stream is a sequence of frames pushed in chunks; pair i = frames (i, i+1) of the WHOLE stream, so the first chunk of
+ * n frames yields n-1 pairs and every later chunk of n frames yields n pairs (n <= max_pairs).  The context keeps the
+ * last frame of a chunk on the device — its gray image and its polynomial expansion at every pyramid level — so no frame
+ * is uploaded or expanded twice, and memory does not grow with the length of the clip.
+ *   dofs3d_stream_begin    forgets the carried frame (a new clip starts)
+ *   dofs3d_stream_submit   asynchronous: the chunk is copied to one of two device staging buffers on a copy stream
+ *                          (under the kernels of the previous chunk), its work is enqueued behind that copy and its
+ *                          results are copied to `out` (HOST pointers) behind the work.  The frame buffer and the
+ *                          output buffers must stay valid until the matching collect; pinned memory makes the copies
+ *                          truly asynchronous.  At most two chunks may be outstanding; the first chunk of a stream needs
+ *                          at least two frames.
+ *   dofs3d_stream_collect  waits for the OLDEST outstanding chunk (its outputs are complete then) and reports its
+ *                          deferred errors; *n_pairs_out = number of pairs of that chunk.
+ * Results are bit-identical to one dofs3d_process call over the whole clip. */
+int dofs3d_stream_begin(dofs3d_ctx* ctx);
+int dofs3d_stream_submit(dofs3d_ctx* ctx, const uint8_t* bgr_frames, int n_frames, const dofs3d_outputs* out);
+int dofs3d_stream_collect(dofs3d_ctx* ctx, int* n_pairs_out);
+
+/* Page-locked host memory for the frame and result buffers of the streaming entry points (cudaMallocHost / cudaFreeHost,
+ * so that callers need no CUDA headers); NULL on failure. */
+void* dofs3d_pinned_alloc(size_t bytes);
+void dofs3d_pinned_free(void* p);
+
+/* ---- per-node state of the finished forest (what the Forest accessors of graph.hpp:96,103 are made of) ---------------
+ * For pair `pair` of the LAST segment/process call:
+ *   dofs3d_node_state     the set `node` was the root of at the moment it was absorbed (for the final root: at the end):
+ *                         its size, mean flow (Node::flow_value, graph.cpp:184-190) and bounding box xmin,ymin,xmax,ymax.
+ *                         The reference clears that state when the node is absorbed (graph.cpp:195,207), so
+ *                         Forest::get_bounding_box (graph.cpp:446-452) only ever shows it for the final root.
+ *   dofs3d_scored_merges  every merge whose get_score was not -1 (graph.cpp:318-326), in no particular order: the root,
+ *                         the merge time, the score, and whether it passed the convexity and threshold gates.
+ *                         Forest::get_segment_best_score(node) (graph.cpp:386-389) is the score of the LATEST such merge
+ *                         of that root (0.0 if none).  Returns the number of such merges (may exceed cap; only cap are
+ *                         written) or a negative status. */
+int dofs3d_node_state(dofs3d_ctx* ctx, int pair, int node, int32_t* size_out, float* mean_flow2_out, int32_t* bbox4_out);
+int dofs3d_scored_merges(dofs3d_ctx* ctx, int pair, int cap, int32_t* root_out, uint32_t* time_out, double* score_out,
+                         uint8_t* kept_out);
 
 /* Device-pointer variants (inputs and outputs resident in HBM, asynchronous on dofs3d_stream). */
 int dofs3d_process_dev(dofs3d_ctx* ctx, const uint8_t* d_bgr_frames, int n_frames, int32_t* d_labels_out,

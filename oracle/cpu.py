@@ -70,6 +70,8 @@ class CpuOracle:
         L.ref_result_entry.argtypes = [C.c_void_p, C.c_int, _ip, _dp, _dp, C.POINTER(Solution)]
         L.ref_result_pixels.argtypes = [C.c_void_p, C.c_int, _ip]
         L.ref_result_free.argtypes = [C.c_void_p]
+        if kind == "ref":
+            L.ref_result_nodes.argtypes = [C.c_void_p, _dp, _ip]
         L.ref_set_counting.argtypes = [C.c_int]
         L.ref_get_counts.argtypes = [C.c_char_p, C.c_int]
         if kind == "port":
@@ -115,7 +117,7 @@ class CpuOracle:
                                    start.ctypes.data_as(_ip), end.ctypes.data_as(_ip), weight.ctypes.data_as(_dp))
         return start[:e].copy(), end[:e].copy(), weight[:e].copy()
 
-    def segment(self, flow_blurred, persp, inv, upper, neighbors=8, score_threshold=0.3, min_size=500, trace=False):
+    def segment(self, flow_blurred, persp, inv, upper, neighbors=8, score_threshold=0.3, min_size=500, trace=False, nodes=False):
         """build_graph + segment_graph + get_best_segments on an already blurred flow field
         (segment.cpp:54-63).  Returns dict(entries=[{root, score, move, size, pixels, sol, ...}], ...)."""
         flow = np.ascontiguousarray(flow_blurred, dtype=np.float32)
@@ -149,6 +151,11 @@ class CpuOracle:
                     L.oracle_result_entry_extra(hnd, k, C.byref(t), fl.ctypes.data_as(_fp), bb.ctypes.data_as(_ip))
                     ent.update(time=t.value, flow=fl, bbox=bb)
                 out["entries"].append(ent)
+            if self.kind == "ref" and nodes:
+                # Forest::get_segment_best_score / get_bounding_box of every node of the finished forest
+                sc, bb = np.zeros(h * w, np.float64), np.zeros((h * w, 4), np.int32)
+                L.ref_result_nodes(hnd, sc.ctypes.data_as(_dp), bb.ctypes.data_as(_ip))
+                out["node_score"], out["node_bbox"] = sc, bb
             if self.kind == "port":
                 cnt = (C.c_long * 9)()
                 L.oracle_result_counters(hnd, cnt)

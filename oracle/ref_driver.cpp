@@ -68,7 +68,8 @@ void put_points(const std::vector<cv::Point2f>& v, float* out) {
 struct RefResult {
     std::vector<SegmentData> history;  // Forest::get_best_segments(), all N entries
     std::vector<int> kept;             // indices with score >= 0
-    std::vector<std::vector<cv::Point2i>> bbox;
+    std::vector<double> last_score;    // Forest::get_segment_best_score(node), all N nodes (graph.cpp:386-389)
+    std::vector<int32_t> node_bbox;    // Forest::get_bounding_box(node) as xmin,ymin,xmax,ymax, all N nodes (graph.cpp:446-452)
     double t_build = 0, t_segment = 0;
     long n_edges = 0;
     int num_sets = 0;
@@ -200,7 +201,26 @@ void* ref_segment(const float* flow_blurred, int width, int height, int neighbor
     res->history = forest.get_best_segments();
     for (size_t i = 0; i < res->history.size(); ++i)
         if (res->history[i].score >= 0) res->kept.push_back((int)i);
+    const int n_nodes = width * height;
+    res->last_score.resize(n_nodes);
+    res->node_bbox.resize((size_t)4 * n_nodes);
+    for (int i = 0; i < n_nodes; ++i) {
+        res->last_score[i] = forest.get_segment_best_score(i);
+        const std::vector<cv::Point2i> bb = forest.get_bounding_box(i);  // empty for every absorbed node (graph.cpp:207)
+        const bool has = bb.size() == 2;
+        res->node_bbox[4 * (size_t)i + 0] = has ? bb[0].x : -1;
+        res->node_bbox[4 * (size_t)i + 1] = has ? bb[0].y : -1;
+        res->node_bbox[4 * (size_t)i + 2] = has ? bb[1].x : -1;
+        res->node_bbox[4 * (size_t)i + 3] = has ? bb[1].y : -1;
+    }
     return res;
+}
+
+// the two per-node accessors of the finished forest, for all N nodes: score_out[N], bbox_out[N][4]
+void ref_result_nodes(void* h, double* score_out, int32_t* bbox_out) {
+    auto* r = static_cast<RefResult*>(h);
+    if (score_out) std::memcpy(score_out, r->last_score.data(), r->last_score.size() * sizeof(double));
+    if (bbox_out) std::memcpy(bbox_out, r->node_bbox.data(), r->node_bbox.size() * sizeof(int32_t));
 }
 
 int ref_result_count(void* h) { return (int)static_cast<RefResult*>(h)->kept.size(); }

@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <stdexcept>
 #include <vector>
 
 #include "graph.hpp"
@@ -86,13 +87,33 @@ int main(int argc, char** argv) {
         CHECK(sd.seg.count(root) == 1);  // every root pixel is a member of its own set
         long long h = 0;
         for (int px : sd.seg) h = (h * 1000003LL + px) % 2147483647LL;
-        std::printf("segment root=%d size=%zu hash=%lld cls=%d score=%.17g move=%.17g orient=%.17g\n", root, sd.seg.size(), h,
-                    sd.sol.cls, sd.score, sd.move, sd.sol.orient);
-        auto bb = forest.get_bounding_box(root);
-        CHECK(bb.size() == 2 && bb[0].x <= bb[1].x && bb[0].y <= bb[1].y);
-        CHECK(forest.get_segment_best_score(root) == sd.score);
+        // segment_scores[root] (graph.cpp:386-389) is the LATEST scored merge of the root, not the kept maximum: it can
+        // be lower than the kept score, never higher; the Python test compares it with the unchanged reference
+        const double last = forest.get_segment_best_score(root);
+        CHECK(last > 0.0 && last <= sd.score);
+        std::printf("segment root=%d size=%zu hash=%lld cls=%d score=%.17g move=%.17g orient=%.17g last=%.17g\n", root,
+                    sd.seg.size(), h, sd.sol.cls, sd.score, sd.move, sd.sol.orient, last);
+        // every absorbed root has lost its box (graph.cpp:207)
+        CHECK(forest.get_bounding_box(root).empty() == (root != forest.find(0)));
     }
     CHECK(forest.find(0) == forest.find(W * H - 1));
+    {
+        auto bb = forest.get_bounding_box(forest.find(0));
+        CHECK(bb.size() == 2 && bb[0].x == 0 && bb[0].y == 0 && bb[1].x == W - 1 && bb[1].y == H - 1);
+        CHECK(forest.get_segment_best_score(0) == 0.0 || forest.get_segment_best_score(0) > 0.0);
+    }
+    // a re-weighted edge list is refused, not silently ignored
+    {
+        std::vector<Edge> tampered = build_graph(flow, W, H, diff, true);
+        tampered[tampered.size() / 2].weight += 1.0;
+        bool threw = false;
+        try {
+            segment_graph(flow, tampered, bev, mats.first, mats.second, upper);
+        } catch (const std::invalid_argument&) {
+            threw = true;
+        }
+        CHECK(threw);
+    }
 
     // build_graph + segment_graph on the (now blurred) flow must give the same forest
     std::vector<Edge> edges = build_graph(flow, W, H, diff, true);

@@ -1,0 +1,233 @@
+"""GPU tests of the round-2 boundary additions, through the C ABI: compact label formats, the streaming driver,
+per-node accessors against the UNCHANGED reference, deferred errors of queued asynchronous calls, several contexts
+with different Farneback windows in one process."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from conftest import random_flow
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dofs():
+    import denseopticalflowsegmentation3d_b200 as d
+    return d
+
+
+def test_label_formats_agree(dofs, golden_synth):
+    """u16 and run-length labels carry exactly the int32 label image."""
+    from denseopticalflowsegmentation3d_b200 import capi
+    fr = golden_synth["bgr"]
+    n, H, W = fr.shape[0] - 1, fr.shape[1], fr.shape[2]
+    with dofs.Context(W, H, max_pairs=n) as c:
+        ref = c.process(fr)
+        u16 = c.process_ex(fr, capi.LABELS_U16)
+        rle = c.process_ex(fr, capi.LABELS_RLE, max_runs=4096)
+        painted_rle, _ = c.paint(n, 0.5)   # the paint kernel reads whichever dense format the last call left
+        again = c.process(fr)
+        painted_i32, _ = c.paint(n, 0.5)
+    assert np.array_equal(ref["labels"], again["labels"])
+    assert np.array_equal(painted_rle, painted_i32)
+    assert u16["labels"].dtype == np.uint16
+    dense = u16["labels"].astype(np.int32)
+    dense[u16["labels"] == 0xFFFF] = -1
+    assert np.array_equal(dense, ref["labels"])
+    assert (ref["labels"] >= 0).any()
+    for i in range(n):
+        assert 0 < rle["n_runs"][i] <= 4096
+        runs = rle["labels"][i, :rle["n_runs"][i]]
+        assert runs["start"][0] == 0 and np.all(np.diff(runs["start"].astype(np.int64)) > 0)
+        assert np.all(runs["label"][1:] != runs["label"][:-1])      # maximal runs
+        assert np.array_equal(capi.runs_to_labels(rle["labels"][i], rle["n_runs"][i], W * H), ref["labels"][i].reshape(-1))
+        assert u16["boxes"][i].tobytes() == ref["boxes"][i].tobytes() == rle["boxes"][i].tobytes()
+    bytes_rle = int(rle["n_runs"].sum()) * 8
+    print("labels per pair: int32 %d B, u16 %d B, run-length %d B" % (W * H * 4, W * H * 2, bytes_rle // n))
+    # too small a run capacity is an overflow, not a truncation
+    with dofs.Context(W, H, max_pairs=n) as c:
+        with pytest.raises(dofs.DofsError) as ei:
+            c.process_ex(fr, capi.LABELS_RLE, max_runs=4)
+        assert ei.value.status == -4
+        ok = c.process_ex(fr, capi.LABELS_RLE, max_runs=4096)   # the context stays usable
+        assert np.array_equal(ok["n_runs"], rle["n_runs"])
+
+
+def test_segment_ex_formats_on_random_fields(dofs):
+    from denseopticalflowsegmentation3d_b200 import capi
+    W, H = 131, 77   # ragged: odd width, label rows not aligned
+    fields = np.stack([random_flow(31 + k, W, H, scale=4.0) for k in range(3)])
+    p = dofs.default_params()
+    p.min_size = 40
+    with dofs.Context(W, H, max_pairs=3, params=p) as c:
+        ref = c.segment(fields, already_blurred=True)
+        rle = c.segment_ex(fields, True, capi.LABELS_RLE, max_runs=W * H)
+    for i in range(3):
+        assert np.array_equal(capi.runs_to_labels(rle["labels"][i], rle["n_runs"][i], W * H), ref["labels"][i].reshape(-1))
+
+
+@pytest.mark.parametrize("chunk", [32, 7])
+def test_stream_equals_one_batch(dofs, chunk):
+    """A 200-frame clip through dofs3d_stream_* in chunks equals one dofs3d_process call over the whole clip bit for bit
+    (VERDICT r01 item 7): the carried frame's gray image and polynomial expansion stand in for re-expanding it."""
+    from denseopticalflowsegmentation3d_b200 import capi, synth
+    W, H, n = 192, 108, 199
+    fr = synth.frames(9, 5, 0, n + 1, W, H)
+    p = dofs.default_params()
+    p.min_size = 120
+    with dofs.Context(W, H, max_pairs=n, params=p) as c:
+        whole = c.process_ex(fr, capi.LABELS_U16)
+    with dofs.Context(W, H, max_pairs=chunk, params=p) as c:
+        c.process_ex(fr[:2], capi.LABELS_RLE, max_runs=8192)   # the flow / run-length buffers exist from here on
+        mem = c.device_bytes
+        st = c.process_stream(fr, label_format=capi.LABELS_U16)
+        st_rle = c.process_stream(fr, label_format=capi.LABELS_RLE, max_runs=8192)
+        assert c.device_bytes - mem == 2 * (chunk + 1) * W * H * 3   # the two staging buffers: nothing grows with the clip
+    assert len(st["boxes"]) == n and st["labels"].shape == whole["labels"].shape
+    assert np.array_equal(st["labels"], whole["labels"])
+    assert np.array_equal(st["n_boxes"], whole["n_boxes"]) and int(whole["n_boxes"].sum()) > 0
+    for a, b in zip(st["boxes"], whole["boxes"]):
+        assert a.tobytes() == b.tobytes()
+    for k in ("n_merges", "n_candidates", "n_scored", "final_root"):
+        assert np.array_equal(st["stats"][k], whole["stats"][k])
+    for i in (0, chunk - 1, chunk, n - 1):
+        dense = capi.runs_to_labels(st_rle["labels"][i], st_rle["n_runs"][i], W * H)
+        want = whole["labels"][i].reshape(-1).astype(np.int32)
+        want[want == 0xFFFF] = -1
+        assert np.array_equal(dense, want)
+
+
+def test_stream_argument_errors(dofs):
+    from denseopticalflowsegmentation3d_b200 import synth
+    W, H = 96, 64
+    fr = synth.frames(3, 2, 0, 6, W, H)
+    with dofs.Context(W, H, max_pairs=2) as c:
+        c.stream_begin()
+        with pytest.raises(dofs.DofsError):
+            c.stream_submit(fr[:1])           # a stream cannot start with a single frame
+        with pytest.raises(dofs.DofsError):
+            c.stream_submit(fr[:4])           # 3 pairs > max_pairs
+        c.stream_submit(fr[:3])
+        c.stream_submit(fr[3:5])
+        with pytest.raises(dofs.DofsError):
+            c.stream_submit(fr[5:6])          # two chunks outstanding
+        assert len(c.stream_collect()["boxes"]) == 2
+        c.stream_submit(fr[5:6])
+        assert len(c.stream_collect()["boxes"]) == 2
+        assert len(c.stream_collect()["boxes"]) == 1
+        with pytest.raises(dofs.DofsError):
+            c.stream_collect()                # nothing outstanding
+
+
+def test_node_accessors_against_unchanged_reference(dofs, ref, golden_pair):
+    """Forest::get_segment_best_score (graph.cpp:386-389) = the score of the root's LATEST scored merge, before the
+    convexity / threshold gates — from dofs3d_scored_merges, against the unchanged reference on the repo's pair."""
+    fb = golden_pair["flow_blurred"]
+    H, W = fb.shape[:2]
+    persp, inv, up = ref.get_mats()
+    res = ref.segment(fb, persp, inv, up, nodes=True)
+    with dofs.Context(W, H) as c:
+        out = c.segment(fb, already_blurred=True)
+        last = c.last_scores(0)
+        merges = c.scored_merges(0)
+        final = c.node_state(0, int(out["stats"][0]["final_root"]))
+    want = {int(i): float(res["node_score"][i]) for i in np.nonzero(res["node_score"])[0]}
+    assert set(last) == set(want) and len(want) > 0
+    for r, s in want.items():
+        assert abs(last[r] - s) <= 1e-5
+    assert merges["kept"].sum() == out["stats"][0]["n_scored"] and len(merges["root"]) >= merges["kept"].sum()
+    # the only box the reference still holds at the end is the final root's (graph.cpp:207 clears the others)
+    has_box = np.nonzero(res["node_bbox"][:, 0] >= 0)[0]
+    assert list(has_box) == [int(out["stats"][0]["final_root"])]
+    assert list(final["bbox"]) == list(res["node_bbox"][has_box[0]]) == [0, 0, W - 1, H - 1] and final["size"] == W * H
+
+
+def test_node_state_against_port_trace(dofs, port):
+    """dofs3d_node_state = the state a root had when it was absorbed = the port's merge trace at the root's last win."""
+    W, H = 96, 64
+    f = random_flow(77, W, H, scale=3.0)
+    persp, inv, up = port.get_mats()
+    res = port.segment(f, persp, inv, up, min_size=30, trace=True)
+    tr = res["trace"]
+    with dofs.Context(W, H) as c:
+        c.segment(f, already_blurred=True)
+        last_win = {}
+        for k in range(len(tr["winner"])):
+            last_win[int(tr["winner"][k])] = k
+        rng = np.random.default_rng(0)
+        for node in rng.choice(sorted(last_win), size=40, replace=False).tolist():
+            k = last_win[node]
+            st = c.node_state(0, node)
+            assert st["size"] == tr["size"][k] and list(st["bbox"]) == list(tr["bbox"][k])
+            assert np.array_equal(st["mean_flow"].view(np.uint32), tr["flow"][k].view(np.uint32))
+        never = [p for p in range(W * H) if p not in last_win][:10]
+        for node in never:
+            st = c.node_state(0, node)
+            assert st["size"] == 1 and list(st["bbox"]) == [node % W, node // W, node % W, node // W]
+
+
+def test_queued_async_calls_report_any_failure(dofs):
+    """Several *_dev calls before one dofs3d_sync: a failure of an EARLIER call is still reported (the
+    context used to remember the last call only)."""
+    import torch
+    W, H = 64, 48
+    bad = random_flow(5, W, H)
+    bad[10:14, 20:24] = np.nan
+    good = random_flow(6, W, H)
+    with dofs.Context(W, H) as c:
+        d_bad, d_good = torch.from_numpy(bad).cuda(), torch.from_numpy(good).cuda()
+        stats = torch.zeros(40, dtype=torch.uint8, device="cuda")
+        c.segment_dev(d_bad.data_ptr(), True, 1, d_stats=stats.data_ptr())
+        c.segment_dev(d_good.data_ptr(), True, 1, d_stats=stats.data_ptr())
+        with pytest.raises(dofs.DofsError) as ei:
+            c.sync()
+        assert ei.value.status == -5
+        c.segment_dev(d_good.data_ptr(), True, 1, d_stats=stats.data_ptr())
+        c.sync()   # reported once, then clear
+    # max_boxes too small for an earlier call of the queue
+    fields = random_flow(11, 160, 96, scale=4.0)
+    p = dofs.default_params()
+    p.min_size = 60
+    with dofs.Context(160, 96, params=p) as c:
+        d = torch.from_numpy(fields).cuda()
+        boxes = torch.zeros(216, dtype=torch.uint8, device="cuda")
+        nb = torch.zeros(1, dtype=torch.int32, device="cuda")
+        c.segment_dev(d.data_ptr(), True, 1, d_boxes=boxes.data_ptr(), d_n_boxes=nb.data_ptr(), max_boxes=1)
+        c.segment_dev(d.data_ptr(), True, 1)
+        if int(nb.item()) > 1:
+            with pytest.raises(dofs.DofsError) as ei:
+                c.sync()
+            assert ei.value.status == -4
+        else:
+            c.sync()
+
+
+def test_contexts_with_different_windows_share_a_process(dofs):
+    """the shared-memory opt-in of the box-filter kernels is set per context, not once per process:
+    a later context with a larger Farneback window must work, and so must the first one afterwards."""
+    cv2 = pytest.importorskip("cv2")
+    from denseopticalflowsegmentation3d_b200 import synth
+    W, H = 256, 144
+    fr = synth.frames(5, 4, 0, 2, W, H)
+    g = [cv2.cvtColor(x, cv2.COLOR_BGR2GRAY) for x in fr]
+
+    def ctx(win):
+        p = dofs.default_params()
+        p.winsize = win
+        return dofs.Context(W, H, params=p)
+
+    with ctx(15) as a, ctx(31) as b, ctx(9) as s:
+        for c, win in ((a, 15), (b, 31), (s, 9), (a, 15)):
+            f = c.flow(g[0], g[1])[0]
+            want = cv2.calcOpticalFlowFarneback(g[0], g[1], None, 0.5, 3, win, 3, 5, 1.2, 0)
+            e = np.sqrt(((f.astype(np.float64) - want) ** 2).sum(-1))[16:-16, 16:-16]
+            assert e.max() <= 1e-3, (win, e.max())
+
+
+def test_negative_score_threshold_keeps_reference_semantics(dofs, port):
+    """dofs3d_params.score_threshold < 0 is admissible: segment_history starts at -1 and keeps any score above the
+    threshold (graph.cpp:348-352); the selection no longer uses 0 as its 'no score' value."""
+    from test_gpu_parity import run_and_compare
+    fields = [random_flow(61 + k, 160, 96, scale=4.0) for k in range(2)]
+    assert run_and_compare(dofs, port, fields, min_size=60, score_threshold=-0.5) > 0

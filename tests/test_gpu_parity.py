@@ -453,6 +453,13 @@ def test_cpp_host_shim_matches_oracle(dofs, port, golden_pair, tmp_path):
             h = (h * 1000003 + px) % 2147483647
         assert int(kv["hash"]) == h
         assert abs(float(kv["score"]) - e["score"]) <= TOL_ERR and abs(float(kv["orient"]) - e["sol"]["orient"]) <= TOL_YAW
+    # Forest::get_segment_best_score of the shim against the unchanged reference (its LAST scored merge, graph.cpp:326)
+    from oracle import cpu
+    if cpu.ref_available():
+        node_score = cpu.ref().segment(fb, persp, inv, up, nodes=True)["node_score"]
+        for line in lines:
+            kv = dict(t.split("=") for t in line.split()[1:])
+            assert abs(float(kv["last"]) - node_score[int(kv["root"])]) <= TOL_ERR
 
 
 def test_4k_sixty_objects_against_oracle(dofs, port):

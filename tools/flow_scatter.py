@@ -37,6 +37,15 @@ for W, H, n_obj in ((1920, 1080, 8), (3840, 2160, 60)):
         m[band:-band, band:-band] = False
         row[f"interior_{band}px"] = {"max": float(inner.max()), "mean": float(inner.mean())}
         row[f"border_band_{band}px"] = {"max": float(e[m].max()), "mean": float(e[m].mean())}
+    if W == 1920:  # a second implementation on the same pair: the numpy oracle with OpenCV's running box sums and with direct sums
+        from oracle import farneback_np
+        stable = ~(cv2.dilate((e > 1e-4).astype(np.uint8), np.ones((33, 33), np.uint8)) > 0)
+        for name, sliding in (("oracle_running_sums_vs_cv2", True), ("oracle_direct_sums_vs_cv2", False)):
+            dd = farneback_np.farneback(g0, g1, sliding=sliding).astype(np.float64) - a
+            ee = np.sqrt((dd ** 2).sum(-1))
+            row[name] = {"stable_fraction": float(stable.mean()), "stable_max": float(ee[stable].max()),
+                         "stable_mean": float(ee[stable].mean()), "stable_frac_gt_1e-3": float((ee[stable] > 1e-3).mean()),
+                         "all_max": float(ee.max()), "frac_gt_1e-3": float((ee > 1e-3).mean())}
     out[f"{W}x{H}_{n_obj}obj"] = row
     print(W, H, json.dumps(row))
 json.dump(out, open(os.path.join(ROOT, "profiles", "r02_flow_scatter.json"), "w"), indent=1)
