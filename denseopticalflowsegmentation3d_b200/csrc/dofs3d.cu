@@ -154,6 +154,8 @@ struct dofs3d_ctx {
     dofs3d_run* runs = nullptr;       // [F][runs_cap], allocated on the first run-length call
     int runs_cap = 0;
     dofs3d_stats* stats = nullptr;
+    bool blur_tma = true;             // A/B knob: DOFS3D_BLUR_TMA=0 stages the blur tiles with LDG -> STS instead of bulk copies
+    double* rcp_table = nullptr;      // [RCP_TABLE] 1.0 / n for the replay of small sets
     int* sticky = nullptr;            // device: STICKY_* bits of every call since the last dofs3d_sync
     int* h_sticky = nullptr;          // pinned copy, refreshed after every call
 
@@ -363,7 +365,12 @@ enum { CNT_CAND = 0, CNT_CHAIN = 1, CNT_SCORED = 2, CNT_BOXES = 3, CNT_ROOTS = 4
 void blur_launch(dofs3d_ctx* ctx, const float2* src, float2* dst, int n) {
     const int W = ctx->W, H = ctx->H;
     if (ctx->taps.radius == 12) {
-        LAUNCH(ctx, k_blur_fused<12>, dim3((W + FB_T - 1) / FB_T, (H + FB_T - 1) / FB_T, n), 256, 0, src, dst, W, H, ctx->taps);
+        const dim3 grid((W + FB_T - 1) / FB_T, (H + FB_T - 1) / FB_T, n);
+        // TMA-staged tiles need 16-byte aligned rows of float2: an even width and an aligned base
+        if (ctx->blur_tma && (W & 1) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0)
+            LAUNCH(ctx, k_blur_fused_tma<12>, grid, 256, 0, src, dst, W, H, ctx->taps);
+        else
+            LAUNCH(ctx, k_blur_fused<12>, grid, 256, 0, src, dst, W, H, ctx->taps);
     } else {
         const dim3 gN = grid1(ctx->N, SEG_THREADS, n);
         LAUNCH(ctx, k_blur_rows, gN, SEG_THREADS, 0, src, ctx->flow_tmp, W, H, ctx->taps);
@@ -419,7 +426,7 @@ int segment_dev(dofs3d_ctx* ctx, const float* d_flow, int already_blurred, int n
             LAUNCH(ctx, k_bor_root, gS, SEG_THREADS, 0, B, W, N, level);
         }
         LAUNCH(ctx, k_bor_contract, gS, SEG_THREADS, 0, B, N, level);
-        LAUNCH(ctx, k_bor_relabel, gS, SEG_THREADS, 0, B, N, level);
+        if (level == 0) LAUNCH(ctx, k_bor_relabel, gS, SEG_THREADS, 0, B, N, level);
     }
     LAUNCH(ctx, k_bor_finish, gS, SEG_THREADS, 0, B, N, levels);
     mark(ctx, "boruvka");
@@ -531,6 +538,7 @@ int segment_dev(dofs3d_ctx* ctx, const float* d_flow, int already_blurred, int n
     R.tile_agg = ctx->tile_agg;
     R.tile_carry = ctx->tile_carry;
     R.tiles_cap = ctx->tiles_cap;
+    R.rcp = ctx->rcp_table;
     for (int wave = 1; wave <= levels; ++wave) {
         LAUNCH(ctx, k_replay_short, gS, SEG_THREADS, 0, R, wave);
         LAUNCH(ctx, k_replay_scan, gS, REPLAY_TILE, 0, R, wave);
@@ -875,9 +883,16 @@ int dofs3d_create(dofs3d_ctx** out, int device, int width, int height, int max_p
         if (v >= 1 && v < ctx->max_levels) ctx->max_levels = v;
     }
     if (const char* e = getenv("DOFS3D_FORCE_TIME_FALLBACK")) ctx->force_time_fallback = atoi(e) != 0;
+    if (const char* e = getenv("DOFS3D_BLUR_TMA")) ctx->blur_tma = atoi(e) != 0;
     CK(cudaMallocHost(&ctx->h_sticky, sizeof(int)));
     *ctx->h_sticky = 0;
     DA(ctx->sticky, 1);
+    {
+        std::vector<double> rcp(RCP_TABLE, 0.0);
+        for (int i = 1; i < RCP_TABLE; ++i) rcp[i] = 1.0 / (double)i;
+        DA(ctx->rcp_table, RCP_TABLE);
+        CK(cudaMemcpy(ctx->rcp_table, rcp.data(), sizeof(double) * RCP_TABLE, cudaMemcpyHostToDevice));
+    }
     CK(cudaMemsetAsync(ctx->sticky, 0, sizeof(int), ctx->stream));
     DA(ctx->boxes_tmp, F * ctx->box_cap);
     DA(ctx->boxes, F * ctx->box_cap);
@@ -906,6 +921,7 @@ static int ensure_flow(dofs3d_ctx* ctx) {
         size_t fbytes = 0;
         int rc = farneback_alloc(&ctx->fb, width, height, (int)F, fc, &fbytes);
         ctx->bytes += (long long)fbytes;
+        if (const char* e = getenv("DOFS3D_PYR_UNTILED")) ctx->fb.pyr_untiled = atoi(e) != 0;
         if (rc) {
             ctx->err = farneback_error(rc);
             return rc == 1 ? DOFS3D_ERR_ARG : rc == 3 ? DOFS3D_ERR_CUDA : DOFS3D_ERR_NOMEM;

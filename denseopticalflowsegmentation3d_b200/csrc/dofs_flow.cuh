@@ -86,6 +86,7 @@ struct FlowBuffers {
     float* M = nullptr;      // [F][N][5]
     float2* flowA = nullptr; // [F][N]
     float2* flowB = nullptr; // [F][N]
+    bool pyr_untiled = false;            // test / A-B knob (DOFS3D_PYR_UNTILED=1): the per-thread pyramid kernel
     float* R_carry = nullptr;            // polynomial expansion of ONE frame at every level (streaming: the last frame of a chunk)
     size_t carry_off[FLOW_MAX_LEVELS];   // float offset of level k in R_carry
 };
@@ -332,6 +333,92 @@ k_pyr_level(ImageSet imgs, float* __restrict__ I, int W, int H, int Wk, int Hk, 
         v = fmaf(bot, fy, top * (1.f - fy));
     }
     I[((size_t)img * Hk + y) * Wk + x] = v;
+}
+
+// The same level from a shared-memory tile: the block's source window is staged once as floats (reflected borders
+// resolved while loading), row-filtered at the two source columns every output needs, then column-filtered and
+// interpolated.  The fmaf chains are those of k_pyr_level in the same order, so the result is bit-identical to it; what
+// changes is that a source byte is loaded and converted once per block instead of once per tap per thread (the coarse
+// levels were bound by byte loads and conversions: 18 x 18 of them per output at the coarsest level).
+// Dynamic shared memory: tile [TH][TW] floats, then row-filtered values [TH][64] floats.
+__global__ void __launch_bounds__(256)
+k_pyr_level_tiled(ImageSet imgs, float* __restrict__ I, int W, int H, int Wk, int Hk, SmoothTaps taps, int TW, int TH) {
+    extern __shared__ __align__(16) float pyr_smem[];
+    float* s_t = pyr_smem;            // [TH][TW]
+    float* s_h = pyr_smem + TH * TW;  // [TH][64]
+    const int img = blockIdx.z;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int xb = blockIdx.x * 32, yb = blockIdx.y * 8;
+    const size_t N = (size_t)W * H;
+    const u8* src = img < imgs.split ? imgs.base0 + (size_t)img * N : imgs.base1 + (size_t)(img - imgs.split) * N;
+    const int r = taps.radius;
+    const double scx = (double)W / Wk, scy = (double)H / Hk;
+    int sx, sy, t0;
+    float fx, fy, tf;
+    flow_linear_coord(min(xb + tx, Wk - 1), scx, W, &sx, &fx);
+    flow_linear_coord(min(yb + ty, Hk - 1), scy, H, &sy, &fy);
+    // window of the block: columns X0 .. X0+tw-1, rows Y0 .. Y0+th-1 (source coordinates, may leave the image)
+    flow_linear_coord(xb, scx, W, &t0, &tf);
+    const int X0 = t0 - r;
+    flow_linear_coord(min(xb + 31, Wk - 1), scx, W, &t0, &tf);
+    const int tw = t0 + 1 + r - X0 + 1;
+    flow_linear_coord(yb, scy, H, &t0, &tf);
+    const int Y0 = t0 - r;
+    flow_linear_coord(min(yb + 7, Hk - 1), scy, H, &t0, &tf);
+    const int th = t0 + 1 + r - Y0 + 1;
+    for (int ry = ty; ry < th; ry += 8) {
+        const u8* row = src + (size_t)flow_reflect101(Y0 + ry, H) * W;
+        for (int cx = tx; cx < tw; cx += 32) s_t[ry * TW + cx] = (float)row[flow_reflect101(X0 + cx, W)];
+    }
+    __syncthreads();
+    // row filter at columns sx and sx+1 of every output column of the block, for every row of the window
+    {
+        const int lx = sx - X0;  // local column of the centre tap
+        for (int ry = ty; ry < th; ry += 8) {
+            const float* t = s_t + ry * TW + lx;
+            float h0 = 0.f, h1 = 0.f;
+            float prev = t[-r];
+            for (int i = -r; i <= r; ++i) {
+                const float nxt = t[i + 1];
+                h0 = fmaf(taps.k[i + r], prev, h0);
+                h1 = fmaf(taps.k[i + r], nxt, h1);
+                prev = nxt;
+            }
+            s_h[ry * 64 + 2 * tx] = h0;
+            s_h[ry * 64 + 2 * tx + 1] = h1;
+        }
+    }
+    __syncthreads();
+    const int x = xb + tx, y = yb + ty;
+    if (x >= Wk || y >= Hk) return;
+    const int nx = fx != 0.f ? 2 : 1, ny = fy != 0.f ? 2 : 1;
+    float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};  // [dy][dx]
+    const float* hcol = s_h + (sy - Y0) * 64 + 2 * tx;
+    for (int j = -r; j <= r + ny - 1; ++j) {
+        const float h0 = hcol[j * 64], h1 = hcol[j * 64 + 1];
+        if (j <= r) {
+            acc[0][0] = fmaf(taps.k[j + r], h0, acc[0][0]);
+            acc[0][1] = fmaf(taps.k[j + r], h1, acc[0][1]);
+        }
+        if (ny == 2 && j >= -r + 1) {
+            acc[1][0] = fmaf(taps.k[j - 1 + r], h0, acc[1][0]);
+            acc[1][1] = fmaf(taps.k[j - 1 + r], h1, acc[1][1]);
+        }
+    }
+    const float top = nx == 2 ? fmaf(acc[0][1], fx, acc[0][0] * (1.f - fx)) : acc[0][0];
+    float v = top;
+    if (ny == 2) {
+        const float bot = nx == 2 ? fmaf(acc[1][1], fx, acc[1][0] * (1.f - fx)) : acc[1][0];
+        v = fmaf(bot, fy, top * (1.f - fy));
+    }
+    I[((size_t)img * Hk + y) * Wk + x] = v;
+}
+#define PYR_TILED_MAX_SMEM (160 * 1024)
+// window bound of a block of 32 x 8 outputs: the source step of 31 (7) outputs, the two interpolation taps, the filter
+// radius on both sides, and slack for the rounding of the coordinate map
+inline void pyr_tile_dims(int W, int H, int Wk, int Hk, int r, int* TW, int* TH) {
+    *TW = (int)ceil(31.0 * W / Wk) + 2 * r + 4;
+    *TH = (int)ceil(7.0 * H / Hk) + 2 * r + 4;
 }
 
 // Level 0 of the pyramid (same size as the frame, 3 taps): the general kernel's arithmetic, without its loops
@@ -750,6 +837,8 @@ inline int farneback_set_attributes() {
     if (cudaFuncSetAttribute(k_box_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)box_solve_smem(63 / 2)) != cudaSuccess)
         return 3;
     if (cudaFuncSetAttribute(k_box_solve7, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BS7_SMEM) != cudaSuccess) return 3;
+    if (cudaFuncSetAttribute(k_pyr_level_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, PYR_TILED_MAX_SMEM) != cudaSuccess)
+        return 3;
     return 0;
 }
 
@@ -800,8 +889,15 @@ inline int farneback_run(FlowBuffers& fb, const u8* d_gray0, const u8* d_gray1, 
         start.mul = 1.0 / fb.cfg.pyr_scale;
         if (L.w == fb.W && L.h == fb.H && L.taps.radius == 1)
             k_pyr_level0<<<g_img, blk, 0, stream>>>(fresh, I_fresh, fb.W, fb.H, L.taps);
-        else
-            k_pyr_level<<<g_img, blk, 0, stream>>>(fresh, I_fresh, fb.W, fb.H, L.w, L.h, L.taps);
+        else {
+            int TW, TH;
+            pyr_tile_dims(fb.W, fb.H, L.w, L.h, L.taps.radius, &TW, &TH);
+            const size_t smem = ((size_t)TH * TW + (size_t)TH * 64) * sizeof(float);
+            if (smem <= PYR_TILED_MAX_SMEM && !fb.pyr_untiled)
+                k_pyr_level_tiled<<<g_img, blk, smem, stream>>>(fresh, I_fresh, fb.W, fb.H, L.w, L.h, L.taps, TW, TH);
+            else
+                k_pyr_level<<<g_img, blk, 0, stream>>>(fresh, I_fresh, fb.W, fb.H, L.w, L.h, L.taps);
+        }
         FLOW_MARK(st, "flow.pyramid");
         if (fb.poly.n == 5)
             k_polyexp<5><<<g_img, blk, 0, stream>>>(I_fresh, R_fresh, L.w, L.h, fb.poly);

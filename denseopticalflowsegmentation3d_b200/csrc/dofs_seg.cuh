@@ -167,6 +167,105 @@ k_blur_fused(const float2* __restrict__ src, float2* __restrict__ dst, int W, in
     }
 }
 
+// The same kernel with the tile staged by the TMA engine instead of LDG -> STS through the LSU pipe: for a tile whose halo
+// lies inside the image, one elected thread arms an mbarrier with the tile's byte count and issues one bulk copy
+// (cp.async.bulk, SASS: UBLKCP) per tile row — 56 x 448 contiguous bytes — straight into the padded shared-memory rows;
+// the block waits on the barrier's phase.  Border tiles resolve their reflections with ordinary loads into the same
+// layout.  Needs 16-byte aligned rows (even width, aligned base); the compute phases and their arithmetic are those of
+// k_blur_fused, so the results are bit-identical.
+DOFS_D u32 dofs_smem_addr(const void* p) { return (u32)__cvta_generic_to_shared(p); }
+DOFS_D void mbar_init(u64* bar, u32 count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(dofs_smem_addr(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+DOFS_D void mbar_expect_tx(u64* bar, u32 bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(dofs_smem_addr(bar)), "r"(bytes) : "memory");
+}
+DOFS_D void bulk_copy_g2s(void* dst, const void* src, u32 bytes, u64* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     dofs_smem_addr(dst)),
+                 "l"(src), "r"(bytes), "r"(dofs_smem_addr(bar))
+                 : "memory");
+}
+DOFS_D bool mbar_try_wait(u64* bar, u32 phase) {
+    u32 ok;
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(ok)
+        : "r"(dofs_smem_addr(bar)), "r"(phase)
+        : "memory");
+    return ok != 0;
+}
+
+template <int R>
+__global__ void __launch_bounds__(256)
+k_blur_fused_tma(const float2* __restrict__ src, float2* __restrict__ dst, int W, int H, BlurTaps taps) {
+    constexpr int C = FB_T + 2 * R;  // tile columns / rows with halo
+    constexpr int P = (C + 2) & ~1;  // row pitch in float2: a multiple of 16 bytes for the bulk copies
+    __shared__ __align__(16) float2 s_in[C][P];
+    __shared__ float2 s_h[C][FB_T + 1];
+    __shared__ __align__(8) u64 s_bar;
+    const int frame = blockIdx.z;
+    const int x0 = blockIdx.x * FB_T, y0 = blockIdx.y * FB_T;
+    const float2* img = src + (size_t)frame * W * H;
+    const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+    if (x0 >= R && y0 >= R && x0 + FB_T + R <= W && y0 + FB_T + R <= H) {  // no border in reach (block-uniform)
+        if (threadIdx.x == 0) mbar_init(&s_bar, 1);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            mbar_expect_tx(&s_bar, (u32)(C * C * sizeof(float2)));
+            const float2* row = img + (size_t)(y0 - R) * W + (x0 - R);
+            for (int ry = 0; ry < C; ++ry) bulk_copy_g2s(&s_in[ry][0], row + (size_t)ry * W, (u32)(C * sizeof(float2)), &s_bar);
+        }
+        while (!mbar_try_wait(&s_bar, 0u)) {
+        }
+    } else {
+        for (int ry = wrp; ry < C; ry += 8) {
+            const int yy = reflect101(y0 + ry - R, H);
+            const float2* row = img + (size_t)yy * W;
+            for (int cx = lane; cx < C; cx += 32) s_in[ry][cx] = row[reflect101(x0 + cx - R, W)];
+        }
+        __syncthreads();
+    }
+    // rows: (tile row, group of 4 columns)
+    for (int w = threadIdx.x; w < C * (FB_T / 4); w += 256) {
+        const int ry = w / (FB_T / 4), g = w % (FB_T / 4);
+        float2 v[2 * R + 4];
+#pragma unroll
+        for (int i = 0; i < 2 * R + 4; ++i) v[i] = s_in[ry][4 * g + i];
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+            float sx = 0.f, sy = 0.f;
+#pragma unroll
+            for (int k = 0; k <= 2 * R; ++k) {
+                sx = fmaf(taps.k[k], v[o + k].x, sx);
+                sy = fmaf(taps.k[k], v[o + k].y, sy);
+            }
+            s_h[ry][4 * g + o] = make_float2(sx, sy);
+        }
+    }
+    __syncthreads();
+    // columns: (tile column, group of 4 rows)
+    {
+        const int tx = threadIdx.x & 31, g = threadIdx.x >> 5;  // 8 groups of 4 rows
+        float2 v[2 * R + 4];
+#pragma unroll
+        for (int i = 0; i < 2 * R + 4; ++i) v[i] = s_h[4 * g + i][tx];
+        const int x = x0 + tx;
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+            float sx = 0.f, sy = 0.f;
+#pragma unroll
+            for (int k = 0; k <= 2 * R; ++k) {
+                sx = fmaf(taps.k[k], v[o + k].x, sx);
+                sy = fmaf(taps.k[k], v[o + k].y, sy);
+            }
+            const int y = y0 + 4 * g + o;
+            if (x < W && y < H) dst[(size_t)frame * W * H + (size_t)y * W + x] = make_float2(sx, sy);
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // K7  edge weights: build_graph's enumeration (graph.cpp:62-93) with diff (segment.cpp:20-32).
 // Slot 4*p+d of pixel p=(x,y): d=0 left (x-1,y), d=1 up (x,y-1), d=2 up-left (x-1,y-1),
@@ -601,19 +700,29 @@ k_bor_pixel(BorState S, const u32* __restrict__ prefix, size_t prefix_stride, co
     const int frame = blockIdx.y;
     if (bor_done(S, level, frame)) return;
     const size_t fo = (size_t)frame * N;
-    const u32* comp = S.comp + fo;
+    u32* comp = S.comp + fo;
+    const u32* up = S.up + fo;
     const u32* pre = prefix + (size_t)frame * prefix_stride;
     u64* best = S.best + fo;
     GRID_STRIDE(p, N) {
         const u32 m = S.mask[fo + p];
         if (m == 0) continue;
-        const u32 cp = comp[p];
+        // `comp` of a live pixel is one contraction behind (there is no separate relabel pass after level 0): the
+        // contraction left the current root of every root of the previous level in `up` (a survivor points at itself),
+        // so one hop refreshes it.  A neighbour's entry may already have been refreshed by its own thread: one hop from
+        // a current root is the root itself.  Pixels whose edges are all internal are never read again and stay stale.
+        const u32 c0 = comp[p];
+        const u32 cp = up[c0];
+        if (cp != c0) comp[p] = cp;
         const u64 seen0 = best[cp];
         // independent loads first (the kernel is bound by memory latency): neighbour components, then their prefixes
         u32 out = 0;
 #pragma unroll
         for (int e = 0; e < 8; ++e)
-            if (((m >> e) & 1u) && comp[incident_pixel(p, e, W)] != cp) out |= 1u << e;
+            if ((m >> e) & 1u) {
+                const u32 q0 = comp[incident_pixel(p, e, W)];
+                if (q0 != c0 && up[q0] != cp) out |= 1u << e;  // equal stale roots are equal current roots
+            }
         if (out != m) S.mask[fo + p] = (u8)out;  // an edge that became internal stays internal
         if (out == 0) continue;
         u32 pr[8];
@@ -794,7 +903,8 @@ k_bor_contract(BorState S, int N, int level) {
     }
 }
 
-// every pixel follows its root's new link (one hop: the contraction stored the group root itself)
+// every pixel follows its root's new link (one hop: the contraction stored the group root itself).  Only launched after
+// level 0, where it is the first write of `comp`; from level 1 on the pixel kernel of the next level does the hop itself.
 __global__ void __launch_bounds__(SEG_THREADS)
 k_bor_relabel(BorState S, int N, int level) {
     const int frame = blockIdx.y;
@@ -1168,7 +1278,14 @@ struct ReplayArgs {
     int W, H, N;
     int min_size;
     EvBits eb;
+    const double* rcp;     // [RCP_TABLE] 1.0 / n, correctly rounded (filled on the host: IEEE division), for the small set
+                           // sizes of the early waves
 };
+#define RCP_TABLE 4096
+// 1.0 / n in double, as Vec2f / int computes it (graph.cpp:188): the table entry for small n, the division otherwise
+DOFS_D double size_reciprocal(const ReplayArgs& A, int n) {
+    return n < RCP_TABLE ? __ldg(A.rcp + n) : xddiv(1.0, (double)n);
+}
 
 // Forest::merge's size-weighted mean (graph.cpp:184-190) with OpenCV's Vec2f rounding:
 // Vec2f * int -> float products, float sum, Vec2f / int -> multiply by the double reciprocal.
@@ -1261,7 +1378,7 @@ k_replay_short(ReplayArgs A, int wave) {
             const ushort4 ba = ra.bbox;
             const float fsa = (float)sa;
             const int s_after = s + sa;
-            const double inv = xddiv(1.0, (double)s_after);
+            const double inv = size_reciprocal(A, s_after);
             f.x = merge_mean(xfmul(fa.x, fsa), f.x, (float)s, inv);
             f.y = merge_mean(xfmul(fa.y, fsa), f.y, (float)s, inv);
             s = s_after;
@@ -1454,7 +1571,7 @@ k_replay_operands(ReplayArgs A, int wave) {
         const int sa = A.ev_sa[fo + j];
         const float2 pr = A.ev_prod[fo + j];
         A.ev_op[fo + j] = make_float4(pr.x, pr.y, (float)(s_after - sa), (float)s_after);
-        A.ev_inv[fo + j] = xddiv(1.0, (double)s_after);
+        A.ev_inv[fo + j] = size_reciprocal(A, s_after);
         A.ev_size[fo + j] = s_after;
         A.ev_bbox[fo + j] = bb;
     }

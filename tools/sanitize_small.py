@@ -18,6 +18,15 @@ with d.Context(W, H, max_pairs=n) as c:
     fb = (rng.normal(size=(H, W, 2)) * 2).astype(np.float32)
     c.edges_sorted(fb)
     c.lift([[1.0, 2.0]], [[10, 20, 60, 70]], [1])
+    # compact label formats, per-node accessors, the streaming entry points (carried frame, two staging buffers)
+    from denseopticalflowsegmentation3d_b200 import capi
+    rle = c.process_ex(fr, capi.LABELS_RLE, max_runs=4096)
+    c.process_ex(fr, capi.LABELS_U16)
+    c.scored_merges(0)
+    c.node_state(0, int(out["stats"][0]["final_root"]))
+    clip = synth.frames(3, 4, 0, 7, W, H)
+    st = c.process_stream(clip, label_format=capi.LABELS_RLE, max_runs=4096)
+    print("runs", rle["n_runs"].tolist(), "stream pairs", len(st["boxes"]))
 # near-tie field: long prefix runs and the 64-bit fallback
 fb = np.zeros((200, 300, 2), np.float32)
 fb[..., 1] = np.arange(200, dtype=np.float32)[:, None]
