@@ -55,6 +55,15 @@ class Stats(C.Structure):
 STATS_DTYPE = np.dtype([(k, "<i4") for k in ("n_edges", "n_merges", "n_levels", "n_candidates", "n_scored",
                                              "n_boxes", "longest_chain", "final_root", "sort_fallback", "replay_exact_chunks")])
 
+class FhParams(C.Structure):
+    """dofs3d_fh_params: the Felzenszwalb mode of the reference's Python twin (graph.py:156-177)."""
+    _fields_ = [("k", C.c_double), ("min_size", C.c_int), ("neighbors", C.c_int), ("flow_dist", C.c_double),
+                ("edge_dist", C.c_double), ("stage", C.c_int)]
+
+
+BEV_WIDTH, BEV_HEIGHT = 2500, 14000
+
+
 class Run(C.Structure):
     _fields_ = [("start", C.c_uint32), ("label", C.c_int32)]
 
@@ -79,7 +88,8 @@ def runs_to_labels(runs, n_runs, n_pixels):
 # every symbol include/dofs3d.h declares
 SYMBOLS = [
     "dofs3d_process_ex", "dofs3d_process_ex_dev", "dofs3d_segment_ex", "dofs3d_stream_begin", "dofs3d_stream_submit",
-    "dofs3d_stream_collect", "dofs3d_node_state", "dofs3d_scored_merges", "dofs3d_pinned_alloc", "dofs3d_pinned_free",
+    "dofs3d_stream_collect", "dofs3d_fh_default_params", "dofs3d_segment_fh", "dofs3d_warp_perspective",
+    "dofs3d_bev_transform", "dofs3d_node_state", "dofs3d_scored_merges", "dofs3d_pinned_alloc", "dofs3d_pinned_free",
     "dofs3d_default_params", "dofs3d_params_for_size", "dofs3d_create", "dofs3d_destroy", "dofs3d_sync", "dofs3d_last_error", "dofs3d_stream",
     "dofs3d_launch_count", "dofs3d_device_bytes", "dofs3d_gray", "dofs3d_gray_dev", "dofs3d_flow", "dofs3d_blur",
     "dofs3d_segment", "dofs3d_paint", "dofs3d_lift", "dofs3d_edges_sorted", "dofs3d_process", "dofs3d_process_dev",
@@ -138,6 +148,11 @@ def load_library():
     L.dofs3d_stream_collect.argtypes = [vp, C.POINTER(C.c_int)]
     L.dofs3d_node_state.argtypes = [vp, C.c_int, C.c_int, ip, fp, ip]
     L.dofs3d_scored_merges.argtypes = [vp, C.c_int, C.c_int, ip, ip, vp, u8p]
+    L.dofs3d_fh_default_params.argtypes = [C.POINTER(FhParams)]
+    L.dofs3d_fh_default_params.restype = None
+    L.dofs3d_segment_fh.argtypes = [vp, fp, C.POINTER(FhParams), ip, ip]
+    L.dofs3d_warp_perspective.argtypes = [vp, u8p, C.c_int, C.c_int, C.c_int, fp, C.c_int, C.c_int, u8p]
+    L.dofs3d_bev_transform.argtypes = [vp, u8p, u8p]
     L.dofs3d_pinned_alloc.argtypes = [C.c_size_t]
     L.dofs3d_pinned_alloc.restype = C.c_void_p
     L.dofs3d_pinned_free.argtypes = [vp]
@@ -345,6 +360,33 @@ class Context:
         return {"labels": np.concatenate([o["labels"] for o in outs]), "n_runs": np.concatenate([o["n_runs"] for o in outs]),
                 "n_boxes": np.concatenate([o["n_boxes"] for o in outs]), "boxes": [b for o in outs for b in o["boxes"]],
                 "stats": np.concatenate([o["stats"] for o in outs])}
+
+    # ---- Felzenszwalb mode, bird's-eye-view warp ------------------------------------------------
+    def segment_fh(self, flow, K=10.0, min_size=100, neighbors=8, flow_dist=5.0, edge_dist=5.0, stage=3):
+        """graph.py's segment_graph_flow on ONE flow field [H][W][2]: (labels[H][W] = root id per pixel, n_components)."""
+        f = np.ascontiguousarray(flow, np.float32).reshape(self.H, self.W, 2)
+        p = FhParams(float(K), int(min_size), int(neighbors), float(flow_dist), float(edge_dist), int(stage))
+        labels = np.empty((self.H, self.W), np.int32)
+        n = C.c_int32(0)
+        self._ck(self.L.dofs3d_segment_fh(self.h, _ptr(f), C.byref(p), _ptr(labels), C.byref(n)))
+        return labels, n.value
+
+    def warp_perspective(self, img, mat, out_w, out_h):
+        """cv::warpPerspective(img, mat, (out_w, out_h), INTER_CUBIC, BORDER_REPLICATE) on a u8 image [H][W](C)."""
+        img = np.ascontiguousarray(img, np.uint8)
+        ch = 1 if img.ndim == 2 else img.shape[2]
+        m = np.ascontiguousarray(mat, np.float32).reshape(9)
+        out = np.empty((out_h, out_w) if img.ndim == 2 else (out_h, out_w, ch), np.uint8)
+        self._ck(self.L.dofs3d_warp_perspective(self.h, _ptr(img), img.shape[1], img.shape[0], ch, _ptr(m), out_w, out_h,
+                                                _ptr(out)))
+        return out
+
+    def bev_transform(self, bgr_frame):
+        """The reference's transform(frame, get_mat().first): the 2500 x 14000 bird's-eye-view image."""
+        fr = np.ascontiguousarray(bgr_frame, np.uint8).reshape(self.H, self.W, 3)
+        out = np.empty((BEV_HEIGHT, BEV_WIDTH, 3), np.uint8)
+        self._ck(self.L.dofs3d_bev_transform(self.h, _ptr(fr), _ptr(out)))
+        return out
 
     # ---- per-node state of the last call ----------------------------------------------------
     def node_state(self, pair, node):

@@ -16,9 +16,11 @@
 #include <string>
 #include <vector>
 
+#include "dofs_bev.cuh"
 #include "dofs_common.cuh"
 #include "dofs_flow.cuh"
 #include "dofs_lift.cuh"
+#include "dofs_fh.cuh"
 #include "dofs_seg.cuh"
 #include "dofs_sort.cuh"
 #include "dofs_synth.cuh"
@@ -154,6 +156,9 @@ struct dofs3d_ctx {
     dofs3d_run* runs = nullptr;       // [F][runs_cap], allocated on the first run-length call
     int runs_cap = 0;
     dofs3d_stats* stats = nullptr;
+    int carveout = -1;                // DOFS3D_CARVEOUT: preferred shared-memory carveout (percent) of every kernel; -1 = the driver's choice
+    std::vector<const void*> carveout_done;
+    bool bor_fold = false;            // A/B knob: DOFS3D_BOR_FOLD=1 folds the Boruvka relabel pass into the pixel kernel
     bool blur_tma = true;             // A/B knob: DOFS3D_BLUR_TMA=0 stages the blur tiles with LDG -> STS instead of bulk copies
     double* rcp_table = nullptr;      // [RCP_TABLE] 1.0 / n for the replay of small sets
     int* sticky = nullptr;            // device: STICKY_* bits of every call since the last dofs3d_sync
@@ -189,11 +194,21 @@ namespace {
         }                                                                                             \
     } while (0)
 
+// Every kernel of a context can be given the same preferred shared-memory carveout (DOFS3D_CARVEOUT=<percent>): with
+// several contexts interleaving kernels on one GPU, kernels that ask for different L1 / shared-memory splits make the SMs
+// drain and reconfigure between them.  Applied once per kernel and context.
 #define LAUNCH(ctx, kernel, grid, block, smem, ...)                        \
     do {                                                                   \
+        if ((ctx)->carveout >= 0) prefer_carveout((ctx), (const void*)(kernel)); \
         kernel<<<grid, block, smem, (ctx)->stream>>>(__VA_ARGS__);         \
         (ctx)->launches++;                                                 \
     } while (0)
+
+void prefer_carveout(dofs3d_ctx* ctx, const void* kernel) {
+    if (std::find(ctx->carveout_done.begin(), ctx->carveout_done.end(), kernel) != ctx->carveout_done.end()) return;
+    ctx->carveout_done.push_back(kernel);
+    cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, ctx->carveout);
+}
 
 template <typename T>
 int dalloc(dofs3d_ctx* ctx, T** p, size_t count) {
@@ -422,11 +437,11 @@ int segment_dev(dofs3d_ctx* ctx, const float* d_flow, int already_blurred, int n
             LAUNCH(ctx, k_bor_level0_pick, gS, SEG_THREADS, 0, B, prefix, ctx->S, ctx->flow_blur, W, H, N);
             LAUNCH(ctx, k_bor_level0_root, gS, SEG_THREADS, 0, B, W, H, N, ctx->seg.neighbors == 8 ? 1 : 0);
         } else {
-            LAUNCH(ctx, k_bor_pixel, gS, SEG_THREADS, 0, B, prefix, ctx->S, ctx->flow_blur, W, N, level);
+            LAUNCH(ctx, k_bor_pixel, gS, SEG_THREADS, 0, B, prefix, ctx->S, ctx->flow_blur, W, N, level, ctx->bor_fold ? 1 : 0);
             LAUNCH(ctx, k_bor_root, gS, SEG_THREADS, 0, B, W, N, level);
         }
         LAUNCH(ctx, k_bor_contract, gS, SEG_THREADS, 0, B, N, level);
-        if (level == 0) LAUNCH(ctx, k_bor_relabel, gS, SEG_THREADS, 0, B, N, level);
+        if (level == 0 || !ctx->bor_fold) LAUNCH(ctx, k_bor_relabel, gS, SEG_THREADS, 0, B, N, level);
     }
     LAUNCH(ctx, k_bor_finish, gS, SEG_THREADS, 0, B, N, levels);
     mark(ctx, "boruvka");
@@ -884,6 +899,8 @@ int dofs3d_create(dofs3d_ctx** out, int device, int width, int height, int max_p
     }
     if (const char* e = getenv("DOFS3D_FORCE_TIME_FALLBACK")) ctx->force_time_fallback = atoi(e) != 0;
     if (const char* e = getenv("DOFS3D_BLUR_TMA")) ctx->blur_tma = atoi(e) != 0;
+    if (const char* e = getenv("DOFS3D_BOR_FOLD")) ctx->bor_fold = atoi(e) != 0;
+    if (const char* e = getenv("DOFS3D_CARVEOUT")) ctx->carveout = std::max(-1, std::min(100, atoi(e)));
     CK(cudaMallocHost(&ctx->h_sticky, sizeof(int)));
     *ctx->h_sticky = 0;
     DA(ctx->sticky, 1);
@@ -922,6 +939,7 @@ static int ensure_flow(dofs3d_ctx* ctx) {
         int rc = farneback_alloc(&ctx->fb, width, height, (int)F, fc, &fbytes);
         ctx->bytes += (long long)fbytes;
         if (const char* e = getenv("DOFS3D_PYR_UNTILED")) ctx->fb.pyr_untiled = atoi(e) != 0;
+        if (ctx->carveout >= 0) farneback_set_carveout(ctx->carveout);
         if (rc) {
             ctx->err = farneback_error(rc);
             return rc == 1 ? DOFS3D_ERR_ARG : rc == 3 ? DOFS3D_ERR_CUDA : DOFS3D_ERR_NOMEM;
@@ -1350,6 +1368,121 @@ int dofs3d_stream_collect(dofs3d_ctx* ctx, int* n_pairs_out) {
         return check_sticky(ctx);
     }
     return 0;
+}
+
+// ------------------------------------------------------------------------------------- Felzenszwalb mode
+void dofs3d_fh_default_params(dofs3d_fh_params* p) {
+    if (!p) return;
+    p->k = 10.0;
+    p->min_size = 100;
+    p->neighbors = 8;
+    p->flow_dist = 5.0;
+    p->edge_dist = 5.0;
+    p->stage = 3;
+}
+
+int dofs3d_segment_fh(dofs3d_ctx* ctx, const float* flow, const dofs3d_fh_params* params, int32_t* labels_out,
+                      int32_t* n_components_out) {
+    if (!ctx || !flow) return DOFS3D_ERR_ARG;
+    dofs3d_fh_params p;
+    if (params) p = *params;
+    else dofs3d_fh_default_params(&p);
+    if ((p.neighbors != 4 && p.neighbors != 8) || p.stage < 1 || p.stage > 3 || !(p.k >= 0) || p.min_size < 0) {
+        ctx->err = "bad dofs3d_fh_params";
+        return DOFS3D_ERR_ARG;
+    }
+    CK(cudaSetDevice(ctx->device));
+    const int N = ctx->N, W = ctx->W, H = ctx->H;
+    const int S = (int)ctx->S;
+    CK(cudaMemcpyAsync(ctx->flow_blur, flow, (size_t)N * sizeof(float2), cudaMemcpyHostToDevice, ctx->stream));
+    timer_begin(ctx);
+    // float32 weights of all 4N slots, stable radix sort: (weight, insertion order) like Python's sorted()
+    u32* keyA = reinterpret_cast<u32*>(ctx->keysB);
+    u32* keyB = keyA + ctx->S;
+    LAUNCH(ctx, k_fh_edge_keys, grid1(N, SEG_THREADS, 1), SEG_THREADS, 0, ctx->flow_blur, keyA, W, H, p.neighbors == 8 ? 1 : 0);
+    mark(ctx, "fh.edge_keys");
+    const int side = radix_sort_onesweep<u32>(ctx, keyA, ctx->valsA, keyB, ctx->valsB, ctx->S, S, 1, 32, true, "fh.sort.hist",
+                                              "fh.sort.scatter");
+    if (side != 0) {
+        ctx->err = "internal: odd number of sort passes";
+        return DOFS3D_ERR_INTERNAL;
+    }
+    FhState st;
+    st.parent = reinterpret_cast<int*>(ctx->bor.comp);
+    st.rank = ctx->bor.lvl;
+    st.size = ctx->ev_size;
+    st.color = ctx->ev_flow;
+    st.thr = ctx->ev_inv;
+    LAUNCH(ctx, k_fh_init, grid1(N, SEG_THREADS, 1), SEG_THREADS, 0, st, ctx->flow_blur, N, p.k);
+    const int E = n_edges_of(W, H, p.neighbors);  // non-finite weights sort behind them and are never walked
+    for (int pass = 1; pass <= p.stage; ++pass) {
+        LAUNCH(ctx, k_fh_walk, dim3(1), 32, 0, st, keyA, ctx->valsA, E, W, pass, p.k, p.min_size, p.flow_dist, p.edge_dist);
+        mark(ctx, pass == 1 ? "fh.walk.threshold" : pass == 2 ? "fh.walk.small" : "fh.walk.merge");
+    }
+    int* d_count = ctx->counters;  // [0] of the per-frame counters: free between calls
+    CK(cudaMemsetAsync(d_count, 0, sizeof(int), ctx->stream));
+    LAUNCH(ctx, k_fh_labels, grid1(N, SEG_THREADS, 1), SEG_THREADS, 0, st, ctx->labels, d_count, N);
+    mark(ctx, "fh.labels");
+    CK(cudaGetLastError());
+    if (labels_out) CK(cudaMemcpyAsync(labels_out, ctx->labels, (size_t)N * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    if (n_components_out) CK(cudaMemcpyAsync(n_components_out, d_count, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------- BEV warp
+int dofs3d_warp_perspective(dofs3d_ctx* ctx, const uint8_t* img, int width, int height, int channels, const float* mat9,
+                            int out_w, int out_h, uint8_t* out) {
+    if (!ctx || !img || !mat9 || !out || width < 1 || height < 1 || out_w < 1 || out_h < 1) return DOFS3D_ERR_ARG;
+    if (channels != 1 && channels != 3 && channels != 4) {
+        ctx->err = "channels must be 1, 3 or 4";
+        return DOFS3D_ERR_ARG;
+    }
+    if (width > 32767 || height > 32767) {
+        ctx->err = "source image too large for warpPerspective's 16-bit coordinates";
+        return DOFS3D_ERR_ARG;
+    }
+    CK(cudaSetDevice(ctx->device));
+    WarpMatrix M;
+    warp_invert(mat9, &M);
+    std::vector<short> tab;
+    warp_cubic_table(&tab);
+    u8 *d_src = nullptr, *d_dst = nullptr;
+    short* d_tab = nullptr;
+    const size_t src_bytes = (size_t)width * height * channels, dst_bytes = (size_t)out_w * out_h * channels;
+    int rc = 0;
+    cudaError_t e;
+    if ((e = cudaMalloc(&d_src, src_bytes)) != cudaSuccess || (e = cudaMalloc(&d_dst, dst_bytes)) != cudaSuccess ||
+        (e = cudaMalloc(&d_tab, tab.size() * sizeof(short))) != cudaSuccess) {
+        ctx->err = cudaGetErrorString(e);
+        rc = DOFS3D_ERR_NOMEM;
+    }
+    if (!rc) {
+        cudaMemcpyAsync(d_src, img, src_bytes, cudaMemcpyHostToDevice, ctx->stream);
+        cudaMemcpyAsync(d_tab, tab.data(), tab.size() * sizeof(short), cudaMemcpyHostToDevice, ctx->stream);
+        timer_begin(ctx);
+        const dim3 grid((out_w + WARP_BW - 1) / WARP_BW, (out_h + WARP_BH - 1) / WARP_BH);
+        if (channels == 1) LAUNCH(ctx, k_warp_perspective_cubic<1>, grid, 256, 0, d_src, width, height, d_dst, out_w, out_h, M, d_tab);
+        else if (channels == 3) LAUNCH(ctx, k_warp_perspective_cubic<3>, grid, 256, 0, d_src, width, height, d_dst, out_w, out_h, M, d_tab);
+        else LAUNCH(ctx, k_warp_perspective_cubic<4>, grid, 256, 0, d_src, width, height, d_dst, out_w, out_h, M, d_tab);
+        mark(ctx, "bev.warp");
+        cudaMemcpyAsync(out, d_dst, dst_bytes, cudaMemcpyDeviceToHost, ctx->stream);
+        e = cudaStreamSynchronize(ctx->stream);
+        if (e == cudaSuccess) e = cudaGetLastError();
+        if (e != cudaSuccess) {
+            ctx->err = cudaGetErrorString(e);
+            rc = DOFS3D_ERR_CUDA;
+        }
+    }
+    cudaFree(d_src);
+    cudaFree(d_dst);
+    cudaFree(d_tab);
+    return rc;
+}
+
+int dofs3d_bev_transform(dofs3d_ctx* ctx, const uint8_t* bgr_frame, uint8_t* bev_out) {
+    if (!ctx) return DOFS3D_ERR_ARG;
+    return dofs3d_warp_perspective(ctx, bgr_frame, ctx->W, ctx->H, 3, ctx->prm.persp, DOFS3D_BEV_WIDTH, DOFS3D_BEV_HEIGHT, bev_out);
 }
 
 void* dofs3d_pinned_alloc(size_t bytes) {

@@ -335,17 +335,18 @@ k_pyr_level(ImageSet imgs, float* __restrict__ I, int W, int H, int Wk, int Hk, 
     I[((size_t)img * Hk + y) * Wk + x] = v;
 }
 
-// The same level from a shared-memory tile: the block's source window is staged once as floats (reflected borders
-// resolved while loading), row-filtered at the two source columns every output needs, then column-filtered and
-// interpolated.  The fmaf chains are those of k_pyr_level in the same order, so the result is bit-identical to it; what
-// changes is that a source byte is loaded and converted once per block instead of once per tap per thread (the coarse
-// levels were bound by byte loads and conversions: 18 x 18 of them per output at the coarsest level).
-// Dynamic shared memory: tile [TH][TW] floats, then row-filtered values [TH][64] floats.
+// The same level from a shared-memory tile: the block's source window is staged once as bytes (whole 32-bit words with
+// several loads in flight per thread when the window lies inside the image, reflected byte by byte otherwise),
+// row-filtered at the two source columns every output needs, then column-filtered and interpolated.  The fmaf chains
+// are those of k_pyr_level in the same order, so the result is bit-identical to it.  What changes: k_pyr_level is bound by
+// latency — every tap is a dependent global byte load -> convert -> fma chain with a run-time trip count (18 x 18 of
+// them per output at the coarsest level) — while here a source byte comes from HBM/L2 once per block.
+// Dynamic shared memory: row-filtered values [TH][64] floats, then the byte tile [TH][TWB].
 __global__ void __launch_bounds__(256)
-k_pyr_level_tiled(ImageSet imgs, float* __restrict__ I, int W, int H, int Wk, int Hk, SmoothTaps taps, int TW, int TH) {
+k_pyr_level_tiled(ImageSet imgs, float* __restrict__ I, int W, int H, int Wk, int Hk, SmoothTaps taps, int TWB, int TH) {
     extern __shared__ __align__(16) float pyr_smem[];
-    float* s_t = pyr_smem;            // [TH][TW]
-    float* s_h = pyr_smem + TH * TW;  // [TH][64]
+    float* s_h = pyr_smem;                                   // [TH][64]
+    u8* s_t = reinterpret_cast<u8*>(pyr_smem + TH * 64);     // [TH][TWB], TWB a multiple of 4
     const int img = blockIdx.z;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int xb = blockIdx.x * 32, yb = blockIdx.y * 8;
@@ -366,20 +367,43 @@ k_pyr_level_tiled(ImageSet imgs, float* __restrict__ I, int W, int H, int Wk, in
     const int Y0 = t0 - r;
     flow_linear_coord(min(yb + 7, Hk - 1), scy, H, &t0, &tf);
     const int th = t0 + 1 + r - Y0 + 1;
-    for (int ry = ty; ry < th; ry += 8) {
-        const u8* row = src + (size_t)flow_reflect101(Y0 + ry, H) * W;
-        for (int cx = tx; cx < tw; cx += 32) s_t[ry * TW + cx] = (float)row[flow_reflect101(X0 + cx, W)];
+    int shift = 0;  // tile column of source column X0
+    if (X0 >= 0 && Y0 >= 0 && X0 + tw <= W && Y0 + th <= H && (W & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 3) == 0) {
+        const int Xa = X0 & ~3;
+        shift = X0 - Xa;
+        const int nw = (shift + tw + 3) >> 2;  // words per tile row; Xa + 4 nw <= W because W is a multiple of 4
+        const int total = th * nw;
+        u32* s_w = reinterpret_cast<u32*>(s_t);
+        for (int base = 0; base < total; base += 256 * 4) {
+            u32 v[4];
+            int at[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int idx = base + u * 256 + (int)threadIdx.x;
+                const int ry = idx / nw, c = idx - ry * nw;
+                at[u] = idx < total ? ry * (TWB >> 2) + c : -1;
+                v[u] = idx < total ? *reinterpret_cast<const u32*>(src + (size_t)(Y0 + ry) * W + Xa + 4 * c) : 0u;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (at[u] >= 0) s_w[at[u]] = v[u];
+        }
+    } else {
+        for (int ry = ty; ry < th; ry += 8) {
+            const u8* row = src + (size_t)flow_reflect101(Y0 + ry, H) * W;
+            for (int cx = tx; cx < tw; cx += 32) s_t[ry * TWB + cx] = row[flow_reflect101(X0 + cx, W)];
+        }
     }
     __syncthreads();
     // row filter at columns sx and sx+1 of every output column of the block, for every row of the window
     {
-        const int lx = sx - X0;  // local column of the centre tap
+        const int lx = sx - X0 + shift;  // tile column of the centre tap
         for (int ry = ty; ry < th; ry += 8) {
-            const float* t = s_t + ry * TW + lx;
+            const u8* t = s_t + ry * TWB + lx;
             float h0 = 0.f, h1 = 0.f;
-            float prev = t[-r];
+            float prev = (float)t[-r];
             for (int i = -r; i <= r; ++i) {
-                const float nxt = t[i + 1];
+                const float nxt = (float)t[i + 1];
                 h0 = fmaf(taps.k[i + r], prev, h0);
                 h1 = fmaf(taps.k[i + r], nxt, h1);
                 prev = nxt;
@@ -413,11 +437,12 @@ k_pyr_level_tiled(ImageSet imgs, float* __restrict__ I, int W, int H, int Wk, in
     }
     I[((size_t)img * Hk + y) * Wk + x] = v;
 }
-#define PYR_TILED_MAX_SMEM (160 * 1024)
+#define PYR_TILED_MAX_SMEM (48 * 1024)  // no opt-in: the level falls back to k_pyr_level when its window needs more
 // window bound of a block of 32 x 8 outputs: the source step of 31 (7) outputs, the two interpolation taps, the filter
 // radius on both sides, and slack for the rounding of the coordinate map
-inline void pyr_tile_dims(int W, int H, int Wk, int Hk, int r, int* TW, int* TH) {
-    *TW = (int)ceil(31.0 * W / Wk) + 2 * r + 4;
+inline void pyr_tile_dims(int W, int H, int Wk, int Hk, int r, int* TWB, int* TH) {
+    const int tw = (int)ceil(31.0 * W / Wk) + 2 * r + 4;
+    *TWB = (tw + 3 + 3) & ~3;  // + the alignment shift of the word loads, rounded to whole words
     *TH = (int)ceil(7.0 * H / Hk) + 2 * r + 4;
 }
 
@@ -837,9 +862,15 @@ inline int farneback_set_attributes() {
     if (cudaFuncSetAttribute(k_box_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)box_solve_smem(63 / 2)) != cudaSuccess)
         return 3;
     if (cudaFuncSetAttribute(k_box_solve7, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BS7_SMEM) != cudaSuccess) return 3;
-    if (cudaFuncSetAttribute(k_pyr_level_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, PYR_TILED_MAX_SMEM) != cudaSuccess)
-        return 3;
     return 0;
+}
+
+// the same preferred shared-memory carveout for every kernel of the flow stage (see LAUNCH in dofs3d.cu)
+inline void farneback_set_carveout(int pct) {
+    const void* ks[] = {(const void*)k_bgr2gray, (const void*)k_pyr_level0, (const void*)k_pyr_level, (const void*)k_pyr_level_tiled,
+                        (const void*)k_polyexp<5>, (const void*)k_polyexp<0>, (const void*)k_update_matrices<UM_FLOW>,
+                        (const void*)k_update_matrices<UM_START>, (const void*)k_box_solve, (const void*)k_box_solve7};
+    for (const void* k : ks) cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -892,7 +923,7 @@ inline int farneback_run(FlowBuffers& fb, const u8* d_gray0, const u8* d_gray1, 
         else {
             int TW, TH;
             pyr_tile_dims(fb.W, fb.H, L.w, L.h, L.taps.radius, &TW, &TH);
-            const size_t smem = ((size_t)TH * TW + (size_t)TH * 64) * sizeof(float);
+            const size_t smem = (size_t)TH * 64 * sizeof(float) + (size_t)TH * TW;
             if (smem <= PYR_TILED_MAX_SMEM && !fb.pyr_untiled)
                 k_pyr_level_tiled<<<g_img, blk, smem, stream>>>(fresh, I_fresh, fb.W, fb.H, L.w, L.h, L.taps, TW, TH);
             else

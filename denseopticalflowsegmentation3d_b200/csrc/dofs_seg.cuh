@@ -696,7 +696,7 @@ DOFS_D bool pick_meets(u64 cand, u64 seen) {
 
 __global__ void __launch_bounds__(SEG_THREADS, BOR_PIXEL_BLOCKS)
 k_bor_pixel(BorState S, const u32* __restrict__ prefix, size_t prefix_stride, const float2* __restrict__ flow, int W, int N,
-            int level) {
+            int level, int fold) {
     const int frame = blockIdx.y;
     if (bor_done(S, level, frame)) return;
     const size_t fo = (size_t)frame * N;
@@ -707,12 +707,14 @@ k_bor_pixel(BorState S, const u32* __restrict__ prefix, size_t prefix_stride, co
     GRID_STRIDE(p, N) {
         const u32 m = S.mask[fo + p];
         if (m == 0) continue;
-        // `comp` of a live pixel is one contraction behind (there is no separate relabel pass after level 0): the
-        // contraction left the current root of every root of the previous level in `up` (a survivor points at itself),
-        // so one hop refreshes it.  A neighbour's entry may already have been refreshed by its own thread: one hop from
-        // a current root is the root itself.  Pixels whose edges are all internal are never read again and stay stale.
+        // fold != 0 (A/B knob, DOFS3D_BOR_FOLD=1): there is no separate relabel pass after level 0 and `comp` of a live
+        // pixel is one contraction behind: the contraction left the current root of every root of the previous level in
+        // `up` (a survivor points at itself), so one hop refreshes it.  A neighbour's entry may already have been
+        // refreshed by its own thread: one hop from a current root is the root itself.  Pixels whose edges are all
+        // internal are never read again and stay stale.  Measured on the B200 (32 pairs, alone): the extra random
+        // gathers cost more than the streaming relabel pass they replace (Boruvka 9.4 -> 11.2 ms), so it is off.
         const u32 c0 = comp[p];
-        const u32 cp = up[c0];
+        const u32 cp = fold ? up[c0] : c0;
         if (cp != c0) comp[p] = cp;
         const u64 seen0 = best[cp];
         // independent loads first (the kernel is bound by memory latency): neighbour components, then their prefixes
@@ -721,7 +723,7 @@ k_bor_pixel(BorState S, const u32* __restrict__ prefix, size_t prefix_stride, co
         for (int e = 0; e < 8; ++e)
             if ((m >> e) & 1u) {
                 const u32 q0 = comp[incident_pixel(p, e, W)];
-                if (q0 != c0 && up[q0] != cp) out |= 1u << e;  // equal stale roots are equal current roots
+                if (q0 != c0 && (!fold || up[q0] != cp)) out |= 1u << e;  // equal stale roots are equal current roots
             }
         if (out != m) S.mask[fo + p] = (u8)out;  // an edge that became internal stays internal
         if (out == 0) continue;
@@ -903,8 +905,8 @@ k_bor_contract(BorState S, int N, int level) {
     }
 }
 
-// every pixel follows its root's new link (one hop: the contraction stored the group root itself).  Only launched after
-// level 0, where it is the first write of `comp`; from level 1 on the pixel kernel of the next level does the hop itself.
+// every pixel follows its root's new link (one hop: the contraction stored the group root itself).  With the fold knob
+// it is only launched after level 0, where it is the first write of `comp`.
 __global__ void __launch_bounds__(SEG_THREADS)
 k_bor_relabel(BorState S, int N, int level) {
     const int frame = blockIdx.y;

@@ -218,6 +218,39 @@ int dofs3d_stream_begin(dofs3d_ctx* ctx);
 int dofs3d_stream_submit(dofs3d_ctx* ctx, const uint8_t* bgr_frames, int n_frames, const dofs3d_outputs* out);
 int dofs3d_stream_collect(dofs3d_ctx* ctx, int* n_pairs_out);
 
+/* ---- Felzenszwalb adaptive-threshold mode --------------------------------------------------------
+ * The segmentation of the reference's Python twin on a flow field: graph.py:156-177 segment_graph_flow = sorted edges
+ * (graph.py:77-96 build_graph, main.py:310-312 diff in float32), the threshold loop `w <= thr[a] && w <= thr[b]`,
+ * thr = w + K / size (graph.py:163-172, main.py:314-315), remove_small_components (graph.py:98-106) and merge_components
+ * (graph.py:108-130: mean-flow distance < flow_dist and edge weight < edge_dist, both 5 in the reference).
+ * Node ids are row * W + col (the reference addresses its array as img[x][y]; give it the transposed field to compare).
+ * flow: ONE field [H][W][2] f32 (host), taken as it is (blur it first with dofs3d_blur if wanted).
+ * labels_out [H][W] int32 = Forest.find(pixel), the root id of the pixel's component; *n_components_out = their number.
+ * stage: 3 = the whole of segment_graph_flow; 2 = stop after remove_small_components (the reference's segment_graph,
+ * graph.py:133-153); 1 = the threshold loop only. */
+typedef struct {
+    double k;          /* 10.0  --K of main.py:483 */
+    int min_size;      /* 100   --min-comp-size of main.py:485 */
+    int neighbors;     /* 8     --neighbor of main.py:480 */
+    double flow_dist;  /* 5     graph.py:126 */
+    double edge_dist;  /* 5     graph.py:126 */
+    int stage;         /* 3 */
+} dofs3d_fh_params;
+void dofs3d_fh_default_params(dofs3d_fh_params* p);
+int dofs3d_segment_fh(dofs3d_ctx* ctx, const float* flow, const dofs3d_fh_params* params, int32_t* labels_out,
+                      int32_t* n_components_out);
+
+/* ---- bird's-eye-view warp -----------------------------------------------------------------------
+ * cv::warpPerspective(img, result, mat, Size(out_w, out_h), INTER_CUBIC, BORDER_REPLICATE) on an 8-bit image of 1, 3 or 4
+ * interleaved channels (host pointers): what the reference's `transform` (lifting_3d.cpp:516-522) computes with
+ * out_w x out_h = 2500 x 14000 (lifting_3d.cpp:34-35) to build the `bev` image of segment.cpp:143,196.  Bit-exact against
+ * cv2 4.13.  dofs3d_bev_transform = transform(frame, get_mat().first) for a frame of the context's size. */
+#define DOFS3D_BEV_WIDTH 2500
+#define DOFS3D_BEV_HEIGHT 14000
+int dofs3d_warp_perspective(dofs3d_ctx* ctx, const uint8_t* img, int width, int height, int channels, const float* mat9,
+                            int out_w, int out_h, uint8_t* out);
+int dofs3d_bev_transform(dofs3d_ctx* ctx, const uint8_t* bgr_frame, uint8_t* bev_out);
+
 /* Page-locked host memory for the frame and result buffers of the streaming entry points (cudaMallocHost / cudaFreeHost,
  * so that callers need no CUDA headers); NULL on failure. */
 void* dofs3d_pinned_alloc(size_t bytes);

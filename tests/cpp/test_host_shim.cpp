@@ -87,10 +87,11 @@ int main(int argc, char** argv) {
         CHECK(sd.seg.count(root) == 1);  // every root pixel is a member of its own set
         long long h = 0;
         for (int px : sd.seg) h = (h * 1000003LL + px) % 2147483647LL;
-        // segment_scores[root] (graph.cpp:386-389) is the LATEST scored merge of the root, not the kept maximum: it can
-        // be lower than the kept score, never higher; the Python test compares it with the unchanged reference
+        // segment_scores[root] (graph.cpp:386-389) is the LATEST scored merge of the root, written before the convexity and
+        // threshold gates: it can be lower OR higher than the kept score; the Python test compares it with the unchanged
+        // reference
         const double last = forest.get_segment_best_score(root);
-        CHECK(last > 0.0 && last <= sd.score);
+        CHECK(last > 0.0);
         std::printf("segment root=%d size=%zu hash=%lld cls=%d score=%.17g move=%.17g orient=%.17g last=%.17g\n", root,
                     sd.seg.size(), h, sd.sol.cls, sd.score, sd.move, sd.sol.orient, last);
         // every absorbed root has lost its box (graph.cpp:207)

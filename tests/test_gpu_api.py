@@ -231,3 +231,91 @@ def test_negative_score_threshold_keeps_reference_semantics(dofs, port):
     from test_gpu_parity import run_and_compare
     fields = [random_flow(61 + k, 160, 96, scale=4.0) for k in range(2)]
     assert run_and_compare(dofs, port, fields, min_size=60, score_threshold=-0.5) > 0
+
+
+def test_kernel_variants_are_bit_identical(dofs, monkeypatch):
+    """The A/B knobs select another staging of the same arithmetic: the shared-memory tiled pyramid levels against the
+    per-thread kernel, the TMA (bulk copy) staged flow blur against LDG -> STS staging, the relabel pass folded into
+    the Boruvka pixel kernel against the separate pass.  Results must not change by a bit."""
+    from denseopticalflowsegmentation3d_b200 import synth
+    W, H, n = 328, 190, 2      # not a multiple of the tile sizes; W a multiple of 4 (word-aligned fast path taken)
+    fr = synth.frames(21, 6, 0, n + 1, W, H)
+    fr_odd = np.ascontiguousarray(fr[:, :, :-1])   # W = 327: every fast path falls back
+
+    def run(frames):
+        w = frames.shape[2]
+        p = dofs.default_params()
+        p.min_size = 150
+        with dofs.Context(w, H, max_pairs=n, params=p) as c:
+            g = c.gray(frames)
+            f = c.flow(g[:-1], g[1:])
+            out = c.segment(f, already_blurred=False, want_blurred=True)
+        return f, out
+
+    base = {k: run(v) for k, v in (("even", fr), ("odd", fr_odd))}
+    for knob, val in (("DOFS3D_PYR_UNTILED", "1"), ("DOFS3D_BLUR_TMA", "0"), ("DOFS3D_BOR_FOLD", "1")):
+        monkeypatch.setenv(knob, val)
+        for k, v in (("even", fr), ("odd", fr_odd)):
+            f, out = run(v)
+            assert np.array_equal(f, base[k][0]), (knob, k, "flow")
+            assert np.array_equal(out["flow_blurred"], base[k][1]["flow_blurred"]), (knob, k, "blur")
+            assert np.array_equal(out["labels"], base[k][1]["labels"]), (knob, k, "labels")
+            for a, b in zip(out["boxes"], base[k][1]["boxes"]):
+                assert a.tobytes() == b.tobytes()
+        monkeypatch.delenv(knob)
+
+
+@pytest.mark.parametrize("name", ["synth_crop", "blocks_8", "blocks_4", "ties", "thin"])
+def test_fh_mode_equals_reference_python_golden(dofs, name):
+    """the Felzenszwalb adaptive-threshold mode (graph.py:156-177) on the device against outputs of the
+    reference's own Python (tests/golden/fh_cases.npz, tools/make_golden_fh.py): root id of every pixel identical, after
+    the whole of segment_graph_flow and after its first two passes (= segment_graph)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fh_cases.npz"))
+    f = g[name + "_flow"]
+    K, ms, nb = g[name + "_params"]
+    H, W = f.shape[:2]
+    p = dofs.default_params()
+    p.neighbors = int(nb)
+    with dofs.Context(W, H, params=p) as c:
+        lab3, n3 = c.segment_fh(f, K, int(ms), int(nb), stage=3)
+        lab2, n2 = c.segment_fh(f, K, int(ms), int(nb), stage=2)
+    assert np.array_equal(lab3, g[name + "_labels"]) and n3 == len(np.unique(lab3))
+    assert np.array_equal(lab2, g[name + "_labels_stage2"]) and n2 == len(np.unique(lab2))
+
+
+def test_fh_mode_equals_oracle_on_a_real_flow_field(dofs, golden_pair):
+    """The repo's own frame pair (640x360, 918 602 edges) through the Felzenszwalb mode: device == CPU restatement."""
+    from oracle import fh
+    fb = np.ascontiguousarray(golden_pair["flow_blurred"]) * np.float32(3.0)
+    H, W = fb.shape[:2]
+    with dofs.Context(W, H) as c:
+        c.set_timing(True)
+        lab, n = c.segment_fh(fb, 10.0, 100, 8)
+        t = c.timing()
+    want, wn = fh.segment_flow(fb, 10.0, 100, 8)
+    assert n == wn and np.array_equal(lab, want) and n > 1
+    print("Felzenszwalb mode 640x360: %d components; device ms %s" % (n, {k: round(v[0], 2) for k, v in t.items()}))
+
+
+def test_bev_warp_equals_cv2(dofs, golden_pair):
+    """SURVEY.md 8f.3: the reference's transform() = cv::warpPerspective(INTER_CUBIC, BORDER_REPLICATE) to 2500 x 14000,
+    bit-exact against cv2 live, plus small ragged cases (1 and 3 channels, replicated borders)."""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(2)
+    img = cv2.GaussianBlur(rng.integers(0, 256, (360, 640, 3), dtype=np.uint8), (0, 0), 2.0)
+    with dofs.Context(640, 360) as c:
+        persp = np.array(list(dofs.default_params().persp), np.float32).reshape(3, 3)
+        c.set_timing(True)
+        bev = c.bev_transform(img)
+        ms = c.timing()["bev.warp"][0]
+        ref = cv2.warpPerspective(img, persp, (2500, 14000), flags=cv2.INTER_CUBIC, borderMode=cv2.BORDER_REPLICATE)
+        assert bev.shape == ref.shape and np.array_equal(bev, ref)
+        print("BEV warp 2500x14000x3: %.3f ms on the device = %.0f GB/s of output" % (ms, ref.size / ms / 1e6))
+        src = np.float32([[50, 70], [20, 30], [75, 30], [150, 70]])
+        dst = np.float32([[20, 300], [20, 40], [180, 40], [180, 300]])
+        M = cv2.getPerspectiveTransform(src, dst).astype(np.float32)
+        small = np.ascontiguousarray(img[:90, :160])
+        for im, (ow, oh) in ((small, (220, 340)), (np.ascontiguousarray(small[..., 1]), (101, 77)), (small, (67, 33))):
+            want = cv2.warpPerspective(im, M, (ow, oh), flags=cv2.INTER_CUBIC, borderMode=cv2.BORDER_REPLICATE)
+            assert np.array_equal(c.warp_perspective(im, M, ow, oh), want)
