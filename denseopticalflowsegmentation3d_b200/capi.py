@@ -89,7 +89,7 @@ def runs_to_labels(runs, n_runs, n_pixels):
 SYMBOLS = [
     "dofs3d_process_ex", "dofs3d_process_ex_dev", "dofs3d_segment_ex", "dofs3d_stream_begin", "dofs3d_stream_submit",
     "dofs3d_stream_collect", "dofs3d_fh_default_params", "dofs3d_segment_fh", "dofs3d_warp_perspective",
-    "dofs3d_bev_transform", "dofs3d_node_state", "dofs3d_scored_merges", "dofs3d_pinned_alloc", "dofs3d_pinned_free",
+    "dofs3d_bev_transform", "dofs3d_render", "dofs3d_pack_boxes_dev", "dofs3d_node_state", "dofs3d_scored_merges", "dofs3d_pinned_alloc", "dofs3d_pinned_free",
     "dofs3d_default_params", "dofs3d_params_for_size", "dofs3d_create", "dofs3d_destroy", "dofs3d_sync", "dofs3d_last_error", "dofs3d_stream",
     "dofs3d_launch_count", "dofs3d_device_bytes", "dofs3d_gray", "dofs3d_gray_dev", "dofs3d_flow", "dofs3d_blur",
     "dofs3d_segment", "dofs3d_paint", "dofs3d_lift", "dofs3d_edges_sorted", "dofs3d_process", "dofs3d_process_dev",
@@ -153,6 +153,8 @@ def load_library():
     L.dofs3d_segment_fh.argtypes = [vp, fp, C.POINTER(FhParams), ip, ip]
     L.dofs3d_warp_perspective.argtypes = [vp, u8p, C.c_int, C.c_int, C.c_int, fp, C.c_int, C.c_int, u8p]
     L.dofs3d_bev_transform.argtypes = [vp, u8p, u8p]
+    L.dofs3d_pack_boxes_dev.argtypes = [vp, C.c_int, vp, C.c_int, ip]
+    L.dofs3d_render.argtypes = [vp, C.c_int, C.c_double, u8p]
     L.dofs3d_pinned_alloc.argtypes = [C.c_size_t]
     L.dofs3d_pinned_alloc.restype = C.c_void_p
     L.dofs3d_pinned_free.argtypes = [vp]
@@ -261,6 +263,12 @@ class Context:
             bgr = np.ascontiguousarray(bgr, np.uint8).reshape(n_pairs, self.H, self.W, 3)
         self._ck(self.L.dofs3d_paint(self.h, n_pairs, float(min_score), _ptr(painted), _ptr(bgr)))
         return painted, bgr
+
+    def render(self, bgr_frames, min_score=0.7):
+        """plot_best_segments_simple's returned frame for the results of the last segment/process call."""
+        fr = np.array(bgr_frames, np.uint8, copy=True).reshape(-1, self.H, self.W, 3)
+        self._ck(self.L.dofs3d_render(self.h, fr.shape[0], float(min_score), _ptr(fr)))
+        return fr
 
     def lift(self, direction, bbox, cls):
         d = np.ascontiguousarray(direction, np.float32).reshape(-1, 2)
@@ -416,6 +424,9 @@ class Context:
     # ---- raw device-pointer entry points (ints are device addresses, e.g. torch.Tensor.data_ptr()) ----
     def synth_frames_dev(self, seed, n_objects, first_frame, n_frames, d_bgr_ptr):
         self._ck(self.L.dofs3d_synth_frames_dev(self.h, seed, n_objects, first_frame, n_frames, C.c_void_p(d_bgr_ptr)))
+
+    def pack_boxes_dev(self, n_pairs, d_out, capacity, d_total):
+        self._ck(self.L.dofs3d_pack_boxes_dev(self.h, n_pairs, C.c_void_p(d_out), capacity, C.c_void_p(d_total)))
 
     def process_ex_dev(self, d_bgr_ptr, n_frames, outputs):
         self._ck(self.L.dofs3d_process_ex_dev(self.h, C.c_void_p(d_bgr_ptr), n_frames, C.byref(outputs)))

@@ -18,6 +18,7 @@
 
 #include "dofs_bev.cuh"
 #include "dofs_common.cuh"
+#include "dofs_draw.cuh"
 #include "dofs_flow.cuh"
 #include "dofs_lift.cuh"
 #include "dofs_fh.cuh"
@@ -156,10 +157,12 @@ struct dofs3d_ctx {
     dofs3d_run* runs = nullptr;       // [F][runs_cap], allocated on the first run-length call
     int runs_cap = 0;
     dofs3d_stats* stats = nullptr;
+    int stride_blocks_per_sm = 16;    // grid of the grid-stride kernels (DOFS3D_STRIDE_BLOCKS): blocks per SM over the whole batch
     int carveout = -1;                // DOFS3D_CARVEOUT: preferred shared-memory carveout (percent) of every kernel; -1 = the driver's choice
     std::vector<const void*> carveout_done;
     bool bor_fold = false;            // A/B knob: DOFS3D_BOR_FOLD=1 folds the Boruvka relabel pass into the pixel kernel
     bool blur_tma = true;             // A/B knob: DOFS3D_BLUR_TMA=0 stages the blur tiles with LDG -> STS instead of bulk copies
+    u8* render_seg = nullptr;         // [F][N][3] the painted copy of dofs3d_render, allocated on first use
     double* rcp_table = nullptr;      // [RCP_TABLE] 1.0 / n for the replay of small sets
     int* sticky = nullptr;            // device: STICKY_* bits of every call since the last dofs3d_sync
     int* h_sticky = nullptr;          // pinned copy, refreshed after every call
@@ -230,7 +233,7 @@ int dalloc(dofs3d_ctx* ctx, T** p, size_t count) {
 inline dim3 grid1(size_t n, int threads, int frames) { return dim3((unsigned)((n + threads - 1) / threads), frames); }
 // small fixed grid for the grid-stride kernels: about 16 blocks per SM over the whole batch
 inline dim3 grid_stride(const dofs3d_ctx* ctx, int frames) {
-    const unsigned total = 148u * 16u;
+    const unsigned total = 148u * (unsigned)ctx->stride_blocks_per_sm;
     const unsigned per_frame = std::max(1u, std::min(total / (unsigned)frames, (unsigned)((ctx->N + SEG_THREADS - 1) / SEG_THREADS)));
     return dim3(per_frame, frames);
 }
@@ -900,6 +903,7 @@ int dofs3d_create(dofs3d_ctx** out, int device, int width, int height, int max_p
     if (const char* e = getenv("DOFS3D_FORCE_TIME_FALLBACK")) ctx->force_time_fallback = atoi(e) != 0;
     if (const char* e = getenv("DOFS3D_BLUR_TMA")) ctx->blur_tma = atoi(e) != 0;
     if (const char* e = getenv("DOFS3D_BOR_FOLD")) ctx->bor_fold = atoi(e) != 0;
+    if (const char* e = getenv("DOFS3D_STRIDE_BLOCKS")) ctx->stride_blocks_per_sm = std::max(1, std::min(64, atoi(e)));
     if (const char* e = getenv("DOFS3D_CARVEOUT")) ctx->carveout = std::max(-1, std::min(100, atoi(e)));
     CK(cudaMallocHost(&ctx->h_sticky, sizeof(int)));
     *ctx->h_sticky = 0;
@@ -938,7 +942,7 @@ static int ensure_flow(dofs3d_ctx* ctx) {
         size_t fbytes = 0;
         int rc = farneback_alloc(&ctx->fb, width, height, (int)F, fc, &fbytes);
         ctx->bytes += (long long)fbytes;
-        if (const char* e = getenv("DOFS3D_PYR_UNTILED")) ctx->fb.pyr_untiled = atoi(e) != 0;
+        if (const char* e = getenv("DOFS3D_PYR_TILED")) ctx->fb.pyr_untiled = atoi(e) == 0;
         if (ctx->carveout >= 0) farneback_set_carveout(ctx->carveout);
         if (rc) {
             ctx->err = farneback_error(rc);
@@ -1148,6 +1152,38 @@ int dofs3d_paint(dofs3d_ctx* ctx, int n_pairs, double min_score, int32_t* painte
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(painted_out, d_painted, px * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
     if (bgr_inout) CK(cudaMemcpyAsync(bgr_inout, d_bgr, px * 3, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------- render
+int dofs3d_render(dofs3d_ctx* ctx, int n_pairs, double min_score, uint8_t* bgr_inout) {
+    int rc = check_batch(ctx, n_pairs);
+    if (rc) return rc;
+    if (!bgr_inout) return DOFS3D_ERR_ARG;
+    if (n_pairs == 0) return 0;
+    if ((rc = ensure_flow(ctx))) return rc;  // ctx->bgr: the frames
+    const size_t px = (size_t)ctx->N * n_pairs;
+    if (!ctx->render_seg) DA(ctx->render_seg, (size_t)ctx->F * ctx->N * 3);
+    int32_t* d_painted = reinterpret_cast<int32_t*>(ctx->sel_box);  // dead after the labels were written
+    CK(cudaMemcpyAsync(ctx->bgr, bgr_inout, px * 3, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->render_seg, ctx->bgr, px * 3, cudaMemcpyDeviceToDevice, ctx->stream));  // seg = frame.clone()
+    timer_begin(ctx);
+    const dim3 gN = grid1(ctx->N, SEG_THREADS, n_pairs);
+    if (ctx->labels_fmt == DOFS3D_LABELS_I32)
+        LAUNCH(ctx, (k_paint<dofs3d_box, int>), gN, SEG_THREADS, 0, ctx->labels, ctx->boxes, ctx->box_cap, ctx->N, min_score,
+               d_painted, ctx->render_seg);
+    else
+        LAUNCH(ctx, (k_paint<dofs3d_box, u16>), gN, SEG_THREADS, 0, reinterpret_cast<const u16*>(ctx->labels), ctx->boxes,
+               ctx->box_cap, ctx->N, min_score, d_painted, ctx->render_seg);
+    LAUNCH(ctx, k_cube_lines<dofs3d_box>, dim3((ctx->box_cap * 12 + 127) / 128, n_pairs), 128, 0, ctx->boxes,
+           ctx->counters + CNT_BOXES * ctx->F, ctx->box_cap, d_painted, ctx->bgr, ctx->render_seg, ctx->W, ctx->H, min_score);
+    const double opacity = 2.0 / 5.0;  // draw.cpp:157
+    LAUNCH(ctx, k_add_weighted, dim3((unsigned)((px * 3 / 4 + 256) / 256)), 256, 0, ctx->bgr, ctx->render_seg, px * 3,
+           (float)(1.0 - opacity), (float)opacity);
+    mark(ctx, "render");
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(bgr_inout, ctx->bgr, px * 3, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return 0;
 }
@@ -1483,6 +1519,20 @@ int dofs3d_warp_perspective(dofs3d_ctx* ctx, const uint8_t* img, int width, int 
 int dofs3d_bev_transform(dofs3d_ctx* ctx, const uint8_t* bgr_frame, uint8_t* bev_out) {
     if (!ctx) return DOFS3D_ERR_ARG;
     return dofs3d_warp_perspective(ctx, bgr_frame, ctx->W, ctx->H, 3, ctx->prm.persp, DOFS3D_BEV_WIDTH, DOFS3D_BEV_HEIGHT, bev_out);
+}
+
+int dofs3d_pack_boxes_dev(dofs3d_ctx* ctx, int n_pairs, dofs3d_box* d_out, int capacity, int32_t* d_total_out) {
+    int rc = check_batch(ctx, n_pairs);
+    if (rc) return rc;
+    if (!d_out || !d_total_out || capacity < 0) return DOFS3D_ERR_ARG;
+    if (n_pairs == 0) {
+        CK(cudaMemsetAsync(d_total_out, 0, sizeof(int32_t), ctx->stream));
+        return 0;
+    }
+    LAUNCH(ctx, k_pack_boxes<dofs3d_box>, dim3(n_pairs), 128, 0, ctx->boxes, ctx->counters + CNT_BOXES * ctx->F, ctx->box_cap,
+           n_pairs, d_out, capacity, d_total_out);
+    CK(cudaGetLastError());
+    return 0;
 }
 
 void* dofs3d_pinned_alloc(size_t bytes) {

@@ -86,7 +86,11 @@ struct FlowBuffers {
     float* M = nullptr;      // [F][N][5]
     float2* flowA = nullptr; // [F][N]
     float2* flowB = nullptr; // [F][N]
-    bool pyr_untiled = false;            // test / A-B knob (DOFS3D_PYR_UNTILED=1): the per-thread pyramid kernel
+    bool pyr_untiled = true;             // A/B knob (DOFS3D_PYR_TILED=1 selects k_pyr_level_tiled): measured on the B200, the
+                                         // tiled kernel is 29 % faster alone (pyramid 1.34 -> 0.95 ms per 32 pairs) and costs
+                                         // 10 % of the throughput when six contexts share the GPU (964 -> 862 pairs/s): its
+                                         // 40 KB of shared memory per block keeps the other contexts' kernels off the SM while a
+                                         // latency-bound kernel runs; the per-thread kernel shares the SM with them
     float* R_carry = nullptr;            // polynomial expansion of ONE frame at every level (streaming: the last frame of a chunk)
     size_t carry_off[FLOW_MAX_LEVELS];   // float offset of level k in R_carry
 };

@@ -2064,6 +2064,29 @@ k_lift_problems(const float2* __restrict__ dir, const int4* __restrict__ bbox, c
     if (!s.has_rect) out[i].cls = c;
 }
 
+// The boxes of a batch as one dense list (frame after frame, each frame's boxes in root order) for the gather of
+// per-frame results over NCCL: one block per frame finds its offset from the counts of the frames before it.
+template <typename Box>
+__global__ void __launch_bounds__(128)
+k_pack_boxes(const Box* __restrict__ boxes, const int* __restrict__ n_boxes, int box_cap, int n_frames, Box* __restrict__ out,
+             int capacity, int* __restrict__ total_out) {
+    const int frame = blockIdx.x;
+    int before = 0, total = 0;
+    for (int f = 0; f < n_frames; ++f) {
+        const int c = min(n_boxes[f], box_cap);
+        if (f < frame) before += c;
+        total += c;
+    }
+    if (frame == 0 && threadIdx.x == 0) *total_out = total;
+    const int mine = min(n_boxes[frame], box_cap);
+    // a box is 27 8-byte words
+    constexpr int WORDS = sizeof(Box) / 8;
+    const unsigned long long* src = reinterpret_cast<const unsigned long long*>(boxes + (size_t)frame * box_cap);
+    unsigned long long* dst = reinterpret_cast<unsigned long long*>(out + before);
+    const int keep = max(0, min(mine, capacity - before));
+    for (int i = threadIdx.x; i < keep * WORDS; i += blockDim.x) dst[i] = src[i];
+}
+
 #define STICKY_INTERNAL 1    // Boruvka did not converge (non-finite flow) or a sort look-back timed out
 #define STICKY_CANDIDATES 2  // candidate queue overflow
 #define STICKY_BOXES 4       // more boxes than the caller's max_boxes / the box list

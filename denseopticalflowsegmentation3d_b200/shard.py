@@ -54,3 +54,20 @@ def gather_boxes(n_boxes, boxes, device=None, group=None):
         counts.append(all_cnt[r][:nf].cpu().numpy())
         out.append(all_raw[r][:nb * BOX_DTYPE.itemsize].cpu().numpy().view(BOX_DTYPE).copy())
     return counts, out
+
+
+def gather_packed(counts, boxes_u8, group=None):
+    """Gather of per-frame results straight from device buffers (no host round trip): `counts` int32 [C] = boxes held by
+    each of this rank's C contexts, `boxes_u8` uint8 [C][cap * 216] = their dense box lists (dofs3d_pack_boxes_dev).
+    One fixed-size all_gather of the counts, one of the boxes trimmed to the largest count of any context of any rank.
+    Returns (all_counts int32 [world][C], all_boxes uint8 [world][C][m * 216]) on the tensors' device."""
+    world = dist.get_world_size(group)
+    itemsize = BOX_DTYPE.itemsize
+    all_counts = torch.empty((world,) + tuple(counts.shape), dtype=counts.dtype, device=counts.device)
+    dist.all_gather(list(all_counts.unbind(0)), counts.contiguous(), group=group)
+    m = max(int(all_counts.max().item()), 1)
+    m = min(m, boxes_u8.shape[1] // itemsize)
+    send = boxes_u8[:, :m * itemsize].contiguous()
+    all_boxes = torch.empty((world,) + tuple(send.shape), dtype=send.dtype, device=send.device)
+    dist.all_gather(list(all_boxes.unbind(0)), send, group=group)
+    return all_counts, all_boxes

@@ -145,8 +145,15 @@ int dofs3d_segment(dofs3d_ctx* ctx, const float* flow, int already_blurred, int 
  * segment/process call of this context: segments are painted in ascending root order when score > min_score, later over
  * earlier (draw.cpp:120-147).  painted_out [n][H][W] = index of the box whose colour the pixel ends with, -1 if unpainted.
  * bgr_inout (optional, [n][H][W][3]) receives the class colour of draw.cpp:130-141 in the painted pixels (the "seg"
- * image before blending); cube wireframes are not drawn. */
+ * image before the cubes and the blending; dofs3d_render is the whole display). */
 int dofs3d_paint(dofs3d_ctx* ctx, int n_pairs, double min_score, int32_t* painted_out, uint8_t* bgr_inout);
+
+/* The frame plot_best_segments_simple (draw.cpp:102-160) returns, for the n_pairs results of the LAST segment/process call:
+ * bgr_inout [n][H][W][3] holds the frames to draw on (segment.cpp:166 passes the second frame of the pair) and receives
+ * the result: segments with score > min_score painted in ascending root order (draw.cpp:120-147), the wireframe cube of
+ * each (draw_cube, draw.cpp:85-100: cv::line, colour (255,0,0), thickness 1) on the frame and on the painted copy, both
+ * blended with cv::addWeighted(frame, 3/5, seg, 2/5) (draw.cpp:157-158).  Bit-exact against the same calls of cv2 4.13. */
+int dofs3d_render(dofs3d_ctx* ctx, int n_pairs, double min_score, uint8_t* bgr_inout);
 
 /* get_bottom_variants (lifting_3d.cpp:350-439) for n independent (direction, box, cls) problems:
  * dir2 [n][2], bbox4 [n][4] = xmin,ymin,xmax,ymax, cls [n].  out[i].score = (w_error+h_error)/2,
@@ -250,6 +257,11 @@ int dofs3d_segment_fh(dofs3d_ctx* ctx, const float* flow, const dofs3d_fh_params
 int dofs3d_warp_perspective(dofs3d_ctx* ctx, const uint8_t* img, int width, int height, int channels, const float* mat9,
                             int out_w, int out_h, uint8_t* out);
 int dofs3d_bev_transform(dofs3d_ctx* ctx, const uint8_t* bgr_frame, uint8_t* bev_out);
+
+/* The boxes of the LAST segment/process call as one dense DEVICE array (frame after frame, root order inside a frame) and
+ * their number: the payload of the NCCL gather of per-frame results without a host round trip.
+ * Asynchronous on the context's stream.  Boxes beyond `capacity` are dropped (*d_total_out still counts them). */
+int dofs3d_pack_boxes_dev(dofs3d_ctx* ctx, int n_pairs, dofs3d_box* d_out, int capacity, int32_t* d_total_out);
 
 /* Page-locked host memory for the frame and result buffers of the streaming entry points (cudaMallocHost / cudaFreeHost,
  * so that callers need no CUDA headers); NULL on failure. */

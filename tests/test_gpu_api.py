@@ -253,7 +253,7 @@ def test_kernel_variants_are_bit_identical(dofs, monkeypatch):
         return f, out
 
     base = {k: run(v) for k, v in (("even", fr), ("odd", fr_odd))}
-    for knob, val in (("DOFS3D_PYR_UNTILED", "1"), ("DOFS3D_BLUR_TMA", "0"), ("DOFS3D_BOR_FOLD", "1")):
+    for knob, val in (("DOFS3D_PYR_TILED", "1"), ("DOFS3D_BLUR_TMA", "0"), ("DOFS3D_BOR_FOLD", "1"), ("DOFS3D_STRIDE_BLOCKS", "5")):
         monkeypatch.setenv(knob, val)
         for k, v in (("even", fr), ("odd", fr_odd)):
             f, out = run(v)
@@ -319,3 +319,40 @@ def test_bev_warp_equals_cv2(dofs, golden_pair):
         for im, (ow, oh) in ((small, (220, 340)), (np.ascontiguousarray(small[..., 1]), (101, 77)), (small, (67, 33))):
             want = cv2.warpPerspective(im, M, (ow, oh), flags=cv2.INTER_CUBIC, borderMode=cv2.BORDER_REPLICATE)
             assert np.array_equal(c.warp_perspective(im, M, ow, oh), want)
+
+
+def test_render_equals_reference_display_with_cv2(dofs, golden_pair):
+    """dofs3d_render = plot_best_segments_simple (draw.cpp:102-160) — painting in ascending root order,
+    the wireframe cube of every drawn segment (draw_cube, draw.cpp:85-100), the final blend — against the same OpenCV
+    calls (cv2.line, cv2.addWeighted) issued here in the reference's order, on the repo's own pair."""
+    cv2 = pytest.importorskip("cv2")
+    from denseopticalflowsegmentation3d_b200.capi import box_pixel_sets
+    fb = golden_pair["flow_blurred"]
+    H, W = fb.shape[:2]
+    rng = np.random.default_rng(3)
+    frame = cv2.GaussianBlur(rng.integers(0, 256, (H, W, 3), dtype=np.uint8), (0, 0), 2.0)
+    for min_score in (0.7, 0.3):
+        with dofs.Context(W, H) as c:
+            out = c.segment(fb, already_blurred=True)
+            got = c.render(frame, min_score)[0]
+        boxes = out["boxes"][0]
+        psets = box_pixel_sets(out["labels"][0], boxes)
+        fr, seg = frame.copy(), frame.copy()
+        drawn = 0
+
+        def pt(v):
+            return (int(np.rint(np.float32(v[0]))), int(np.rint(np.float32(v[1]))))
+
+        for b, px in zip(boxes, psets):           # ascending root = the order of the reference's history vector
+            if not b["score"] > min_score:
+                continue
+            drawn += 1
+            seg.reshape(-1, 3)[px] = (0, 255, 0) if b["cls"] == 1 else (0, 255, 255)
+            for img in (fr, seg):
+                lo, up = b["lower_face"], b["upper_face"]
+                for i in range(4):
+                    cv2.line(img, pt(lo[i]), pt(lo[(i + 1) % 4]), (255, 0, 0), 1)
+                    cv2.line(img, pt(up[i]), pt(up[(i + 1) % 4]), (255, 0, 0), 1)
+                    cv2.line(img, pt(lo[i]), pt(up[i]), (255, 0, 0), 1)
+        want = cv2.addWeighted(fr, 1.0 - 2.0 / 5.0, seg, 2.0 / 5.0, 0)
+        assert drawn > 0 and np.array_equal(got, want), (min_score, int((got != want).sum()))

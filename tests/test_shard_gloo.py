@@ -44,6 +44,24 @@ def _worker(rank, world, port, n_pairs, out_q):
     boxes["root"] = first * 1000 + np.arange(boxes.shape[0])
     boxes["score"] = rank + 0.5
     counts, gathered = shard.gather_boxes(n_boxes, boxes)
+    # the fixed-capacity form used on the GPUs (tensors stay where they are): two "contexts" per rank
+    import torch
+    cap = 16
+    packed = torch.zeros((2, cap * BOX_DTYPE.itemsize), dtype=torch.uint8)
+    half = boxes.shape[0] // 2
+    parts = [boxes[:half], boxes[half:]]
+    for c, part in enumerate(parts):
+        packed[c, :part.nbytes] = torch.from_numpy(part.view(np.uint8).reshape(-1).copy())
+    cnt = torch.tensor([p.shape[0] for p in parts], dtype=torch.int32)
+    all_cnt, all_box = shard.gather_packed(cnt, packed)
+    for r in range(world):
+        for c in range(2):
+            k = int(all_cnt[r, c])
+            got = all_box[r, c, :k * BOX_DTYPE.itemsize].numpy().view(BOX_DTYPE)
+            assert np.all(got["score"] == r + 0.5)
+            if r == rank:
+                assert got["root"].tolist() == parts[c]["root"].tolist()
+    assert int(all_cnt.sum()) == sum(int(c.sum()) for c in counts)
     out_q.put((rank, [c.tolist() for c in counts], [g["root"].tolist() for g in gathered], [g["score"].tolist() for g in gathered],
                n_boxes.tolist(), boxes["root"].tolist()))
     dist.barrier()
