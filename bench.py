@@ -505,7 +505,7 @@ def ours(args):
 
     for c in range(NC):
         ck(ctxs[c], ctxs[c].L.dofs3d_stream_begin(ctxs[c].h))
-    host_steps(min(Wm, 2), False)
+    host_steps(min(Wm, 2), True)  # also the first collective of the communicator (channel set-up) stays out of the timing
     barrier()
     for h in host:
         h["boxes_seen"] = 0

@@ -53,8 +53,22 @@ def build_host_program(src, out):
     return out
 
 
+def build_multi_gpu_driver(out=None):
+    """examples/multi_gpu_driver.cpp: the C++ multi-GPU streaming driver (links the C ABI, the CUDA runtime and NCCL)."""
+    root = os.path.dirname(HERE)
+    out = out or os.path.join(root, "examples", "multi_gpu_driver")
+    cuda = os.path.dirname(os.path.dirname(NVCC))
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-Wall", "-I" + os.path.join(root, "include"),
+                           "-I" + os.path.join(cuda, "include"), os.path.join(root, "examples", "multi_gpu_driver.cpp"),
+                           "-o", out, "-L" + HERE, "-ldofs3d", "-L" + os.path.join(cuda, "lib64"), "-lcudart", "-lnccl",
+                           "-lpthread", "-Wl,-rpath," + HERE])
+    return out
+
+
 if __name__ == "__main__":
     build(force="--force" in sys.argv, verbose=True)
     build_host(force="--force" in sys.argv)
+    if "--examples" in sys.argv:
+        print(build_multi_gpu_driver())
     print(OUT)
     print(HOST_OUT)

@@ -84,6 +84,8 @@ struct FlowBuffers {
     float* I = nullptr;      // [2F][N]
     float* R = nullptr;      // [2F][N][5]
     float* M = nullptr;      // [F][N][5]
+    float* M2 = nullptr;     // [F][N][5] second M buffer of the fused box-filter + update-matrices iterations
+    bool fuse_um = false;    // A/B knob (DOFS3D_FLOW_FUSE=1)
     float2* flowA = nullptr; // [F][N]
     float2* flowB = nullptr; // [F][N]
     bool pyr_untiled = true;             // A/B knob (DOFS3D_PYR_TILED=1 selects k_pyr_level_tiled): measured on the B200, the
@@ -215,7 +217,7 @@ inline int farneback_alloc(FlowBuffers* fb, int W, int H, int F, const FlowConfi
         return cudaMalloc(p, b) == cudaSuccess;
     };
     if (!alloc((void**)&fb->I, 2 * F * N * sizeof(float)) || !alloc((void**)&fb->R, 2 * F * N * 5 * sizeof(float)) ||
-        !alloc((void**)&fb->M, F * N * 5 * sizeof(float)) || !alloc((void**)&fb->flowA, F * N * sizeof(float2)) ||
+        !alloc((void**)&fb->M, F * N * 5 * sizeof(float)) || !alloc((void**)&fb->M2, F * N * 5 * sizeof(float)) || !alloc((void**)&fb->flowA, F * N * sizeof(float2)) ||
         !alloc((void**)&fb->flowB, F * N * sizeof(float2)))
         return 2;
     size_t carry = 0;
@@ -232,6 +234,8 @@ inline void farneback_free(FlowBuffers* fb) {
     cudaFree(fb->I);
     cudaFree(fb->R);
     cudaFree(fb->M);
+    cudaFree(fb->M2);
+    fb->M2 = nullptr;
     cudaFree(fb->flowA);
     cudaFree(fb->flowB);
     cudaFree(fb->R_carry);
@@ -587,21 +591,12 @@ struct FlowStart {
 };
 enum { UM_FLOW = 0, UM_START = 1 };
 
-template <int MODE>
-__global__ void __launch_bounds__(256)
-k_update_matrices(const float* __restrict__ R, const float2* __restrict__ flow, float* __restrict__ M, int Wk, int Hk,
-                  PairSlots ps, FlowStart fs) {
-    const int pair = blockIdx.z;
-    const int x = blockIdx.x * 32 + (threadIdx.x & 31);
-    const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
-    if (x >= Wk || y >= Hk) return;
+// one pixel of FarnebackUpdateMatrices: the five products for pixel (x, y) of `pair` given its current flow d
+DOFS_D void update_matrices_pixel(const float* __restrict__ R, float* __restrict__ M, int Wk, int Hk, PairSlots ps, int pair,
+                                  int x, int y, float2 d) {
     const size_t npx = (size_t)Wk * Hk;
     const float* R0 = R + ((size_t)(pair + ps.first0) * npx + (size_t)y * Wk + x) * 5;
     const float* R1 = R + (size_t)(pair + ps.first1) * npx * 5;
-    float2 d;
-    if (MODE == UM_FLOW) d = flow[(size_t)pair * npx + (size_t)y * Wk + x];
-    else if (fs.prev) d = flow_upsampled(fs.prev + (size_t)pair * fs.Wp * fs.Hp, x, y, fs.Wp, fs.Hp, Wk, Hk, fs.mul);
-    else d = make_float2(0.f, 0.f);
     const float dx = d.x, dy = d.y;
     float fx = xfadd((float)x, dx), fy = xfadd((float)y, dy);
     const int x1 = (int)floorf(fx), y1 = (int)floorf(fy);
@@ -648,6 +643,22 @@ k_update_matrices(const float* __restrict__ R, const float2* __restrict__ flow, 
     out[2] = xfadd(xfmul(r5, r5), xfmul(r6, r6));
     out[3] = xfadd(xfmul(r4, r2), xfmul(r6, r3));
     out[4] = xfadd(xfmul(r6, r2), xfmul(r5, r3));
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256)
+k_update_matrices(const float* __restrict__ R, const float2* __restrict__ flow, float* __restrict__ M, int Wk, int Hk,
+                  PairSlots ps, FlowStart fs) {
+    const int pair = blockIdx.z;
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= Wk || y >= Hk) return;
+    const size_t npx = (size_t)Wk * Hk;
+    float2 d;
+    if (MODE == UM_FLOW) d = flow[(size_t)pair * npx + (size_t)y * Wk + x];
+    else if (fs.prev) d = flow_upsampled(fs.prev + (size_t)pair * fs.Wp * fs.Hp, x, y, fs.Wp, fs.Hp, Wk, Hk, fs.mul);
+    else d = make_float2(0.f, 0.f);
+    update_matrices_pixel(R, M, Wk, Hk, ps, pair, x, y, d);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -768,8 +779,17 @@ k_box_solve(const float* __restrict__ M, float2* __restrict__ flow, int Wk, int 
 DOFS_D constexpr int bs7_pad(int i) { return i + (i >> 3); }
 
 // horizontal sliding windows and the 2x2 solve for the nb rows whose vertical sums are in s_v (rows yb .. yb+nb-1)
+// FUSE: the solved flow of a pixel is not stored; FarnebackUpdateMatrices of the NEXT iteration is applied to it at once
+// (it only needs the pixel's own new flow) and its five products go to the other M buffer.
+struct Bs7Fuse {
+    const float* R;  // polynomial expansions
+    float* M_out;    // the M buffer the next iteration reads
+    PairSlots ps;
+};
+
+template <bool FUSE>
 DOFS_D void bs7_rows(const double* s_v, double* s_h, float2* __restrict__ flow, int pair, int x0, int yb, int nb, int Wk, int Hk,
-                     double scale) {
+                     double scale, const Bs7Fuse& fu) {
     constexpr int m = BS7_M;
     const int e = threadIdx.x;
     const int hg = e & 7, hr = (e >> 3) & 7, hc = e >> 6;  // work item = (group of 8 outputs, row, channel), groups fastest
@@ -803,13 +823,15 @@ DOFS_D void bs7_rows(const double* s_v, double* s_h, float2* __restrict__ flow, 
         const double idet = xddiv(1.0, xdadd(xdsub(xdmul(g11, g22), xdmul(g12, g12)), 1e-3));
         const float u = (float)xdmul(xdsub(xdmul(g11, h2), xdmul(g12, h1)), idet);
         const float w = (float)xdmul(xdsub(xdmul(g22, h1), xdmul(g12, h2)), idet);
-        flow[((size_t)pair * Hk + y) * Wk + x] = make_float2(u, w);
+        if (FUSE) update_matrices_pixel(fu.R, fu.M_out, Wk, Hk, fu.ps, pair, x, y, make_float2(u, w));
+        else flow[((size_t)pair * Hk + y) * Wk + x] = make_float2(u, w);
     }
     __syncthreads();
 }
 
+template <bool FUSE>
 __global__ void __launch_bounds__(BS7_THREADS, BS7_BLOCKS)
-k_box_solve7(const float* __restrict__ M, float2* __restrict__ flow, int Wk, int Hk) {
+k_box_solve7(const float* __restrict__ M, float2* __restrict__ flow, int Wk, int Hk, Bs7Fuse fu) {
     extern __shared__ __align__(16) unsigned char bx7_smem[];
     double* s_v = reinterpret_cast<double*>(bx7_smem);  // [BS7_SUB][5][BS7_VC] (+ padding to BS7_VR)
     double* s_h = s_v + BS7_SUB * BS7_VR;               // [BS7_SUB][5][BS7_HC]
@@ -850,7 +872,7 @@ k_box_solve7(const float* __restrict__ M, float2* __restrict__ flow, int Wk, int
                 s_v[r * BS7_VR + v_at] = s;
             }
         }
-        bs7_rows(s_v, s_h, flow, pair, x0, yb, nb, Wk, Hk, scale);
+        bs7_rows<FUSE>(s_v, s_h, flow, pair, x0, yb, nb, Wk, Hk, scale, fu);
     }
 }
 
@@ -865,7 +887,8 @@ inline int box_solve_threads(int m) { return (((BS_COLS + 2 * m) * 5 + 31) / 32)
 inline int farneback_set_attributes() {
     if (cudaFuncSetAttribute(k_box_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)box_solve_smem(63 / 2)) != cudaSuccess)
         return 3;
-    if (cudaFuncSetAttribute(k_box_solve7, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BS7_SMEM) != cudaSuccess) return 3;
+    if (cudaFuncSetAttribute(k_box_solve7<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BS7_SMEM) != cudaSuccess) return 3;
+    if (cudaFuncSetAttribute(k_box_solve7<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BS7_SMEM) != cudaSuccess) return 3;
     return 0;
 }
 
@@ -873,7 +896,8 @@ inline int farneback_set_attributes() {
 inline void farneback_set_carveout(int pct) {
     const void* ks[] = {(const void*)k_bgr2gray, (const void*)k_pyr_level0, (const void*)k_pyr_level, (const void*)k_pyr_level_tiled,
                         (const void*)k_polyexp<5>, (const void*)k_polyexp<0>, (const void*)k_update_matrices<UM_FLOW>,
-                        (const void*)k_update_matrices<UM_START>, (const void*)k_box_solve, (const void*)k_box_solve7};
+                        (const void*)k_update_matrices<UM_START>, (const void*)k_box_solve, (const void*)k_box_solve7<false>,
+                        (const void*)k_box_solve7<true>};
     for (const void* k : ks) cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
 }
 
@@ -947,16 +971,34 @@ inline int farneback_run(FlowBuffers& fb, const u8* d_gray0, const u8* d_gray1, 
         k_update_matrices<UM_START><<<g_pair, blk, 0, stream>>>(fb.R, cur, fb.M, L.w, L.h, ps, start);
         FLOW_MARK(st, "flow.update_matrices");
         st->launches += 3;
+        float* M_in = fb.M;
+        float* M_next = fb.M2;
         for (int it = 0; it < fb.cfg.iters; ++it) {
+            const bool last = it == fb.cfg.iters - 1;
+            const dim3 g7((L.w + BS7_COLS - 1) / BS7_COLS, (L.h + BS7_ROWS - 1) / BS7_ROWS, n);
+            if (m == BS7_M && fb.fuse_um && !last) {
+                // box filter + solve + the next iteration's update-matrices in one kernel: the flow of this iteration is
+                // never stored, its M goes to the other buffer (blocks still read the halo of the current one)
+                Bs7Fuse fu;
+                fu.R = fb.R;
+                fu.M_out = M_next;
+                fu.ps = ps;
+                k_box_solve7<true><<<g7, BS7_THREADS, BS7_SMEM, stream>>>(M_in, cur, L.w, L.h, fu);
+                st->launches++;
+                FLOW_MARK(st, k == 0 ? "flow.box_solve.L0" : "flow.box_solve");
+                float* t = M_in;
+                M_in = M_next;
+                M_next = t;
+                continue;
+            }
             if (m == BS7_M)
-                k_box_solve7<<<dim3((L.w + BS7_COLS - 1) / BS7_COLS, (L.h + BS7_ROWS - 1) / BS7_ROWS, n), BS7_THREADS, BS7_SMEM,
-                               stream>>>(fb.M, cur, L.w, L.h);
+                k_box_solve7<false><<<g7, BS7_THREADS, BS7_SMEM, stream>>>(M_in, cur, L.w, L.h, Bs7Fuse());
             else
-                k_box_solve<<<g_box, box_solve_threads(m), bx_smem, stream>>>(fb.M, cur, L.w, L.h, m);
+                k_box_solve<<<g_box, box_solve_threads(m), bx_smem, stream>>>(M_in, cur, L.w, L.h, m);
             st->launches++;
             FLOW_MARK(st, k == 0 ? "flow.box_solve.L0" : "flow.box_solve");
-            if (it < fb.cfg.iters - 1) {
-                k_update_matrices<UM_FLOW><<<g_pair, blk, 0, stream>>>(fb.R, cur, fb.M, L.w, L.h, ps, start);
+            if (!last) {
+                k_update_matrices<UM_FLOW><<<g_pair, blk, 0, stream>>>(fb.R, cur, M_in, L.w, L.h, ps, start);
                 st->launches++;
                 FLOW_MARK(st, "flow.update_matrices");
             }

@@ -1347,6 +1347,9 @@ DOFS_D void replay_gate(const ReplayArgs& A, int frame, u32 r, u32 time, int s, 
 // the thread of their first event: Forest::merge's state update (graph.cpp:184-208) and the gates of every merge, one
 // pass over the events instead of five.  The head of a longer chain flags its root and queues the chain for the
 // scan / operands / serial / gates kernels below, which skip everything else.
+#ifndef REPLAY_PIPELINED
+#define REPLAY_PIPELINED 0
+#endif
 #ifndef REPLAY_SHORT_BLOCKS
 #define REPLAY_SHORT_BLOCKS 8  // bound by the latency of the random state gathers: full occupancy (32 registers)
 #endif
@@ -1373,6 +1376,38 @@ k_replay_short(ReplayArgs A, int wave) {
         float2 f = make_float2(r0.fx, r0.fy);
         ushort4 bb = r0.bbox;
         int j = i;
+#if REPLAY_PIPELINED
+        // the state of the NEXT absorbed root is requested before the arithmetic of this event: the chain of dependent
+        // loads (key -> loser id -> its state, a random gather) then runs under the division-free mean update and the gates
+        RootState ra = root_absorbed(A, fo, A.ev_loser[fo + j], wave);
+        for (;;) {
+            const int jn = j + 1;
+            u64 kn = 0;
+            bool same = false;
+            RootState rn = ra;
+            if (jn < w1) {
+                kn = key[jn];
+                same = ev_chain(kn, A.eb) == chain;
+                if (same) rn = root_absorbed(A, fo, A.ev_loser[fo + jn], wave);
+            }
+            const int sa = ra.size;
+            const float fsa = (float)sa;
+            const int s_after = s + sa;
+            const double inv = size_reciprocal(A, s_after);
+            f.x = merge_mean(xfmul(ra.fx, fsa), f.x, (float)s, inv);
+            f.y = merge_mean(xfmul(ra.fy, fsa), f.y, (float)s, inv);
+            s = s_after;
+            bb.x = min(bb.x, ra.bbox.x);
+            bb.y = min(bb.y, ra.bbox.y);
+            bb.z = max(bb.z, ra.bbox.z);
+            bb.w = max(bb.w, ra.bbox.w);
+            replay_gate(A, frame, r, ev_time(k, A.eb), s, f, bb);
+            j = jn;
+            if (!same) break;
+            ra = rn;
+            k = kn;
+        }
+#else
         for (;;) {
             const RootState ra = root_absorbed(A, fo, A.ev_loser[fo + j], wave);
             const int sa = ra.size;
@@ -1394,6 +1429,7 @@ k_replay_short(ReplayArgs A, int wave) {
             k = key[j];
             if (ev_chain(k, A.eb) != chain) break;
         }
+#endif
         root_store(&A.rstate[fo + r], s, f, bb);
         if (j - i > A.longest_chain[frame]) atomicMax(&A.longest_chain[frame], j - i);
     }

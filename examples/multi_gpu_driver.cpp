@@ -144,6 +144,36 @@ int main(int argc, char** argv) {
     std::vector<int> devs(n_gpus);
     for (int g = 0; g < n_gpus; ++g) devs[g] = g;
     NCCL_OK(ncclCommInitAll(comms.data(), n_gpus, devs.data()));
+    // warm-up (untimed): the first chunk of a context allocates its flow and staging buffers, the first collective of a
+    // communicator sets up its channels
+    for (Gpu& G : gpus) {
+        CUDA_OK(cudaSetDevice(G.device));
+        for (Lane& L : G.lanes) {
+            dofs3d_outputs o;
+            std::memset(&o, 0, sizeof o);
+            o.label_format = DOFS3D_LABELS_RLE;
+            o.labels = L.slot[0].runs;
+            o.n_runs = L.slot[0].n_runs;
+            o.max_runs = max_runs;
+            o.boxes = L.slot[0].boxes;
+            o.n_boxes = L.slot[0].n_boxes;
+            o.max_boxes = MAX_BOXES;
+            int got = 0;
+            DOFS_OK(L.ctx, dofs3d_stream_begin(L.ctx));
+            DOFS_OK(L.ctx, dofs3d_stream_submit(L.ctx, L.frames, std::min(L.pairs, chunk) + 1, &o));
+            DOFS_OK(L.ctx, dofs3d_stream_collect(L.ctx, &got));
+        }
+    }
+    NCCL_OK(ncclGroupStart());
+    for (int g = 0; g < n_gpus; ++g) {
+        CUDA_OK(cudaSetDevice(g));
+        NCCL_OK(ncclAllGather(gpus[g].d_counts, gpus[g].d_all_counts, n_lanes, ncclInt32, comms[g], 0));
+    }
+    NCCL_OK(ncclGroupEnd());
+    for (int g = 0; g < n_gpus; ++g) {
+        CUDA_OK(cudaSetDevice(g));
+        CUDA_OK(cudaStreamSynchronize(0));
+    }
 
     // ---- the timed region: every GPU streams its shard, then the gather
     auto collect = [&](Lane& L) {
