@@ -358,3 +358,37 @@ def test_render_equals_reference_display_with_cv2(dofs, golden_pair):
                     cv2.line(img, pt(lo[i]), pt(up[i]), (255, 0, 0), 1)
         want = cv2.addWeighted(fr, 1.0 - 2.0 / 5.0, seg, 2.0 / 5.0, 0)
         assert drawn > 0 and np.array_equal(got, want), (min_score, int((got != want).sum()))
+
+
+def test_repeated_runs_are_deterministic_on_tie_heavy_fields(dofs, port):
+    """compute-sanitizer is closed on this pool (profiles/r02_sanitizer_closed.txt), so the lock-free protocols of the
+    segmentation (exact minimum under concurrent offers in the Boruvka pixel kernel, path halving with benign races in
+    the contraction, decoupled look-back in the one-sweep sort) are exercised the way a race would show: fields made of
+    ties and near-ties, where every tie-break path runs thousands of times, repeated in one context and across fresh
+    contexts — every repetition must reproduce the first one bit for bit, and the first one equals the oracle."""
+    from test_gpu_parity import near_tie_field, compare_boxes
+    from denseopticalflowsegmentation3d_b200.capi import box_pixel_sets
+    W, H = 320, 200
+    zero = np.zeros((H, W, 2), np.float32)
+    blocks = np.zeros((H, W, 2), np.float32)
+    blocks[40:160, 60:260] = (1.5, -2.0)                  # two plateaus: all ties inside, one ring of equal weights
+    rounded = np.round(random_flow(91, W, H, scale=3.0) * 2) / 2   # a handful of distinct weights, huge tie classes
+    fields = np.stack([zero, blocks, near_tie_field(W, H), rounded, random_flow(92, W, H, scale=4.0)])
+    p = dofs.default_params()
+    p.min_size = 200
+    first = None
+    for rep in range(4):
+        with dofs.Context(W, H, max_pairs=len(fields), params=p) as c:
+            for _ in range(4):
+                out = c.segment(fields, already_blurred=True)
+                sig = (out["labels"].tobytes(), b"".join(b.tobytes() for b in out["boxes"]),
+                       out["stats"][["n_merges", "n_candidates", "n_scored", "n_boxes", "final_root"]].tobytes())
+                if first is None:
+                    first = (sig, out)
+                assert sig == first[0], "a repetition differs from the first run"
+    persp, inv, up = port.get_mats()
+    out = first[1]
+    for i in range(len(fields)):
+        res = port.segment(fields[i], persp, inv, up, min_size=200)
+        compare_boxes(out["boxes"][i], box_pixel_sets(out["labels"][i], out["boxes"][i]), res["entries"], W)
+        assert out["stats"][i]["n_candidates"] == res["counters"]["get_score"]

@@ -7,7 +7,7 @@ exist) can check both the CPU restatement (oracle port) and the CUDA path agains
                       reference sources (oracle/_ref) return for build_graph + segment_graph +
                       get_best_segments on that blurred flow, plus its gate counters.
   synth_320x180.npz   same for a seeded synthetic pair small enough for quick tests.
-  lift_kat.npz        get_bottom_variants of the unchanged reference on the gtest golden input
+  lift_random.npz        get_bottom_variants of the unchanged reference on the gtest golden input
                       (cpp/tests/test_liftig_3d.cpp:179-227) and on seeded random problems.
 """
 import hashlib
