@@ -556,9 +556,10 @@ def ours(args):
         live, iso = roof_of(stage_ms), roof_of(iso_ms)
         traffic = committed_traffic()
         box_traffic = None
-        if traffic and traffic.get("pairs") and "k_box_solve7" in traffic.get("kernels", {}):
+        box_keys = [k for k in (traffic or {}).get("kernels", {}) if k.startswith("k_box_solve7")]
+        if traffic and traffic.get("pairs") and box_keys:
             # ncu DRAM bytes of the three full-resolution launches: the kernel's bytes scale with the pixel count
-            kb = traffic["kernels"]["k_box_solve7"]
+            kb = traffic["kernels"][box_keys[0]]
             box_traffic = (kb["dram_read_MB"] + kb["dram_write_MB"]) * 1e6 / traffic["pairs"] * Bc / (3 * 1.328125)
         roof = None
         if iso:

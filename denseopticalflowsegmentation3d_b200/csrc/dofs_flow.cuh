@@ -217,7 +217,8 @@ inline int farneback_alloc(FlowBuffers* fb, int W, int H, int F, const FlowConfi
         return cudaMalloc(p, b) == cudaSuccess;
     };
     if (!alloc((void**)&fb->I, 2 * F * N * sizeof(float)) || !alloc((void**)&fb->R, 2 * F * N * 5 * sizeof(float)) ||
-        !alloc((void**)&fb->M, F * N * 5 * sizeof(float)) || !alloc((void**)&fb->M2, F * N * 5 * sizeof(float)) || !alloc((void**)&fb->flowA, F * N * sizeof(float2)) ||
+        !alloc((void**)&fb->M, F * N * 5 * sizeof(float)) ||
+        (fb->fuse_um && !alloc((void**)&fb->M2, F * N * 5 * sizeof(float))) || !alloc((void**)&fb->flowA, F * N * sizeof(float2)) ||
         !alloc((void**)&fb->flowB, F * N * sizeof(float2)))
         return 2;
     size_t carry = 0;
