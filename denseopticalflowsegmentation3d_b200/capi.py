@@ -89,6 +89,8 @@ def runs_to_labels(runs, n_runs, n_pixels):
 SYMBOLS = [
     "dofs3d_process_ex", "dofs3d_process_ex_dev", "dofs3d_segment_ex", "dofs3d_stream_begin", "dofs3d_stream_submit",
     "dofs3d_stream_collect", "dofs3d_fh_default_params", "dofs3d_segment_fh", "dofs3d_warp_perspective",
+    "dofs3d_forest_create", "dofs3d_forest_destroy", "dofs3d_forest_find", "dofs3d_forest_merge", "dofs3d_forest_new_merge",
+    "dofs3d_forest_num_sets", "dofs3d_forest_last_score", "dofs3d_forest_bbox", "dofs3d_forest_boxes", "dofs3d_forest_pixels",
     "dofs3d_bev_transform", "dofs3d_render", "dofs3d_pack_boxes_dev", "dofs3d_node_state", "dofs3d_scored_merges", "dofs3d_pinned_alloc", "dofs3d_pinned_free",
     "dofs3d_default_params", "dofs3d_params_for_size", "dofs3d_create", "dofs3d_destroy", "dofs3d_sync", "dofs3d_last_error", "dofs3d_stream",
     "dofs3d_launch_count", "dofs3d_device_bytes", "dofs3d_gray", "dofs3d_gray_dev", "dofs3d_flow", "dofs3d_blur",
@@ -154,6 +156,17 @@ def load_library():
     L.dofs3d_warp_perspective.argtypes = [vp, u8p, C.c_int, C.c_int, C.c_int, fp, C.c_int, C.c_int, u8p]
     L.dofs3d_bev_transform.argtypes = [vp, u8p, u8p]
     L.dofs3d_pack_boxes_dev.argtypes = [vp, C.c_int, vp, C.c_int, ip]
+    L.dofs3d_forest_create.argtypes = [vp, fp, C.POINTER(vp)]
+    L.dofs3d_forest_destroy.argtypes = [vp]
+    L.dofs3d_forest_destroy.restype = None
+    L.dofs3d_forest_find.argtypes = [vp, C.c_int, C.POINTER(C.c_int32)]
+    L.dofs3d_forest_merge.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_int32)]
+    L.dofs3d_forest_new_merge.argtypes = [vp, C.c_int, C.c_int, C.c_double, C.c_int]
+    L.dofs3d_forest_num_sets.argtypes = [vp, C.POINTER(C.c_int32)]
+    L.dofs3d_forest_last_score.argtypes = [vp, C.c_int, C.POINTER(C.c_double)]
+    L.dofs3d_forest_bbox.argtypes = [vp, C.c_int, ip]
+    L.dofs3d_forest_boxes.argtypes = [vp, C.c_int, vp]
+    L.dofs3d_forest_pixels.argtypes = [vp, C.c_int, C.c_int, ip]
     L.dofs3d_render.argtypes = [vp, C.c_int, C.c_double, u8p]
     L.dofs3d_pinned_alloc.argtypes = [C.c_size_t]
     L.dofs3d_pinned_alloc.restype = C.c_void_p
@@ -473,6 +486,66 @@ class Context:
         cnt = (C.c_int * 64)()
         n = self._ck(self.L.dofs3d_get_timing(self.h, names, ms, cnt, 64))
         return {names[i].decode(): (ms[i], cnt[i]) for i in range(n)}
+
+
+class Forest:
+    """The reference's incremental Forest (graph.hpp:72-114) over device state, one call at a time (dofs3d_forest_*)."""
+
+    def __init__(self, ctx, flow):
+        self.ctx, self.L = ctx, ctx.L
+        f = np.ascontiguousarray(flow, np.float32).reshape(ctx.H, ctx.W, 2)
+        self.h = C.c_void_p()
+        ctx._ck(self.L.dofs3d_forest_create(ctx.h, _ptr(f), C.byref(self.h)))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.dofs3d_forest_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def find(self, n):
+        r = C.c_int32(0)
+        self.ctx._ck(self.L.dofs3d_forest_find(self.h, int(n), C.byref(r)))
+        return r.value
+
+    def merge(self, a, b):
+        r = C.c_int32(0)
+        self.ctx._ck(self.L.dofs3d_forest_merge(self.h, int(a), int(b), C.byref(r)))
+        return r.value
+
+    def new_merge(self, a, b, score_threshold=0.3, min_size=500):
+        self.ctx._ck(self.L.dofs3d_forest_new_merge(self.h, int(a), int(b), float(score_threshold), int(min_size)))
+
+    @property
+    def num_sets(self):
+        r = C.c_int32(0)
+        self.ctx._ck(self.L.dofs3d_forest_num_sets(self.h, C.byref(r)))
+        return r.value
+
+    def last_score(self, node):
+        r = C.c_double(0)
+        self.ctx._ck(self.L.dofs3d_forest_last_score(self.h, int(node), C.byref(r)))
+        return r.value
+
+    def bbox(self, node):
+        bb = np.zeros(4, np.int32)
+        rc = self.ctx._ck(self.L.dofs3d_forest_bbox(self.h, int(node), _ptr(bb)))
+        return bb if rc == 1 else None
+
+    def boxes(self, max_boxes=4096):
+        out = np.zeros(max_boxes, BOX_DTYPE)
+        n = self.ctx._ck(self.L.dofs3d_forest_boxes(self.h, max_boxes, _ptr(out)))
+        return out[:n]
+
+    def pixels(self, root, size):
+        out = np.zeros(max(size, 1), np.int32)
+        n = self.ctx._ck(self.L.dofs3d_forest_pixels(self.h, int(root), int(size), _ptr(out)))
+        return np.sort(out[:min(n, size)])
 
 
 def box_pixel_sets(labels, boxes):

@@ -22,6 +22,7 @@
 #include "dofs_flow.cuh"
 #include "dofs_lift.cuh"
 #include "dofs_fh.cuh"
+#include "dofs_forest.cuh"
 #include "dofs_seg.cuh"
 #include "dofs_sort.cuh"
 #include "dofs_synth.cuh"
@@ -1534,6 +1535,170 @@ int dofs3d_pack_boxes_dev(dofs3d_ctx* ctx, int n_pairs, dofs3d_box* d_out, int c
            n_pairs, d_out, capacity, d_total_out);
     CK(cudaGetLastError());
     return 0;
+}
+
+// ------------------------------------------------------------------------------------- incremental Forest
+}  // extern "C"
+
+struct dofs3d_forest {
+    dofs3d_ctx* ctx = nullptr;
+    ForestState S;
+    dofs3d_box* boxes = nullptr;
+    int* pixels = nullptr;  // scratch of dofs3d_forest_pixels, N entries
+    std::vector<void*> allocs;
+};
+
+namespace {
+template <typename T>
+bool falloc(dofs3d_forest* f, T** p, size_t count) {
+    void* q = nullptr;
+    if (cudaMalloc(&q, std::max<size_t>(count * sizeof(T), 16)) != cudaSuccess) return false;
+    f->allocs.push_back(q);
+    *p = static_cast<T*>(q);
+    return true;
+}
+int forest_result(dofs3d_forest* f, int* out) {
+    dofs3d_ctx* ctx = f->ctx;
+    int v = 0;
+    CK(cudaMemcpyAsync(&v, f->S.counters + 3, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaGetLastError());
+    if (out) *out = v;
+    return 0;
+}
+bool forest_node_ok(dofs3d_forest* f, int n) { return f && n >= 0 && n < f->S.N; }
+}  // namespace
+
+extern "C" {
+
+int dofs3d_forest_create(dofs3d_ctx* ctx, const float* flow, dofs3d_forest** out) {
+    if (!ctx || !flow || !out) return DOFS3D_ERR_ARG;
+    *out = nullptr;
+    CK(cudaSetDevice(ctx->device));
+    dofs3d_forest* f = new dofs3d_forest();
+    f->ctx = ctx;
+    ForestState& S = f->S;
+    S.W = ctx->W;
+    S.H = ctx->H;
+    S.N = ctx->N;
+    S.box_cap = ctx->box_cap;
+    const size_t N = ctx->N;
+    float2* d_flow = nullptr;
+    if (!falloc(f, &S.parent, N) || !falloc(f, &S.rank, N) || !falloc(f, &S.size, N) || !falloc(f, &S.flow, N) ||
+        !falloc(f, &S.bbox, N) || !falloc(f, &S.next, N) || !falloc(f, &S.tail, N) || !falloc(f, &S.last_score, N) ||
+        !falloc(f, &S.best_score, N) || !falloc(f, &S.snap_size, N) || !falloc(f, &S.box_slot, N) ||
+        !falloc(f, &S.counters, (size_t)4) || !falloc(f, &f->boxes, (size_t)S.box_cap) || !falloc(f, &f->pixels, N) ||
+        !falloc(f, &d_flow, N)) {
+        ctx->err = "device allocation failed (forest)";
+        dofs3d_forest_destroy(f);
+        return DOFS3D_ERR_NOMEM;
+    }
+    CK(cudaMemcpyAsync(d_flow, flow, N * sizeof(float2), cudaMemcpyHostToDevice, ctx->stream));
+    LAUNCH(ctx, k_forest_init, grid1(N, 256, 1), 256, 0, S, d_flow);
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaGetLastError());
+    *out = f;
+    return 0;
+}
+
+void dofs3d_forest_destroy(dofs3d_forest* f) {
+    if (!f) return;
+    cudaSetDevice(f->ctx->device);
+    cudaStreamSynchronize(f->ctx->stream);
+    for (void* p : f->allocs) cudaFree(p);
+    delete f;
+}
+
+int dofs3d_forest_find(dofs3d_forest* f, int n, int32_t* root_out) {
+    if (!forest_node_ok(f, n)) return DOFS3D_ERR_ARG;
+    dofs3d_ctx* ctx = f->ctx;
+    CK(cudaSetDevice(ctx->device));
+    LAUNCH(ctx, k_forest_find, 1, 1, 0, f->S, n);
+    return forest_result(f, root_out);
+}
+
+int dofs3d_forest_merge(dofs3d_forest* f, int a, int b, int32_t* root_out) {
+    if (!forest_node_ok(f, a) || !forest_node_ok(f, b)) return DOFS3D_ERR_ARG;
+    dofs3d_ctx* ctx = f->ctx;
+    CK(cudaSetDevice(ctx->device));
+    LAUNCH(ctx, k_forest_merge<dofs3d_box>, 1, 1, 0, f->S, a, b, 0, 0.0, 0, ctx->seg, f->boxes);
+    return forest_result(f, root_out);
+}
+
+int dofs3d_forest_new_merge(dofs3d_forest* f, int a, int b, double score_threshold, int min_size) {
+    if (!forest_node_ok(f, a) || !forest_node_ok(f, b)) return DOFS3D_ERR_ARG;
+    dofs3d_ctx* ctx = f->ctx;
+    CK(cudaSetDevice(ctx->device));
+    LAUNCH(ctx, k_forest_merge<dofs3d_box>, 1, 1, 0, f->S, a, b, 1, score_threshold, min_size, ctx->seg, f->boxes);
+    return forest_result(f, nullptr);
+}
+
+int dofs3d_forest_num_sets(dofs3d_forest* f, int32_t* num_sets_out) {
+    if (!f || !num_sets_out) return DOFS3D_ERR_ARG;
+    dofs3d_ctx* ctx = f->ctx;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(num_sets_out, f->S.counters, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int dofs3d_forest_last_score(dofs3d_forest* f, int node, double* score_out) {
+    if (!forest_node_ok(f, node) || !score_out) return DOFS3D_ERR_ARG;
+    dofs3d_ctx* ctx = f->ctx;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(score_out, f->S.last_score + node, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int dofs3d_forest_bbox(dofs3d_forest* f, int node, int32_t* bbox4_out) {
+    if (!forest_node_ok(f, node) || !bbox4_out) return DOFS3D_ERR_ARG;
+    dofs3d_ctx* ctx = f->ctx;
+    CK(cudaSetDevice(ctx->device));
+    ushort4 b;
+    CK(cudaMemcpyAsync(&b, f->S.bbox + node, sizeof b, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (b.x == 65535 && b.z == 65535) return 0;  // cleared when the node was absorbed
+    bbox4_out[0] = b.x, bbox4_out[1] = b.y, bbox4_out[2] = b.z, bbox4_out[3] = b.w;
+    return 1;
+}
+
+int dofs3d_forest_boxes(dofs3d_forest* f, int max_boxes, dofs3d_box* boxes_out) {
+    if (!f || max_boxes < 0 || (max_boxes > 0 && !boxes_out)) return DOFS3D_ERR_ARG;
+    dofs3d_ctx* ctx = f->ctx;
+    CK(cudaSetDevice(ctx->device));
+    int used = 0;
+    CK(cudaMemcpyAsync(&used, f->S.counters + 2, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (used > f->S.box_cap || used > max_boxes) {
+        ctx->err = "more boxes than max_boxes";
+        return DOFS3D_ERR_OVERFLOW;
+    }
+    std::vector<dofs3d_box> tmp((size_t)used);
+    if (used) {
+        CK(cudaMemcpyAsync(tmp.data(), f->boxes, sizeof(dofs3d_box) * used, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    std::sort(tmp.begin(), tmp.end(), [](const dofs3d_box& l, const dofs3d_box& r) { return l.root < r.root; });
+    for (int i = 0; i < used; ++i) boxes_out[i] = tmp[i];
+    return used;
+}
+
+int dofs3d_forest_pixels(dofs3d_forest* f, int root, int cap, int32_t* pixels_out) {
+    if (!forest_node_ok(f, root) || cap < 0 || (cap > 0 && !pixels_out)) return DOFS3D_ERR_ARG;
+    dofs3d_ctx* ctx = f->ctx;
+    CK(cudaSetDevice(ctx->device));
+    int n = 0;
+    CK(cudaMemcpyAsync(&n, f->S.snap_size + root, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const int take = std::min(n, cap);
+    if (take > 0) {
+        LAUNCH(ctx, k_forest_pixels, 1, 1, 0, f->S, root, take, f->pixels);
+        CK(cudaMemcpyAsync(pixels_out, f->pixels, sizeof(int) * take, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        CK(cudaGetLastError());
+    }
+    return n;
 }
 
 void* dofs3d_pinned_alloc(size_t bytes) {

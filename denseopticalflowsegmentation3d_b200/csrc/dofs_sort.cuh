@@ -49,7 +49,13 @@ DOFS_D u32 rs_block_excl_scan(u32 v, u32* s_warp /* >= 8 */, u32* total) {
 }
 
 // lanes of the warp holding the same 9-bit value (8-bit digit + the "out of range" flag), by ballots: one vote per bit
+#ifndef RS_USE_MATCH_ANY
+#define RS_USE_MATCH_ANY 0  // A/B: the MATCH.ANY instruction instead of nine votes
+#endif
 DOFS_D u32 rs_match9(u32 d) {
+#if RS_USE_MATCH_ANY
+    return __match_any_sync(0xffffffffu, d);
+#endif
     u32 peers = 0xffffffffu;
 #pragma unroll
     for (int b = 0; b < 9; ++b) {

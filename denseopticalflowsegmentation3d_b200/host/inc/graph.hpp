@@ -75,8 +75,13 @@ public:
     std::vector<cv::Matx33f> inv_mat_upper;
 
     Forest() : num_sets(0), width(0), height(0), min_move(5) {}
+    // The reference's own constructor (graph.cpp:129-148): N singleton sets over `flow`, to be merged one call at a
+    // time with find / merge / new_merge below — every call is a one-thread kernel over device state and a wait.
+    // segment_graph / get_segmented_array run the whole loop on the device at once and are the path for throughput.
+    Forest(const cv::Mat& flow, const cv::Mat& bev, const cv::Matx33f& persp_mat, const cv::Matx33f& inv_mat,
+           const std::vector<cv::Matx33f>& inv_mat_upper, int min_move = 5);
 
-    // Root of n's set in the final forest (graph.cpp:150-168): after the full Kruskal pass that is one set.
+    // Root of n's set (graph.cpp:150-168).  For a forest returned by segment_graph: the final forest, one set.
     int find(int n) const;
     // The whole history vector, index = root id, score == -1 where empty (graph.cpp:391-429).
     std::vector<SegmentData> get_best_segments();
@@ -89,13 +94,18 @@ public:
     // rectangle, written before the convexity and threshold gates (graph.cpp:326); 0.0 if it never had one.
     // (Forests returned by process_video carry no per-merge scores: 0.0.)
     double get_segment_best_score(int node_id) const;
-    // merge / new_merge (graph.cpp:170-218, 272-384) are not callable one at a time: the loop runs on the device.
+    // merge / new_merge (graph.cpp:170-218, 272-384): on a forest built with the constructor above; a forest returned by
+    // segment_graph is finished (its loop ran on the device as a whole) and throws std::logic_error.  min_move and
+    // min_convexity are accepted and ignored like in the reference (its gates use the row-adaptive motion threshold
+    // and the per-class convexity bounds, graph.cpp:296, 328-339).
     int merge(int a, int b);
     void new_merge(int a, int b, double score_threshold = 0.3, int min_size = 500, double min_move = 1.0,
                    double min_convexity = 1.0 / 2.0);
 
     struct Result;  // labels + boxes returned by dofs3d_segment
     std::shared_ptr<Result> result;
+    struct Incremental;  // device forest driven one call at a time
+    std::shared_ptr<Incremental> incremental;
 };
 
 // Kruskal / union-find clustering with per-merge lifting (graph.cpp:503-536).  `graph_edges` is what

@@ -263,13 +263,64 @@ Forest get_segmented_array(const cv::Mat& flow, const cv::Mat& bev, const cv::Ma
 }
 
 // ------------------------------------------------------------------------------------------------
-int Forest::find(int) const {
+struct Forest::Incremental {
+    CtxEntry* ent = nullptr;
+    dofs3d_forest* f = nullptr;
+    ~Incremental() {
+        if (f) {
+            std::lock_guard<std::mutex> call(ent->mu);
+            dofs3d_forest_destroy(f);
+        }
+    }
+};
+
+Forest::Forest(const cv::Mat& flow, const cv::Mat& bev_, const cv::Matx33f& persp, const cv::Matx33f& inv,
+               const std::vector<cv::Matx33f>& upper, int min_move_)
+    : num_sets(flow.rows * flow.cols), width(flow.cols), height(flow.rows), min_move(min_move_), bev(bev_), persp_mat(persp),
+      inv_mat(inv), inv_mat_upper(upper) {
+    check_flow(flow, "Forest");
+    if (upper.size() < 3) throw std::invalid_argument("Forest: inv_mat_upper needs one matrix per class (3)");
+    dofs3d_params p;
+    dofs3d_default_params(&p);
+    fill_mats(p, persp, inv, upper);
+    auto inc = std::make_shared<Incremental>();
+    inc->ent = context_for(width, height, 1, p);
+    std::lock_guard<std::mutex> call(inc->ent->mu);
+    int rc = dofs3d_forest_create(inc->ent->c, flow.ptr<float>(), &inc->f);
+    if (rc != 0) fail(inc->ent->c, rc, "Forest");
+    incremental = inc;
+}
+
+int Forest::find(int n) const {
+    if (incremental) {
+        std::lock_guard<std::mutex> call(incremental->ent->mu);
+        int32_t r = 0;
+        int rc = dofs3d_forest_find(incremental->f, n, &r);
+        if (rc != 0) fail(incremental->ent->c, rc, "Forest::find");
+        return r;
+    }
     if (!result) throw std::logic_error("Forest::find on an empty forest");
     return result->final_root;
 }
 
 std::vector<std::pair<int, SegmentData>> Forest::get_best_segments_sparse() const {
     std::vector<std::pair<int, SegmentData>> out;
+    if (incremental) {
+        std::lock_guard<std::mutex> call(incremental->ent->mu);
+        dofs3d_ctx* c = incremental->ent->c;
+        std::vector<dofs3d_box> boxes(4096);
+        int n = dofs3d_forest_boxes(incremental->f, (int)boxes.size(), boxes.data());
+        if (n < 0) fail(c, n, "Forest::get_best_segments");
+        for (int b = 0; b < n; ++b) {
+            const dofs3d_box& bx = boxes[b];
+            std::vector<int32_t> px((size_t)bx.size);
+            int m = dofs3d_forest_pixels(incremental->f, bx.root, bx.size, px.data());
+            if (m < 0) fail(c, m, "Forest::get_best_segments");
+            out.emplace_back(bx.root, SegmentData(bx.score, std::set<int>(px.begin(), px.begin() + std::min(m, bx.size)),
+                                                  solution_of(bx, true), bx.move));
+        }
+        return out;
+    }
     if (!result) return out;
     result->build_sets();
     for (int b = 0; b < result->n_boxes; ++b) {
@@ -290,6 +341,14 @@ std::vector<SegmentData> Forest::get_best_segments() {
 // (The box a segment had at its best snapshot is SegmentData::sol / dofs3d_box::bbox; the state a node had when it was
 // absorbed is dofs3d_node_state.)
 std::vector<cv::Point2i> Forest::get_bounding_box(int node_id) const {
+    if (incremental) {
+        std::lock_guard<std::mutex> call(incremental->ent->mu);
+        int32_t bb[4];
+        int rc = dofs3d_forest_bbox(incremental->f, node_id, bb);
+        if (rc < 0) fail(incremental->ent->c, rc, "Forest::get_bounding_box");
+        if (rc == 0) return {};
+        return {cv::Point2i(bb[0], bb[1]), cv::Point2i(bb[2], bb[3])};
+    }
     if (!result) return {};
     if (node_id < 0 || node_id >= width * height) throw std::out_of_range("Forest::get_bounding_box: node id");
     if (node_id == result->final_root) return {cv::Point2i(0, 0), cv::Point2i(width - 1, height - 1)};
@@ -299,14 +358,41 @@ std::vector<cv::Point2i> Forest::get_bounding_box(int node_id) const {
 // graph.cpp:386-389: segment_scores[node_id] — the score of the node's latest merge that produced a rectangle
 // (graph.cpp:326, written before the convexity and threshold gates), 0.0 if there was none.
 double Forest::get_segment_best_score(int node_id) const {
+    if (incremental) {
+        std::lock_guard<std::mutex> call(incremental->ent->mu);
+        double sc = 0.0;
+        int rc = dofs3d_forest_last_score(incremental->f, node_id, &sc);
+        if (rc != 0) fail(incremental->ent->c, rc, "Forest::get_segment_best_score");
+        return sc;
+    }
     if (!result) return 0.0;
     auto it = result->last_score.find(node_id);
     return it == result->last_score.end() ? 0.0 : it->second.second;
 }
 
-int Forest::merge(int, int) { throw std::logic_error("Forest::merge: the merge loop runs on the device as a whole (segment_graph)"); }
-void Forest::new_merge(int, int, double, int, double, double) {
-    throw std::logic_error("Forest::new_merge: the merge loop runs on the device as a whole (segment_graph)");
+int Forest::merge(int a, int b) {
+    if (!incremental)
+        throw std::logic_error("Forest::merge: this forest is the finished result of segment_graph (its merge loop ran on the "
+                               "device as a whole); build one with Forest(flow, ...) to merge one call at a time");
+    std::lock_guard<std::mutex> call(incremental->ent->mu);
+    int32_t r = 0, ns = 0;
+    int rc = dofs3d_forest_merge(incremental->f, a, b, &r);
+    if (rc == 0) rc = dofs3d_forest_num_sets(incremental->f, &ns);
+    if (rc != 0) fail(incremental->ent->c, rc, "Forest::merge");
+    num_sets = ns;
+    return r;
+}
+
+void Forest::new_merge(int a, int b, double score_threshold, int min_size, double, double) {
+    if (!incremental)
+        throw std::logic_error("Forest::new_merge: this forest is the finished result of segment_graph (its merge loop ran on "
+                               "the device as a whole); build one with Forest(flow, ...) to merge one call at a time");
+    std::lock_guard<std::mutex> call(incremental->ent->mu);
+    int32_t ns = 0;
+    int rc = dofs3d_forest_new_merge(incremental->f, a, b, score_threshold, min_size);
+    if (rc == 0) rc = dofs3d_forest_num_sets(incremental->f, &ns);
+    if (rc != 0) fail(incremental->ent->c, rc, "Forest::new_merge");
+    num_sets = ns;
 }
 
 // ------------------------------------------------------------------------------------------------

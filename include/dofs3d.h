@@ -263,6 +263,27 @@ int dofs3d_bev_transform(dofs3d_ctx* ctx, const uint8_t* bgr_frame, uint8_t* bev
  * Asynchronous on the context's stream.  Boxes beyond `capacity` are dropped (*d_total_out still counts them). */
 int dofs3d_pack_boxes_dev(dofs3d_ctx* ctx, int n_pairs, dofs3d_box* d_out, int capacity, int32_t* d_total_out);
 
+/* ---- the incremental Forest, one call at a time (graph.hpp:72-114) --------------------------------------------------------
+ * For callers that drive the merge loop themselves, the way the reference's segment_graph does (graph.cpp:520-531):
+ * Forest::Forest (graph.cpp:129-148), find (:150-157), merge (:170-218), new_merge (:272-384) over device state.  Every call
+ * is a one-thread kernel and a wait (tens of microseconds): dofs3d_segment computes the same merge sequence for a whole
+ * Kruskal pass at once and is the path to use for throughput.  The forest uses the context's GPU, stream and parameters
+ * (homographies, class sizes, convexity bounds); flow = one field [H][W][2] of the context's size (host).
+ *   dofs3d_forest_boxes   the history (Forest::get_best_segments, graph.cpp:391-429) as box records in ascending root
+ *                         order (parent_box is not computed: -1); returns their number or a negative status
+ *   dofs3d_forest_pixels  the pixel set of a kept root's snapshot (SegmentData::seg), unsorted; returns its size */
+typedef struct dofs3d_forest dofs3d_forest;
+int dofs3d_forest_create(dofs3d_ctx* ctx, const float* flow, dofs3d_forest** out);
+void dofs3d_forest_destroy(dofs3d_forest* f);
+int dofs3d_forest_find(dofs3d_forest* f, int n, int32_t* root_out);
+int dofs3d_forest_merge(dofs3d_forest* f, int a, int b, int32_t* root_out);
+int dofs3d_forest_new_merge(dofs3d_forest* f, int a, int b, double score_threshold, int min_size);
+int dofs3d_forest_num_sets(dofs3d_forest* f, int32_t* num_sets_out);
+int dofs3d_forest_last_score(dofs3d_forest* f, int node, double* score_out);   /* Forest::get_segment_best_score */
+int dofs3d_forest_bbox(dofs3d_forest* f, int node, int32_t* bbox4_out);         /* Forest::get_bounding_box: returns 0 when the box was cleared, 1 when bbox4_out holds it */
+int dofs3d_forest_boxes(dofs3d_forest* f, int max_boxes, dofs3d_box* boxes_out);
+int dofs3d_forest_pixels(dofs3d_forest* f, int root, int cap, int32_t* pixels_out);
+
 /* Page-locked host memory for the frame and result buffers of the streaming entry points (cudaMallocHost / cudaFreeHost,
  * so that callers need no CUDA headers); NULL on failure. */
 void* dofs3d_pinned_alloc(size_t bytes);

@@ -124,6 +124,41 @@ int main(int argc, char** argv) {
     auto a = forest.get_best_segments_sparse(), b = again.get_best_segments_sparse();
     CHECK(a.size() == b.size() && (int)a.size() == kept);
     for (size_t i = 0; i < a.size(); ++i) CHECK(a[i].first == b[i].first && a[i].second.seg == b[i].second.seg);
+    // The reference's own Forest, driven one merge at a time (graph.cpp:520-531 is this loop) on a crop of the field:
+    // it must end with the history the whole-pass segment_graph returns for the same crop.
+    {
+        const int cw = 72, ch = 56, x0 = W / 2 - cw / 2, y0 = H / 2 - ch / 2;
+        cv::Mat crop(ch, cw, CV_32FC2);
+        for (int y = 0; y < ch; ++y)
+            for (int x = 0; x < cw; ++x) {
+                const cv::Point2f v = flow.at<cv::Point2f>(y0 + y, x0 + x);
+                crop.at<cv::Point2f>(y, x) = cv::Point2f(v.x * 3.0f, v.y * 3.0f);
+            }
+        std::vector<Edge> ce = build_graph(crop, cw, ch, diff, true);
+        Forest whole = segment_graph(crop, ce, bev, mats.first, mats.second, upper);
+        Forest step(crop, bev, mats.first, mats.second, upper);
+        CHECK(step.num_sets == cw * ch);
+        for (const Edge& ed : ce) {
+            const int ra = step.find(ed.start), rb = step.find(ed.end);
+            if (ra != rb) step.new_merge(ra, rb);
+        }
+        CHECK(step.num_sets == 1 && step.find(0) == whole.find(0));
+        auto hs = step.get_best_segments_sparse(), hw = whole.get_best_segments_sparse();
+        CHECK(hs.size() == hw.size());
+        for (size_t i = 0; i < hs.size(); ++i) {
+            CHECK(hs[i].first == hw[i].first && hs[i].second.seg == hw[i].second.seg);
+            CHECK(near(hs[i].second.score, hw[i].second.score, 1e-12) && hs[i].second.sol.cls == hw[i].second.sol.cls);
+            CHECK(step.get_segment_best_score(hs[i].first) == whole.get_segment_best_score(hw[i].first));
+        }
+        std::printf("incremental forest: %zu kept segments equal the whole-pass result\n", hs.size());
+        bool threw = false;
+        try {
+            whole.merge(0, 1);
+        } catch (const std::logic_error&) {
+            threw = true;
+        }
+        CHECK(threw);
+    }
     std::printf("edges=%zu kept=%d\n", edges.size(), kept);
     return 0;
 }

@@ -392,3 +392,41 @@ def test_repeated_runs_are_deterministic_on_tie_heavy_fields(dofs, port):
         res = port.segment(fields[i], persp, inv, up, min_size=200)
         compare_boxes(out["boxes"][i], box_pixel_sets(out["labels"][i], out["boxes"][i]), res["entries"], W)
         assert out["stats"][i]["n_candidates"] == res["counters"]["get_score"]
+
+
+def test_incremental_forest_drives_the_reference_loop(dofs, port):
+    """Forest::Forest / find / merge / new_merge one call at a time (graph.hpp:72-114) over device state: the loop of the
+    reference's segment_graph (graph.cpp:520-531) written against dofs3d_forest_*, on the port's sorted edge list, ends
+    with the history the oracle's whole pass ends with — roots, pixel sets, sizes, mean-flow bits, scores."""
+    from denseopticalflowsegmentation3d_b200.capi import Forest
+    W, H = 56, 40
+    f = random_flow(17, W, H, scale=4.0)
+    persp, inv, up = port.get_mats()
+    res = port.segment(f, persp, inv, up, min_size=40, trace=True)
+    s, e, _ = port.build_graph(f, True)
+    with dofs.Context(W, H) as c, Forest(c, f) as forest:
+        assert forest.num_sets == W * H and forest.find(5) == 5 and list(forest.bbox(5)) == [5, 0, 5, 0]
+        merges = 0
+        for a0, b0 in zip(s.tolist(), e.tolist()):
+            a, b = forest.find(a0), forest.find(b0)
+            if a != b:
+                forest.new_merge(a, b, 0.3, 40)
+                assert forest.find(a0) == forest.find(b0) == int(res["trace"]["winner"][merges])
+                merges += 1
+        assert merges == W * H - 1 and forest.num_sets == 1
+        boxes = forest.boxes()
+        ents = res["entries"]
+        assert [int(b["root"]) for b in boxes] == [en["root"] for en in ents] and len(ents) > 0
+        for b, en in zip(boxes, ents):
+            assert int(b["size"]) == en["size"] and abs(b["score"] - en["score"]) <= 1e-5 and int(b["time"]) == en["time"]
+            assert np.array_equal(np.asarray(b["mean_flow"]).view(np.uint32), en["flow"].view(np.uint32))
+            assert np.array_equal(forest.pixels(int(b["root"]), int(b["size"])), en["pixels"])
+        final = forest.find(0)
+        assert list(forest.bbox(final)) == [0, 0, W - 1, H - 1]
+        absorbed = next(p for p in range(W * H) if p != final)
+        assert forest.bbox(absorbed) is None          # Forest::merge clears the box of an absorbed root (graph.cpp:207)
+    # plain merge (no gates, no history) keeps the union-find bookkeeping of graph.cpp:170-218
+    with dofs.Context(W, H) as c, Forest(c, f) as forest:
+        assert forest.merge(0, 1) == 1 and forest.num_sets == W * H - 1      # equal ranks: b's root survives
+        assert forest.merge(2, 0) == 1 and forest.find(2) == 1                 # lower rank hangs under the higher
+        assert len(forest.boxes()) == 0
