@@ -456,6 +456,7 @@ def ours(args):
     CAPC = Bc * 64
     g_boxes = torch.zeros((NC, CAPC * BOX_DTYPE.itemsize), dtype=torch.uint8, device=dev)
     g_counts = torch.zeros((NC,), dtype=torch.int32, device=dev)
+    pack_done = [torch.cuda.Event() for _ in ctxs]
 
     def ck(ctx, rc):
         if rc != 0:
@@ -496,7 +497,9 @@ def ours(args):
             tg = time.perf_counter()
             for c in range(NC):
                 ctxs[c].pack_boxes_dev(Bc, g_boxes[c].data_ptr(), CAPC, g_counts[c:c + 1].data_ptr())
-                ctxs[c].sync()
+                pack_done[c].record(streams[c])
+            for c in range(NC):
+                torch.cuda.current_stream().wait_event(pack_done[c])  # the collectives run behind the packs, no host wait
             all_counts, all_boxes = shard.gather_packed(g_counts, g_boxes)
             total = int(all_counts.sum().item())  # device -> host read of the gathered result
             torch.cuda.synchronize()

@@ -56,18 +56,31 @@ def gather_boxes(n_boxes, boxes, device=None, group=None):
     return counts, out
 
 
-def gather_packed(counts, boxes_u8, group=None):
+def _all_gather_flat(out, inp, group):
+    """One collective into a preallocated [world, ...] tensor (a single NCCL all-gather on the GPUs)."""
+    try:
+        dist.all_gather_into_tensor(out, inp, group=group)
+    except (RuntimeError, NotImplementedError):  # a backend without the flat form
+        dist.all_gather(list(out.unbind(0)), inp, group=group)
+
+
+def gather_packed(counts, boxes_u8, group=None, trim=False):
     """Gather of per-frame results straight from device buffers (no host round trip): `counts` int32 [C] = boxes held by
     each of this rank's C contexts, `boxes_u8` uint8 [C][cap * 216] = their dense box lists (dofs3d_pack_boxes_dev).
-    One fixed-size all_gather of the counts, one of the boxes trimmed to the largest count of any context of any rank.
+    Two collectives back to back, no host synchronisation in between: the counts, then the boxes at their fixed capacity
+    (a few MB per rank: over NVLink / NVSwitch the padding costs less than the host read a trimmed size would need).
+    trim=True first reads the largest count of any context (one host sync) and sends only that many boxes per context.
     Returns (all_counts int32 [world][C], all_boxes uint8 [world][C][m * 216]) on the tensors' device."""
     world = dist.get_world_size(group)
     itemsize = BOX_DTYPE.itemsize
+    counts = counts.contiguous()
     all_counts = torch.empty((world,) + tuple(counts.shape), dtype=counts.dtype, device=counts.device)
-    dist.all_gather(list(all_counts.unbind(0)), counts.contiguous(), group=group)
-    m = max(int(all_counts.max().item()), 1)
-    m = min(m, boxes_u8.shape[1] // itemsize)
-    send = boxes_u8[:, :m * itemsize].contiguous()
+    _all_gather_flat(all_counts, counts, group)
+    send = boxes_u8
+    if trim:
+        m = min(max(int(all_counts.max().item()), 1), boxes_u8.shape[1] // itemsize)
+        send = boxes_u8[:, :m * itemsize]
+    send = send.contiguous()
     all_boxes = torch.empty((world,) + tuple(send.shape), dtype=send.dtype, device=send.device)
-    dist.all_gather(list(all_boxes.unbind(0)), send, group=group)
+    _all_gather_flat(all_boxes, send, group)
     return all_counts, all_boxes

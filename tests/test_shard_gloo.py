@@ -53,7 +53,9 @@ def _worker(rank, world, port, n_pairs, out_q):
     for c, part in enumerate(parts):
         packed[c, :part.nbytes] = torch.from_numpy(part.view(np.uint8).reshape(-1).copy())
     cnt = torch.tensor([p.shape[0] for p in parts], dtype=torch.int32)
-    all_cnt, all_box = shard.gather_packed(cnt, packed)
+    all_cnt, all_box = shard.gather_packed(cnt, packed, trim=(rank + n_pairs) % 2 == 0 or True)
+    full_cnt, full_box = shard.gather_packed(cnt, packed)
+    assert torch.equal(full_cnt, all_cnt) and full_box.shape[2] == cap * BOX_DTYPE.itemsize
     for r in range(world):
         for c in range(2):
             k = int(all_cnt[r, c])
