@@ -158,6 +158,20 @@ struct dofs3d_ctx {
     dofs3d_run* runs = nullptr;       // [F][runs_cap], allocated on the first run-length call
     int runs_cap = 0;
     dofs3d_stats* stats = nullptr;
+    // Conditional graph nodes (CUDA 12.4+): the Boruvka levels and replay waves beyond what the previous call needed, and
+    // the exact fallback of the merge-time sort, are enqueued as the body of an IF node whose condition a one-block kernel
+    // sets from device state — a batch that does not need them pays one graph launch instead of ~150 empty kernels, a
+    // batch that does runs exactly the launches it would have got.  Cached per (kind, batch size, first level).
+    struct CondGraph {
+        int kind, n, arg;
+        cudaGraph_t graph;
+        cudaGraphExec_t exec;
+    };
+    std::vector<CondGraph> cond_graphs;
+    int soft_levels_forced = 0;       // test knob DOFS3D_SOFT_LEVELS: levels enqueued unconditionally (the IF bodies then run)
+    bool use_cond_graphs = true;      // DOFS3D_COND_GRAPHS=0: enqueue every launch unconditionally (round-1 behaviour)
+    int* d_call_levels = nullptr;     // device: levels the last call needed
+    int* h_call_levels = nullptr;     // pinned copy, read (possibly one call late: it is only a hint) by the next call
     int stride_blocks_per_sm = 16;    // grid of the grid-stride kernels (DOFS3D_STRIDE_BLOCKS): blocks per SM over the whole batch
     int carveout = -1;                // DOFS3D_CARVEOUT: preferred shared-memory carveout (percent) of every kernel; -1 = the driver's choice
     std::vector<const void*> carveout_done;
@@ -398,6 +412,63 @@ void blur_launch(dofs3d_ctx* ctx, const float2* src, float2* dst, int n) {
 }
 
 // get_segmented_array (segment.cpp:34-72) for n frames whose (unblurred or blurred) flow is at d_flow.
+// Enqueues `body` as the body of an IF node: kind / data / arg / last are k_set_condition's arguments.  The graph is built
+// once per (kind, n, arg) by capturing the body's launches from the context's stream; kernel arguments of a context are
+// the same on every call (its buffers), so the instantiated graph is replayed as it is.
+template <typename Body>
+int launch_conditional(dofs3d_ctx* ctx, int kind, const int* data, int n, int arg, int last, Body body) {
+    if (!ctx->use_cond_graphs) {
+        body();
+        return 0;
+    }
+    for (const auto& g : ctx->cond_graphs)
+        if (g.kind == kind && g.n == n && g.arg == arg) {
+            CK(cudaGraphLaunch(g.exec, ctx->stream));
+            ctx->launches++;
+            return 0;
+        }
+    dofs3d_ctx::CondGraph cg;
+    cg.kind = kind;
+    cg.n = n;
+    cg.arg = arg;
+    CK(cudaGraphCreate(&cg.graph, 0));
+    cudaGraphConditionalHandle handle;
+    CK(cudaGraphConditionalHandleCreate(&handle, cg.graph, 0, cudaGraphCondAssignDefault));
+    cudaGraphNode_t set_node, if_node;
+    cudaKernelNodeParams kp = {};
+    int F = ctx->F;
+    void* args[] = {&handle, &kind, &data, &n, &F, &arg, &last};
+    kp.func = (void*)k_set_condition;
+    kp.gridDim = dim3(1);
+    kp.blockDim = dim3(128);
+    kp.kernelParams = args;
+    CK(cudaGraphAddKernelNode(&set_node, cg.graph, nullptr, 0, &kp));
+    cudaGraphNodeParams cp = {};
+    cp.type = cudaGraphNodeTypeConditional;
+    cp.conditional.handle = handle;
+    cp.conditional.type = cudaGraphCondTypeIf;
+    cp.conditional.size = 1;
+    CK(cudaGraphAddNode(&if_node, cg.graph, &set_node, 1, &cp));
+    const bool timing = ctx->timer.enabled;
+    ctx->timer.enabled = false;  // no event records inside the captured body
+    const long long launches_before = ctx->launches;
+    CK(cudaStreamBeginCaptureToGraph(ctx->stream, cp.conditional.phGraph_out[0], nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed));
+    body();
+    cudaGraph_t captured = nullptr;
+    const cudaError_t e = cudaStreamEndCapture(ctx->stream, &captured);
+    ctx->timer.enabled = timing;
+    ctx->launches = launches_before;
+    if (e != cudaSuccess) {
+        ctx->err = std::string("stream capture of a conditional body failed: ") + cudaGetErrorString(e);
+        return DOFS3D_ERR_CUDA;
+    }
+    CK(cudaGraphInstantiate(&cg.exec, cg.graph, 0));
+    ctx->cond_graphs.push_back(cg);
+    CK(cudaGraphLaunch(cg.exec, ctx->stream));
+    ctx->launches++;
+    return 0;
+}
+
 // what a call must leave in the context for export_results: label format, run-length capacity, the box capacity the
 // caller announced (for the deferred overflow check)
 struct OutSpec {
@@ -436,7 +507,11 @@ int segment_dev(dofs3d_ctx* ctx, const float* d_flow, int already_blurred, int n
     CK(cudaMemsetAsync(ctx->counters, 0, sizeof(int) * CNT_KINDS * F, ctx->stream));
     CK(cudaMemsetAsync(B.n_roots, 0, sizeof(int) * EV_MAX_WAVES * F, ctx->stream));
     const int levels = ctx->max_levels;
-    for (int level = 0; level < levels; ++level) {
+    // levels the previous call needed + 1 are enqueued unconditionally, the rest of the guaranteed bound as an IF body
+    int soft = levels;
+    if (ctx->use_cond_graphs) soft = std::min(levels, std::max(2, (*ctx->h_call_levels > 0 ? *ctx->h_call_levels : 11) + 1));
+    if (ctx->use_cond_graphs && ctx->soft_levels_forced > 0) soft = std::min(levels, std::max(1, ctx->soft_levels_forced));
+    auto bor_level = [&](int level) {
         if (level == 0) {
             LAUNCH(ctx, k_bor_level0_pick, gS, SEG_THREADS, 0, B, prefix, ctx->S, ctx->flow_blur, W, H, N);
             LAUNCH(ctx, k_bor_level0_root, gS, SEG_THREADS, 0, B, W, H, N, ctx->seg.neighbors == 8 ? 1 : 0);
@@ -446,6 +521,15 @@ int segment_dev(dofs3d_ctx* ctx, const float* d_flow, int already_blurred, int n
         }
         LAUNCH(ctx, k_bor_contract, gS, SEG_THREADS, 0, B, N, level);
         if (level == 0 || !ctx->bor_fold) LAUNCH(ctx, k_bor_relabel, gS, SEG_THREADS, 0, B, N, level);
+    };
+    for (int level = 0; level < soft; ++level) bor_level(level);
+    if (soft < levels) {
+        // (a skipped level never writes its n_roots entry: the entries of the call were zeroed above, and k_bor_finish /
+        // k_stats read "1" at the first level that reports one component, which is at or below `soft - 1` then)
+        int rc = launch_conditional(ctx, COND_LEVELS, B.n_roots, n, soft, levels, [&] {
+            for (int level = soft; level < levels; ++level) bor_level(level);
+        });
+        if (rc) return rc;
     }
     LAUNCH(ctx, k_bor_finish, gS, SEG_THREADS, 0, B, N, levels);
     mark(ctx, "boruvka");
@@ -484,20 +568,24 @@ int segment_dev(dofs3d_ctx* ctx, const float* d_flow, int already_blurred, int n
         LAUNCH(ctx, k_time_repair_short, gN, SEG_THREADS, 0, R);
         LAUNCH(ctx, k_time_repair_long, dim3(148 * 2), 256, 0, R);
         mark(ctx, "time_repair");
-        // fallback, enabled on the device by *need_full: stable 64-bit sorts by slot, then by weight
+        // fallback, enabled on the device by *need_full: stable 64-bit sorts by slot, then by weight.  Its 36 launches
+        // are the body of an IF node on that flag (launch_conditional): a batch without a long tie run skips them.
         const int* enable = ctx->repair_flags + 1;
         const dim3 gF(std::max(1, 148 * 4 / n), n);
         u64* fA = ctx->keysA + (size_t)F * N;
         u64* fB = ctx->keysA + 2 * (size_t)F * N;
-        LAUNCH(ctx, k_time_fallback_slots, gF, SEG_THREADS, 0, order, B.loss_time, fA, N, enable);
-        int fs = radix_sort<u64>(ctx, fA, order, fB, order_other, (size_t)N, N, n, ceil_log2(ctx->S), false, "time_fallback",
-                                 "time_fallback", "time_fallback", enable);
-        u32* o1 = fs ? order_other : order;  // roots in slot order
-        u32* o1_other = fs ? order : order_other;
-        LAUNCH(ctx, k_time_fallback_weights, gF, SEG_THREADS, 0, o1, B.loss_time, ctx->flow_blur, fA, N, W, enable);
-        fs = radix_sort<u64>(ctx, fA, o1, fB, o1_other, (size_t)N, N, n, 64, false, "time_fallback", "time_fallback",
-                             "time_fallback", enable);
-        LAUNCH(ctx, k_time_fallback_rank, gF, SEG_THREADS, 0, fs ? fB : fA, fs ? o1_other : o1, times, N, enable);
+        int rc_fb = launch_conditional(ctx, COND_FLAG, enable, n, 0, 0, [&] {
+            LAUNCH(ctx, k_time_fallback_slots, gF, SEG_THREADS, 0, order, B.loss_time, fA, N, enable);
+            int fs = radix_sort<u64>(ctx, fA, order, fB, order_other, (size_t)N, N, n, ceil_log2(ctx->S), false, "time_fallback",
+                                     "time_fallback", "time_fallback", enable);
+            u32* o1 = fs ? order_other : order;  // roots in slot order
+            u32* o1_other = fs ? order : order_other;
+            LAUNCH(ctx, k_time_fallback_weights, gF, SEG_THREADS, 0, o1, B.loss_time, ctx->flow_blur, fA, N, W, enable);
+            fs = radix_sort<u64>(ctx, fA, o1, fB, o1_other, (size_t)N, N, n, 64, false, "time_fallback", "time_fallback",
+                                 "time_fallback", enable);
+            LAUNCH(ctx, k_time_fallback_rank, gF, SEG_THREADS, 0, fs ? fB : fA, fs ? o1_other : o1, times, N, enable);
+        });
+        if (rc_fb) return rc_fb;
         mark(ctx, "time_fallback");
     }
     BorState BT = B;  // from here on loss_time means time
@@ -558,14 +646,25 @@ int segment_dev(dofs3d_ctx* ctx, const float* d_flow, int already_blurred, int n
     R.tile_carry = ctx->tile_carry;
     R.tiles_cap = ctx->tiles_cap;
     R.rcp = ctx->rcp_table;
-    for (int wave = 1; wave <= levels; ++wave) {
+    auto replay_wave = [&](int wave) {
         LAUNCH(ctx, k_replay_short, gS, SEG_THREADS, 0, R, wave);
         LAUNCH(ctx, k_replay_scan, gS, REPLAY_TILE, 0, R, wave);
         LAUNCH(ctx, k_replay_carry, dim3(n), 32, 0, R, wave);
         LAUNCH(ctx, k_replay_operands, gS, SEG_THREADS, 0, R, wave);
         LAUNCH(ctx, k_replay_serial_long, dim3(148 * 4), 32 * REPLAY_WARPS, 0, R, wave);
         LAUNCH(ctx, k_replay_gates, gS, SEG_THREADS, 0, R, wave);
+    };
+    // a root's wave is the level at which it loses, so the frames of the previous call's depth have no events beyond wave
+    // `soft`; the waves between it and the last one (the final roots' chains) are an IF body like the late levels
+    const int soft_wave = std::min(soft, levels - 1);
+    for (int wave = 1; wave <= soft_wave; ++wave) replay_wave(wave);
+    if (soft_wave + 1 <= levels - 1) {
+        int rc = launch_conditional(ctx, COND_WAVES, ctx->wave_start, n, soft_wave, levels, [&] {
+            for (int wave = soft_wave + 1; wave <= levels - 1; ++wave) replay_wave(wave);
+        });
+        if (rc) return rc;
     }
+    replay_wave(levels);
     mark(ctx, "chain_replay");
 
     // K11 + K12 lifting, selection, boxes, labels
@@ -618,6 +717,8 @@ int segment_dev(dofs3d_ctx* ctx, const float* d_flow, int already_blurred, int n
            n_edges_of(W, H, ctx->seg.neighbors), levels, ctx->repair_flags + 1, ctx->long_count,
            ctx->sweep_ticket + RS_MAX_PASSES, ctx->sticky, ctx->cand_cap, ctx->box_cap, spec.max_boxes);
     CK(cudaMemcpyAsync(ctx->h_sticky, ctx->sticky, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    LAUNCH(ctx, k_call_levels, 1, 1, 0, B.levels, n, ctx->d_call_levels);
+    CK(cudaMemcpyAsync(ctx->h_call_levels, ctx->d_call_levels, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     return 0;
 }
 
@@ -909,6 +1010,11 @@ int dofs3d_create(dofs3d_ctx** out, int device, int width, int height, int max_p
     CK(cudaMallocHost(&ctx->h_sticky, sizeof(int)));
     *ctx->h_sticky = 0;
     DA(ctx->sticky, 1);
+    DA(ctx->d_call_levels, 1);
+    CK(cudaMallocHost(&ctx->h_call_levels, sizeof(int)));
+    *ctx->h_call_levels = 0;
+    if (const char* e = getenv("DOFS3D_COND_GRAPHS")) ctx->use_cond_graphs = atoi(e) != 0;
+    if (const char* e = getenv("DOFS3D_SOFT_LEVELS")) ctx->soft_levels_forced = atoi(e);
     {
         std::vector<double> rcp(RCP_TABLE, 0.0);
         for (int i = 1; i < RCP_TABLE; ++i) rcp[i] = 1.0 / (double)i;
@@ -962,6 +1068,11 @@ void dofs3d_destroy(dofs3d_ctx* ctx) {
     for (void* p : ctx->allocs) cudaFree(p);
     farneback_free(&ctx->fb);
     if (ctx->h_sticky) cudaFreeHost(ctx->h_sticky);
+    if (ctx->h_call_levels) cudaFreeHost(ctx->h_call_levels);
+    for (auto& g : ctx->cond_graphs) {
+        cudaGraphExecDestroy(g.exec);
+        cudaGraphDestroy(g.graph);
+    }
     for (int i = 0; i < 2; ++i) {
         if (ctx->stage[i]) cudaFree(ctx->stage[i]);
         if (ctx->stage_free[i]) cudaEventDestroy(ctx->stage_free[i]);

@@ -2123,6 +2123,37 @@ k_pack_boxes(const Box* __restrict__ boxes, const int* __restrict__ n_boxes, int
     for (int i = threadIdx.x; i < keep * WORDS; i += blockDim.x) dst[i] = src[i];
 }
 
+// Predicates of the conditional graph nodes that skip work a batch does not need (dofs3d.cu: launch_conditional):
+//   COND_LEVELS  some frame of the batch is not one component yet after level `arg - 1`
+//   COND_WAVES   some frame has merge events in the waves arg+1 .. last-1 (the last wave is always replayed)
+//   COND_FLAG    *flag != 0 (the exact fallback of the merge-time sort)
+enum { COND_LEVELS = 0, COND_WAVES = 1, COND_FLAG = 2 };
+__global__ void k_set_condition(cudaGraphConditionalHandle handle, int kind, const int* __restrict__ data, int n_frames, int F,
+                                int arg, int last) {
+    __shared__ int s_any;
+    if (threadIdx.x == 0) s_any = 0;
+    __syncthreads();
+    int any = 0;
+    if (kind == COND_FLAG) {
+        any = threadIdx.x == 0 && *data != 0;
+    } else {
+        for (int f = threadIdx.x; f < n_frames; f += blockDim.x) {
+            if (kind == COND_LEVELS) any |= data[(arg - 1) * F + f] != 1;                                   // n_roots[level][frame]
+            else any |= data[f * (EV_MAX_WAVES + 1) + arg + 1] != data[f * (EV_MAX_WAVES + 1) + last];     // wave_start[frame][wave]
+        }
+    }
+    if (any) s_any = 1;
+    __syncthreads();
+    if (threadIdx.x == 0) cudaGraphSetConditional(handle, s_any ? 1u : 0u);
+}
+
+// the largest number of Boruvka levels any frame of the call needed: the next call enqueues that many (+1) unconditionally
+__global__ void k_call_levels(const int* __restrict__ levels, int n_frames, int* __restrict__ out) {
+    int m = 0;
+    for (int f = 0; f < n_frames; ++f) m = max(m, levels[f]);
+    *out = m;
+}
+
 #define STICKY_INTERNAL 1    // Boruvka did not converge (non-finite flow) or a sort look-back timed out
 #define STICKY_CANDIDATES 2  // candidate queue overflow
 #define STICKY_BOXES 4       // more boxes than the caller's max_boxes / the box list
