@@ -1048,6 +1048,7 @@ static int ensure_flow(dofs3d_ctx* ctx) {
         fc.poly_sigma = p.poly_sigma;
         size_t fbytes = 0;
         if (const char* e = getenv("DOFS3D_FLOW_FUSE")) ctx->fb.fuse_um = atoi(e) != 0;  // (its second M buffer is only allocated then)
+        if (const char* e = getenv("DOFS3D_BS7_FLOAT")) ctx->fb.bs7_float = atoi(e) != 0;
         int rc = farneback_alloc(&ctx->fb, width, height, (int)F, fc, &fbytes);
         ctx->bytes += (long long)fbytes;
         if (const char* e = getenv("DOFS3D_PYR_TILED")) ctx->fb.pyr_untiled = atoi(e) == 0;

@@ -86,6 +86,7 @@ struct FlowBuffers {
     float* M = nullptr;      // [F][N][5]
     float* M2 = nullptr;     // [F][N][5] second M buffer of the fused box-filter + update-matrices iterations
     bool fuse_um = false;    // A/B knob (DOFS3D_FLOW_FUSE=1)
+    bool bs7_float = true;   // A/B knob (DOFS3D_BS7_FLOAT=0: double window sums in shared memory, k_box_solve7)
     float2* flowA = nullptr; // [F][N]
     float2* flowB = nullptr; // [F][N]
     bool pyr_untiled = true;             // A/B knob (DOFS3D_PYR_TILED=1 selects k_pyr_level_tiled): measured on the B200, the
@@ -877,6 +878,125 @@ k_box_solve7(const float* __restrict__ M, float2* __restrict__ flow, int Wk, int
     }
 }
 
+// ---- the same kernel with FLOAT window sums in shared memory ----------------------------------------------------------
+// k_box_solve7 is bound by 64-bit shared-memory wavefronts (ncu: l1tex 76 %, DRAM 22 %): five channels of double window sums
+// cross shared memory three times.  Here the vertical 15-row sum is still accumulated in a double register (first window
+// direct, then + entering - leaving, exactly as above) but rounded to float ONCE when it is handed over; the horizontal
+// windows are balanced float trees (<= 5 roundings each); only the 2x2 solve converts back to double.  Every shared-memory access is 32 bits wide:
+// half the wavefronts, a third of the footprint (25.6 KB instead of 55.3 KB per block).
+// Accuracy: OpenCV keeps these sums in double; the float hand-over perturbs a window sum by <= 2^-24 relative and the
+// 15 + 7 float additions of a horizontal window by about 1e-6 relative.  Measured with oracle/farneback_np.py on the
+// repo's pair against cv2: EPE max 1.6e-4 / mean 1.37e-6 with double sums, max 2.2e-4 / mean 1.46e-6 with float sums in BOTH
+// directions (the stated bar is 1e-3 / 1e-5) — the flow tolerance does not notice; tests/test_gpu_fullsize.py checks the
+// 1080p and 4K fields on the device.
+#define BS7F_VC 87   // floats per (row, channel) of vertical sums: conflict-free sliding-window reads (brute-forced layout)
+#define BS7F_VR 440
+#define BS7F_HC 71   // floats per (row, channel) of window sums
+#define BS7F_HR 360
+#ifndef BS7F_BLOCKS
+#define BS7F_BLOCKS 3
+#endif
+#ifndef BS7F_SUB
+#define BS7F_SUB 8    // rows per shared-memory phase
+#endif
+#ifndef BS7F_ROWS
+#define BS7F_ROWS 64  // rows per strip
+#endif
+#define BS7F_SMEM ((size_t)BS7F_SUB * (BS7F_VR + BS7F_HR) * sizeof(float))
+
+template <bool FUSE>
+DOFS_D void bs7f_rows(const float* s_v, float* s_h, float2* __restrict__ flow, int pair, int x0, int yb, int nb, int Wk, int Hk,
+                      double scale, const Bs7Fuse& fu) {
+    constexpr int m = BS7_M;
+    const int e = threadIdx.x;
+    __syncthreads();
+    for (int wi = e; wi < 5 * 8 * BS7F_SUB; wi += BS7_THREADS) {
+        const int hg = wi & 7, hr = (wi >> 3) % BS7F_SUB, hc = wi / (8 * BS7F_SUB);  // (group of 8 outputs, row, channel), groups fastest
+        if (hr >= nb) continue;
+        const float* v = s_v + hr * BS7F_VR + hc * BS7F_VC + 9 * hg;  // column 8*hg of the strip
+        float* h = s_h + hr * BS7F_HR + hc * BS7F_HC + 9 * hg;
+        // the eight 15-wide windows of the group as balanced trees over shared partial sums (pairs, quads, octets): at
+        // most five float roundings per window instead of the 15 + 2 per step of a sliding float sum
+        float a[2 * m + 8];
+#pragma unroll
+        for (int i = 0; i < 2 * m + 8; ++i) a[i] = v[bs7_pad(i)];
+        float p2[2 * m + 7], p4[2 * m + 5], p8[2 * m + 1];
+#pragma unroll
+        for (int i = 0; i < 2 * m + 7; ++i) p2[i] = xfadd(a[i], a[i + 1]);
+#pragma unroll
+        for (int i = 0; i < 2 * m + 5; ++i) p4[i] = xfadd(p2[i], p2[i + 2]);
+#pragma unroll
+        for (int i = 0; i < 2 * m + 1; ++i) p8[i] = xfadd(p4[i], p4[i + 4]);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) h[k] = xfadd(p8[k], xfadd(p4[k + 8], xfadd(p2[k + 12], a[k + 14])));
+    }
+    __syncthreads();
+    for (int o = e; o < nb * BS7_COLS; o += BS7_THREADS) {
+        const int tx = o & (BS7_COLS - 1), r = o >> 6;
+        const int x = x0 + tx, y = yb + r;
+        if (x >= Wk) continue;
+        const float* h = s_h + r * BS7F_HR + bs7_pad(tx);
+        const double g11 = xdmul((double)h[0], scale), g12 = xdmul((double)h[BS7F_HC], scale), g22 = xdmul((double)h[2 * BS7F_HC], scale);
+        const double h1 = xdmul((double)h[3 * BS7F_HC], scale), h2 = xdmul((double)h[4 * BS7F_HC], scale);
+        const double idet = xddiv(1.0, xdadd(xdsub(xdmul(g11, g22), xdmul(g12, g12)), 1e-3));
+        const float u = (float)xdmul(xdsub(xdmul(g11, h2), xdmul(g12, h1)), idet);
+        const float w = (float)xdmul(xdsub(xdmul(g22, h1), xdmul(g12, h2)), idet);
+        if (FUSE) update_matrices_pixel(fu.R, fu.M_out, Wk, Hk, fu.ps, pair, x, y, make_float2(u, w));
+        else flow[((size_t)pair * Hk + y) * Wk + x] = make_float2(u, w);
+    }
+    __syncthreads();
+}
+
+template <bool FUSE>
+__global__ void __launch_bounds__(BS7_THREADS, BS7F_BLOCKS)
+k_box_solve7f(const float* __restrict__ M, float2* __restrict__ flow, int Wk, int Hk, Bs7Fuse fu) {
+    extern __shared__ __align__(16) unsigned char bx7f_smem[];
+    float* s_v = reinterpret_cast<float*>(bx7f_smem);  // [BS7_SUB][5][BS7F_VC] (+ padding to BS7F_VR)
+    float* s_h = s_v + BS7F_SUB * BS7F_VR;              // [BS7_SUB][5][BS7F_HC]
+    constexpr int m = BS7_M;
+    const int pair = blockIdx.z;
+    const int x0 = blockIdx.x * BS7_COLS;
+    const int y_begin = blockIdx.y * BS7F_ROWS, y_end = min(y_begin + BS7F_ROWS, Hk);
+    const float* src = M + (size_t)pair * Wk * Hk * 5;
+    const size_t pitch = (size_t)Wk * 5;
+    const int e = threadIdx.x;
+    const bool owner = e < BS7_SPAN * 5;
+    const float* col = src;
+    int v_at = 0;
+    if (owner) {
+        const int cx = e / 5, c = e - cx * 5;
+        col = src + (size_t)min(max(x0 + cx - m, 0), Wk - 1) * 5 + c;  // replicated border columns
+        v_at = c * BS7F_VC + bs7_pad(cx);
+    }
+    double s = 0;
+    if (owner) {
+#pragma unroll
+        for (int j = -m; j <= m; ++j) s += (double)col[(size_t)min(max(y_begin + j, 0), Hk - 1) * pitch];
+    }
+    const double scale = 1.0 / (double)(BS7_WIN * BS7_WIN);
+    for (int yb = y_begin; yb < y_end; yb += BS7F_SUB) {
+        const int nb = min(BS7F_SUB, y_end - yb);
+        if (owner) {
+#pragma unroll
+            for (int r0 = 0; r0 < BS7F_SUB; r0 += 4) {  // four rows of loads in flight at a time
+                float vin[4], vout[4];
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const int y = yb + r0 + r;
+                    vin[r] = col[(size_t)min(y + m, Hk - 1) * pitch];
+                    vout[r] = col[(size_t)max(y - m - 1, 0) * pitch];
+                }
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    if (yb + r0 + r != y_begin) s += (double)vin[r] - (double)vout[r];
+                    s_v[(r0 + r) * BS7F_VR + v_at] = (float)s;
+                }
+            }
+        }
+        bs7f_rows<FUSE>(s_v, s_h, flow, pair, x0, yb, nb, Wk, Hk, scale, fu);
+    }
+}
+
 #define BS7_SMEM ((size_t)BS7_SUB * (BS7_VR + BS7_HR) * sizeof(double))
 
 inline size_t box_solve_smem(int m) {
@@ -890,6 +1010,10 @@ inline int farneback_set_attributes() {
         return 3;
     if (cudaFuncSetAttribute(k_box_solve7<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BS7_SMEM) != cudaSuccess) return 3;
     if (cudaFuncSetAttribute(k_box_solve7<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BS7_SMEM) != cudaSuccess) return 3;
+    if (BS7F_SMEM > 48 * 1024) {
+        if (cudaFuncSetAttribute(k_box_solve7f<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BS7F_SMEM) != cudaSuccess) return 3;
+        if (cudaFuncSetAttribute(k_box_solve7f<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BS7F_SMEM) != cudaSuccess) return 3;
+    }
     return 0;
 }
 
@@ -898,7 +1022,7 @@ inline void farneback_set_carveout(int pct) {
     const void* ks[] = {(const void*)k_bgr2gray, (const void*)k_pyr_level0, (const void*)k_pyr_level, (const void*)k_pyr_level_tiled,
                         (const void*)k_polyexp<5>, (const void*)k_polyexp<0>, (const void*)k_update_matrices<UM_FLOW>,
                         (const void*)k_update_matrices<UM_START>, (const void*)k_box_solve, (const void*)k_box_solve7<false>,
-                        (const void*)k_box_solve7<true>};
+                        (const void*)k_box_solve7<true>, (const void*)k_box_solve7f<false>, (const void*)k_box_solve7f<true>};
     for (const void* k : ks) cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
 }
 
@@ -976,7 +1100,8 @@ inline int farneback_run(FlowBuffers& fb, const u8* d_gray0, const u8* d_gray1, 
         float* M_next = fb.M2;
         for (int it = 0; it < fb.cfg.iters; ++it) {
             const bool last = it == fb.cfg.iters - 1;
-            const dim3 g7((L.w + BS7_COLS - 1) / BS7_COLS, (L.h + BS7_ROWS - 1) / BS7_ROWS, n);
+            const int rows7 = fb.bs7_float ? BS7F_ROWS : BS7_ROWS;
+            const dim3 g7((L.w + BS7_COLS - 1) / BS7_COLS, (L.h + rows7 - 1) / rows7, n);
             if (m == BS7_M && fb.fuse_um && !last) {
                 // box filter + solve + the next iteration's update-matrices in one kernel: the flow of this iteration is
                 // never stored, its M goes to the other buffer (blocks still read the halo of the current one)
@@ -984,7 +1109,8 @@ inline int farneback_run(FlowBuffers& fb, const u8* d_gray0, const u8* d_gray1, 
                 fu.R = fb.R;
                 fu.M_out = M_next;
                 fu.ps = ps;
-                k_box_solve7<true><<<g7, BS7_THREADS, BS7_SMEM, stream>>>(M_in, cur, L.w, L.h, fu);
+                if (fb.bs7_float) k_box_solve7f<true><<<g7, BS7_THREADS, BS7F_SMEM, stream>>>(M_in, cur, L.w, L.h, fu);
+                else k_box_solve7<true><<<g7, BS7_THREADS, BS7_SMEM, stream>>>(M_in, cur, L.w, L.h, fu);
                 st->launches++;
                 FLOW_MARK(st, k == 0 ? "flow.box_solve.L0" : "flow.box_solve");
                 float* t = M_in;
@@ -992,7 +1118,9 @@ inline int farneback_run(FlowBuffers& fb, const u8* d_gray0, const u8* d_gray1, 
                 M_next = t;
                 continue;
             }
-            if (m == BS7_M)
+            if (m == BS7_M && fb.bs7_float)
+                k_box_solve7f<false><<<g7, BS7_THREADS, BS7F_SMEM, stream>>>(M_in, cur, L.w, L.h, Bs7Fuse());
+            else if (m == BS7_M)
                 k_box_solve7<false><<<g7, BS7_THREADS, BS7_SMEM, stream>>>(M_in, cur, L.w, L.h, Bs7Fuse());
             else
                 k_box_solve<<<g_box, box_solve_threads(m), bx_smem, stream>>>(M_in, cur, L.w, L.h, m);
