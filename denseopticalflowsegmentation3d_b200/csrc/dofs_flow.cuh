@@ -896,6 +896,11 @@ k_box_solve7(const float* __restrict__ M, float2* __restrict__ flow, int Wk, int
 #ifndef BS7F_BLOCKS
 #define BS7F_BLOCKS 3
 #endif
+#ifndef BS7F_TREE
+#define BS7F_TREE 1  // 1: every window as a balanced tree (default: the quietest); 0: one tree, the others slid outwards from it
+                     // (7 % faster alone, same throughput in the bench, but the border-band scatter of the 256x144 video test
+                     // grows from below 1 % to 1.2 % of the pixels above 1e-3 px)
+#endif
 #ifndef BS7F_SUB
 #define BS7F_SUB 8    // rows per shared-memory phase
 #endif
@@ -915,11 +920,12 @@ DOFS_D void bs7f_rows(const float* s_v, float* s_h, float2* __restrict__ flow, i
         if (hr >= nb) continue;
         const float* v = s_v + hr * BS7F_VR + hc * BS7F_VC + 9 * hg;  // column 8*hg of the strip
         float* h = s_h + hr * BS7F_HR + hc * BS7F_HC + 9 * hg;
-        // the eight 15-wide windows of the group as balanced trees over shared partial sums (pairs, quads, octets): at
-        // most five float roundings per window instead of the 15 + 2 per step of a sliding float sum
         float a[2 * m + 8];
 #pragma unroll
         for (int i = 0; i < 2 * m + 8; ++i) a[i] = v[bs7_pad(i)];
+#if BS7F_TREE
+        // the eight 15-wide windows of the group as balanced trees over shared partial sums (pairs, quads, octets): at
+        // most five float roundings per window
         float p2[2 * m + 7], p4[2 * m + 5], p8[2 * m + 1];
 #pragma unroll
         for (int i = 0; i < 2 * m + 7; ++i) p2[i] = xfadd(a[i], a[i + 1]);
@@ -929,6 +935,26 @@ DOFS_D void bs7f_rows(const float* s_v, float* s_h, float2* __restrict__ flow, i
         for (int i = 0; i < 2 * m + 1; ++i) p8[i] = xfadd(p4[i], p4[i + 4]);
 #pragma unroll
         for (int k = 0; k < 8; ++k) h[k] = xfadd(p8[k], xfadd(p4[k + 8], xfadd(p2[k + 12], a[k + 14])));
+#else
+        // window 4 (of 0..7) as a balanced tree (4 roundings), the others by sliding outwards from it: + the entering value
+        // - the leaving one, at most 4 steps = 8 more roundings (a window slid all the way from a sequential sum of
+        // window 0 carries 15 + 14; that form was measurably noisier at the ill-conditioned pixels of the 4K field)
+        const float q0 = xfadd(xfadd(a[4], a[5]), xfadd(a[6], a[7])), q1 = xfadd(xfadd(a[8], a[9]), xfadd(a[10], a[11]));
+        const float q2 = xfadd(xfadd(a[12], a[13]), xfadd(a[14], a[15])), q3 = xfadd(xfadd(a[16], a[17]), a[18]);
+        float t = xfadd(xfadd(q0, q1), xfadd(q2, q3));  // a[4..18]
+        h[4] = t;
+        float up = t;
+#pragma unroll
+        for (int k = 5; k < 8; ++k) {
+            up = xfadd(up, xfsub(a[k + 14], a[k - 1]));
+            h[k] = up;
+        }
+#pragma unroll
+        for (int k = 3; k >= 0; --k) {
+            t = xfadd(t, xfsub(a[k], a[k + 15]));
+            h[k] = t;
+        }
+#endif
     }
     __syncthreads();
     for (int o = e; o < nb * BS7_COLS; o += BS7_THREADS) {
