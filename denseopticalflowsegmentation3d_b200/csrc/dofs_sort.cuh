@@ -20,7 +20,12 @@
 #include "dofs_common.cuh"
 
 #define RS_THREADS 256
-#define RS_ITEMS 8
+#ifndef RS_ITEMS
+#define RS_ITEMS 12
+#endif
+#ifndef RS_BLOCKS
+#define RS_BLOCKS 3
+#endif
 #define RS_TILE (RS_THREADS * RS_ITEMS)
 #define RS_WARPS (RS_THREADS / 32)
 #define RS_BINS 256
@@ -264,7 +269,7 @@ k_radix_bases(const u32* __restrict__ ghist, u32* __restrict__ gbase) {
 }
 
 template <typename K>
-__global__ void __launch_bounds__(RS_THREADS, 4)
+__global__ void __launch_bounds__(RS_THREADS, RS_BLOCKS)
 k_radix_onesweep(const K* __restrict__ keys_in, const u32* __restrict__ vals_in, K* __restrict__ keys_out,
                  u32* __restrict__ vals_out, size_t frame_stride, const u32* __restrict__ gbase /* this pass: [frame][..] */,
                  u32* __restrict__ status /* [frame][tile][256], zeroed */, int* __restrict__ ticket /* zeroed */,
