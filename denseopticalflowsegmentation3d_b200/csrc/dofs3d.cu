@@ -583,7 +583,7 @@ int segment_dev(dofs3d_ctx* ctx, const float* d_flow, int already_blurred, int n
             LAUNCH(ctx, k_time_fallback_weights, gF, SEG_THREADS, 0, o1, B.loss_time, ctx->flow_blur, fA, N, W, enable);
             fs = radix_sort<u64>(ctx, fA, o1, fB, o1_other, (size_t)N, N, n, 64, false, "time_fallback", "time_fallback",
                                  "time_fallback", enable);
-            LAUNCH(ctx, k_time_fallback_rank, gF, SEG_THREADS, 0, fs ? fB : fA, fs ? o1_other : o1, times, N, enable);
+            LAUNCH(ctx, k_time_fallback_rank, gF, SEG_THREADS, 0, fs ? fB : fA, fs ? o1_other : o1, times, order, N, enable);
         });
         if (rc_fb) return rc_fb;
         mark(ctx, "time_fallback");
@@ -591,24 +591,28 @@ int segment_dev(dofs3d_ctx* ctx, const float* d_flow, int already_blurred, int n
     BorState BT = B;  // from here on loss_time means time
     BT.loss_time = times;
 
-    // K9b events: winner of every loss, sorted by (wave, winner, time); buffers alias the dead edge prefixes / time keys
+    // K9b events: winner of every loss, in (wave, winner, time) order = a stable 32-bit sort by (wave, winner) of the
+    // time-ordered list of losing roots.  Buffers alias the dead edge prefixes (keysB holds 4 F N u32).
     EvBits eb;
-    eb.tb = ceil_log2((unsigned long long)N);  // times are positions among the <= N-1 merges
     eb.wb = ceil_log2((unsigned long long)N);
-    u64* evA = ctx->keysB;
-    u64* evB = ctx->keysB + (size_t)F * N;
-    u32* evlA = ctx->valsA;
-    u32* evlB = ctx->valsB;
-    LAUNCH(ctx, k_event_keys, gS, SEG_THREADS, 0, BT, ctx->win, evA, N, eb);
+    if (eb.wb + 5 > 31) {
+        ctx->err = "internal: event key too wide";
+        return DOFS3D_ERR_INTERNAL;
+    }
+    u32* evR = reinterpret_cast<u32*>(ctx->keysB);  // key by root id
+    u32* evA = evR + (size_t)F * N;
+    u32* evB = evA + (size_t)F * N;
+    LAUNCH(ctx, k_event_keys, gS, SEG_THREADS, 0, BT, ctx->win, evR, N, eb);
+    LAUNCH(ctx, k_event_gather, gS, SEG_THREADS, 0, order, evR, evA, N);
     mark(ctx, "event_keys");
-    side = radix_sort_onesweep<u64>(ctx, evA, evlA, evB, evlB, (size_t)N, N, n, eb.tb + eb.wb + 5, true, "event_sort.hist",
+    side = radix_sort_onesweep<u32>(ctx, evA, order, evB, order_other, (size_t)N, N, n, eb.wb + 5, false, "event_sort.hist",
                                     "event_sort.scatter");
     if (side < 0) {
         ctx->err = "internal: event key too wide";
         return DOFS3D_ERR_INTERNAL;
     }
-    const u64* ev_key = side ? evB : evA;
-    const u32* ev_loser = side ? evlB : evlA;
+    const u32* ev_key = side ? evB : evA;
+    const u32* ev_loser = side ? order_other : order;
     LAUNCH(ctx, k_wave_starts, gS, SEG_THREADS, 0, ev_key, ctx->wave_start, N, eb);
     mark(ctx, "event_waves");
 
@@ -616,6 +620,7 @@ int segment_dev(dofs3d_ctx* ctx, const float* d_flow, int already_blurred, int n
     ReplayArgs R;
     R.ev_key = ev_key;
     R.ev_loser = ev_loser;
+    R.time = times;
     R.wave_start = ctx->wave_start;
     R.rstate = ctx->rstate;
     R.flow = ctx->flow_blur;

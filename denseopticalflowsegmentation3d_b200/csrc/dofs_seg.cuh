@@ -611,6 +611,25 @@ DOFS_D bool bor_done(const BorState& S, int level, int frame) {
 
 #define GRID_STRIDE(p, N) for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < (N); p += gridDim.x * blockDim.x)
 
+// The per-pixel Boruvka kernels read the rows above and below a pixel (neighbour components, neighbour edge slots).
+// BOR_TILE_W > 0: a block visits BOR_TILE_W x (SEG_THREADS / BOR_TILE_W) tiles of the image instead of 256 consecutive
+// pixels of a row, so the neighbour rows are its own lines in L1.  `continue` in the body moves on to the next tile.
+#ifndef BOR_TILE_W
+#define BOR_TILE_W 0
+#endif
+#if BOR_TILE_W
+#define BOR_TILE_H (SEG_THREADS / BOR_TILE_W)
+#define PIXEL_TILES(p, W, H)                                                                                              \
+    for (int t_ = blockIdx.x, tnx_ = ((W) + BOR_TILE_W - 1) / BOR_TILE_W, tn_ = tnx_ * (((H) + BOR_TILE_H - 1) / BOR_TILE_H); \
+         t_ < tn_; t_ += gridDim.x)                                                                                       \
+        for (int px_ = (t_ % tnx_) * BOR_TILE_W + (int)(threadIdx.x % BOR_TILE_W),                                          \
+                 py_ = (t_ / tnx_) * BOR_TILE_H + (int)(threadIdx.x / BOR_TILE_W), p = py_ * (W) + px_, once_ = 1;         \
+             once_; once_ = 0)                                                                                            \
+            if (px_ < (W) && py_ < (H))
+#else
+#define PIXEL_TILES(p, W, H) for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < (W) * (H); p += gridDim.x * blockDim.x)
+#endif
+
 // Incident edge e of pixel p: e < 4 its own back-edge slots 4p+e; e = 4..7 the back-edges of the right, lower-right,
 // upper-right and lower neighbours that point at p.
 DOFS_D int incident_pixel(int p, int e, int W) {
@@ -704,7 +723,7 @@ k_bor_pixel(BorState S, const u32* __restrict__ prefix, size_t prefix_stride, co
     const u32* up = S.up + fo;
     const u32* pre = prefix + (size_t)frame * prefix_stride;
     u64* best = S.best + fo;
-    GRID_STRIDE(p, N) {
+    PIXEL_TILES(p, W, N / W) {
         const u32 m = S.mask[fo + p];
         if (m == 0) continue;
         // fold != 0 (A/B knob, DOFS3D_BOR_FOLD=1): there is no separate relabel pass after level 0 and `comp` of a live
@@ -777,7 +796,7 @@ k_bor_level0_pick(BorState S, const u32* __restrict__ prefix, size_t prefix_stri
     const size_t fo = (size_t)frame * N;
     const u32* pre = prefix + (size_t)frame * prefix_stride;
     const float2* f = flow + fo;
-    GRID_STRIDE(p, N) {
+    PIXEL_TILES(p, W, H) {
         const int y = p / W, x = p - y * W;
         const uint4 r4 = *reinterpret_cast<const uint4*>(pre + 4 * (size_t)p);
         u64 b = PICK_NONE;
@@ -979,7 +998,8 @@ k_time_keys(BorState S, const u32* __restrict__ prefix, size_t prefix_stride, u3
 
 struct TimeRepairArgs {
     const u32* key;      // [F][N] sorted keys
-    const u32* comp;     // [F][N] sorted payload (losing roots); the list itself is left as it is
+    u32* comp;           // [F][N] sorted payload (losing roots); runs that share a prefix are put in exact order in place
+                         //         (the event sort below is a stable sort of this list)
     const u32* slot;     // [F][N] by root id: the slot of the edge at which it loses
     const float2* flow;  // [F][N] blurred flow
     u32* time;           // [F][N] out: time[c] = position, INF for roots that never lose
@@ -1041,7 +1061,10 @@ k_time_repair_short(TimeRepairArgs A) {
         ss[m + 1] = sl;
         kk[m + 1] = w;
     }
-    for (int j = 0; j < len; ++j) A.time[fo + cc[j]] = (u32)(i + j);
+    for (int j = 0; j < len; ++j) {
+        A.time[fo + cc[j]] = (u32)(i + j);
+        A.comp[fo + i + j] = cc[j];
+    }
 }
 
 __global__ void __launch_bounds__(256)
@@ -1099,7 +1122,10 @@ k_time_repair_long(TimeRepairArgs A) {
             }
             __syncthreads();
         }
-        for (int j = threadIdx.x; j < len; j += 256) A.time[fo + s_cmp[j]] = (u32)(i0 + j);
+        for (int j = threadIdx.x; j < len; j += 256) {
+            A.time[fo + s_cmp[j]] = (u32)(i0 + j);
+            A.comp[fo + i0 + j] = s_cmp[j];
+        }
         __syncthreads();
     }
 }
@@ -1130,54 +1156,68 @@ k_time_fallback_weights(const u32* __restrict__ comp, const u32* __restrict__ sl
 }
 
 __global__ void __launch_bounds__(SEG_THREADS)
-k_time_fallback_rank(const u64* __restrict__ wkey, const u32* __restrict__ comp, u32* __restrict__ time, int N,
+k_time_fallback_rank(const u64* __restrict__ wkey, const u32* comp, u32* __restrict__ time, u32* order_out, int N,
                      const int* __restrict__ enable) {
     if (*enable == 0) return;
     const int frame = blockIdx.y;
     const size_t fo = (size_t)frame * N;
-    GRID_STRIDE(i, N) time[fo + comp[fo + i]] = wkey[fo + i] == 0xFFFFFFFFFFFFFFFFull ? DOFS_INF32 : (u32)i;
+    GRID_STRIDE(i, N) {
+        const u32 c = comp[fo + i];
+        time[fo + c] = wkey[fo + i] == 0xFFFFFFFFFFFFFFFFull ? DOFS_INF32 : (u32)i;
+        order_out[fo + i] = c;  // (may be `comp` itself) the list the event sort starts from
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
-// K9b  winner of every merge event (one event per losing root) and the event sort key
-//      key = lvl[winner] << (tb + wb) | winner << tb | time ; payload = loser
-//      tb = bits of a time (< N), wb = bits of a pixel id (< N): as few radix passes as the frame size
-//      allows (1080p: 21 + 21 + 5 = 47 bits -> 6 passes)
+// K9b  winner of every merge event (one event per losing root) and the event sort.  Events are wanted in
+//      (wave of the winner, winner, time) order.  The losing roots are already listed in time order (K8), so a
+//      STABLE sort of that list on the 32-bit key
+//          key = lvl[winner] << wb | winner        (wb = bits of a pixel id; 1080p: 5 + 21 bits -> 4 radix passes)
+//      is enough: the time never enters the key (it is read back from time[loser] by the few merges that pass the
+//      gates).  k_event_keys writes the key by root id (coalesced, next to the walk that finds the winner),
+//      k_event_gather lines the keys up with the time-ordered list.
 // ---------------------------------------------------------------------------------------------
-#define EV_KEY_NONE 0xFFFFFFFFFFFFFFFFull
+#define EV_KEY_NONE 0xFFFFFFFFu  // a root that never loses; real keys are below 2^(wb + 5) <= 2^31
 
 struct EvBits {
-    int tb, wb;
+    int wb;
 };
-DOFS_D u64 ev_chain(u64 key, EvBits b) { return key >> b.tb; }  // wave | winner
-DOFS_D u32 ev_winner(u64 key, EvBits b) { return (u32)(key >> b.tb) & ((1u << b.wb) - 1u); }
-DOFS_D u32 ev_time(u64 key, EvBits b) { return (u32)key & ((1u << b.tb) - 1u); }
-DOFS_D int ev_wave(u64 key, EvBits b) { return key == EV_KEY_NONE ? EV_MAX_WAVES - 1 : (int)(key >> (b.tb + b.wb)); }
+DOFS_D u32 ev_chain(u32 key, EvBits) { return key; }  // wave | winner
+DOFS_D u32 ev_winner(u32 key, EvBits b) { return key & ((1u << b.wb) - 1u); }
+DOFS_D int ev_wave(u32 key, EvBits b) { return key == EV_KEY_NONE ? EV_MAX_WAVES - 1 : (int)(key >> b.wb); }
 
 __global__ void __launch_bounds__(SEG_THREADS)
-k_event_keys(BorState S, u32* __restrict__ win, u64* __restrict__ ev_key, int N, EvBits eb) {
+k_event_keys(BorState S, u32* __restrict__ win, u32* __restrict__ key_by_root, int N, EvBits eb) {
     const int frame = blockIdx.y;
     const size_t fo = (size_t)frame * N;
     GRID_STRIDE(c, N) {
         const u32 t = S.loss_time[fo + c];
         if (t == DOFS_INF32) {
             win[fo + c] = (u32)c;
-            ev_key[fo + c] = EV_KEY_NONE;
+            key_by_root[fo + c] = EV_KEY_NONE;
             continue;
         }
         u32 cur = S.up[fo + c];
         while (S.loss_time[fo + cur] < t) cur = S.up[fo + cur];
         win[fo + c] = cur;
-        ev_key[fo + c] = ((u64)S.lvl[fo + cur] << (eb.tb + eb.wb)) | ((u64)cur << eb.tb) | (u64)t;
+        key_by_root[fo + c] = ((u32)S.lvl[fo + cur] << eb.wb) | cur;
     }
+}
+
+// position i of the time-ordered list of losing roots -> the key of that root (roots that never lose are its tail)
+__global__ void __launch_bounds__(SEG_THREADS)
+k_event_gather(const u32* __restrict__ order, const u32* __restrict__ key_by_root, u32* __restrict__ ev_key, int N) {
+    const int frame = blockIdx.y;
+    const size_t fo = (size_t)frame * N;
+    GRID_STRIDE(i, N) ev_key[fo + i] = key_by_root[fo + order[fo + i]];
 }
 
 // first event index of every wave (events are sorted by key)
 __global__ void __launch_bounds__(SEG_THREADS)
-k_wave_starts(const u64* __restrict__ ev_key, int* __restrict__ wave_start /* [F][EV_MAX_WAVES+1] */, int N,
+k_wave_starts(const u32* __restrict__ ev_key, int* __restrict__ wave_start /* [F][EV_MAX_WAVES+1] */, int N,
               EvBits eb) {
     const int frame = blockIdx.y;
-    const u64* k = ev_key + (size_t)frame * N;
+    const u32* k = ev_key + (size_t)frame * N;
     int* ws = wave_start + frame * (EV_MAX_WAVES + 1);
     GRID_STRIDE(i, N) {
         const int wi = ev_wave(k[i], eb);
@@ -1252,8 +1292,9 @@ struct TileAgg {  // what a tile passes on: the scan value of its last event, an
 };
 
 struct ReplayArgs {
-    const u64* ev_key;     // [F][N] sorted
-    const u32* ev_loser;   // [F][N] sorted payload
+    const u32* ev_key;     // [F][N] sorted: wave | winner
+    const u32* ev_loser;   // [F][N] sorted payload, in time order inside a chain
+    const u32* time;       // [F][N] per root id: position of its loss in the merge sequence
     const int* wave_start; // [F][EV_MAX_WAVES+1]
     RootState* rstate;     // [F][N] size, mean flow and box of every root that has won a merge (written when its chain ends)
     const float2* flow;    // [F][N] blurred flow: the state of a root that never won is its pixel (Forest::Forest, graph.cpp:129-148)
@@ -1334,12 +1375,12 @@ DOFS_D RootState root_absorbed(const ReplayArgs& A, size_t fo, u32 a, int wave) 
 
 #define EV_FLAG_STARTED 0x80000000u  // in ev_size after k_replay_scan: the event's chain started inside its tile
 
-DOFS_D void replay_gate(const ReplayArgs& A, int frame, u32 r, u32 time, int s, float2 f, ushort4 bb) {
+DOFS_D void replay_gate(const ReplayArgs& A, int frame, u32 r, u32 loser, int s, float2 f, ushort4 bb) {
     const int y = (int)r / A.W;
     if (s >= A.min_size && !(y < A.H / 10)) {                                       // graph.cpp:280, 288
         const double move = norm2d(f.x, f.y);
         if (!(move < xddiv((double)(3 * (y + 1)), (double)A.H)))                     // graph.cpp:296
-            push_candidate(A, frame, r, time, s, f, bb);
+            push_candidate(A, frame, r, A.time[(size_t)frame * A.N + loser], s, f, bb);
     }
 }
 
@@ -1359,10 +1400,10 @@ k_replay_short(ReplayArgs A, int wave) {
     const int w0 = A.wave_start[frame * (EV_MAX_WAVES + 1) + wave];
     const int w1 = A.wave_start[frame * (EV_MAX_WAVES + 1) + wave + 1];
     const size_t fo = (size_t)frame * A.N;
-    const u64* key = A.ev_key + fo;
+    const u32* key = A.ev_key + fo;
     for (int i = w0 + blockIdx.x * blockDim.x + threadIdx.x; i < w1; i += gridDim.x * blockDim.x) {
-        u64 k = key[i];
-        const u64 chain = ev_chain(k, A.eb);
+        u32 k = key[i];
+        const u32 chain = ev_chain(k, A.eb);
         if (i > w0 && ev_chain(key[i - 1], A.eb) == chain) continue;  // not a head
         const u32 r = ev_winner(k, A.eb);
         if (i + REPLAY_SHORT < w1 && ev_chain(key[i + REPLAY_SHORT], A.eb) == chain) {
@@ -1379,16 +1420,20 @@ k_replay_short(ReplayArgs A, int wave) {
 #if REPLAY_PIPELINED
         // the state of the NEXT absorbed root is requested before the arithmetic of this event: the chain of dependent
         // loads (key -> loser id -> its state, a random gather) then runs under the division-free mean update and the gates
-        RootState ra = root_absorbed(A, fo, A.ev_loser[fo + j], wave);
+        u32 la = A.ev_loser[fo + j];
+        RootState ra = root_absorbed(A, fo, la, wave);
         for (;;) {
             const int jn = j + 1;
-            u64 kn = 0;
+            u32 kn = 0, ln = 0;
             bool same = false;
             RootState rn = ra;
             if (jn < w1) {
                 kn = key[jn];
                 same = ev_chain(kn, A.eb) == chain;
-                if (same) rn = root_absorbed(A, fo, A.ev_loser[fo + jn], wave);
+                if (same) {
+                    ln = A.ev_loser[fo + jn];
+                    rn = root_absorbed(A, fo, ln, wave);
+                }
             }
             const int sa = ra.size;
             const float fsa = (float)sa;
@@ -1401,15 +1446,17 @@ k_replay_short(ReplayArgs A, int wave) {
             bb.y = min(bb.y, ra.bbox.y);
             bb.z = max(bb.z, ra.bbox.z);
             bb.w = max(bb.w, ra.bbox.w);
-            replay_gate(A, frame, r, ev_time(k, A.eb), s, f, bb);
+            replay_gate(A, frame, r, la, s, f, bb);
             j = jn;
             if (!same) break;
             ra = rn;
+            la = ln;
             k = kn;
         }
 #else
         for (;;) {
-            const RootState ra = root_absorbed(A, fo, A.ev_loser[fo + j], wave);
+            const u32 la = A.ev_loser[fo + j];
+            const RootState ra = root_absorbed(A, fo, la, wave);
             const int sa = ra.size;
             const float2 fa = make_float2(ra.fx, ra.fy);
             const ushort4 ba = ra.bbox;
@@ -1423,7 +1470,7 @@ k_replay_short(ReplayArgs A, int wave) {
             bb.y = min(bb.y, ba.y);
             bb.z = max(bb.z, ba.z);
             bb.w = max(bb.w, ba.w);
-            replay_gate(A, frame, r, ev_time(k, A.eb), s, f, bb);
+            replay_gate(A, frame, r, la, s, f, bb);
             ++j;
             if (j >= w1) break;
             k = key[j];
@@ -1451,7 +1498,7 @@ k_replay_scan(ReplayArgs A, int wave) {
         const bool valid = j < w1;
         ScanTuple t = scan_identity();
         bool head = false;
-        u64 key = 0;
+        u32 key = 0;
         bool is_long = false;
         if (valid) {
             key = A.ev_key[fo + j];
@@ -1584,7 +1631,7 @@ k_replay_operands(ReplayArgs A, int wave) {
     const size_t fo = (size_t)frame * A.N;
     if (A.long_count[wave] == 0) return;
     for (int j = w0 + blockIdx.x * blockDim.x + threadIdx.x; j < w1; j += gridDim.x * blockDim.x) {
-        const u64 key = A.ev_key[fo + j];
+        const u32 key = A.ev_key[fo + j];
         const u32 r = ev_winner(key, A.eb);
         if (A.long_flag[fo + r] == 0) continue;  // replayed by k_replay_short
         const u32 raw = (u32)A.ev_size[fo + j];
@@ -1650,8 +1697,8 @@ k_replay_serial_long(ReplayArgs A, int wave) {
         const int frame = (int)it.x, i0 = (int)it.y;
         const size_t fo = (size_t)frame * A.N;
         const int w1 = A.wave_start[frame * (EV_MAX_WAVES + 1) + wave + 1];
-        const u64 k0 = A.ev_key[fo + i0];
-        const u64 chain = ev_chain(k0, A.eb);
+        const u32 k0 = A.ev_key[fo + i0];
+        const u32 chain = ev_chain(k0, A.eb);
         float2 f;
         {
             f = A.flow[fo + ev_winner(k0, A.eb)];  // the root's own pixel (root_initial)
@@ -1661,7 +1708,7 @@ k_replay_serial_long(ReplayArgs A, int wave) {
         // event (operands of any event position are readable), the test happens when the round is consumed
         float4 n_op[2];
         double n_inv[2];
-        u64 n_key[2];
+        u32 n_key[2];
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
             const int j = j0 + 32 * q + lane;
@@ -1779,13 +1826,13 @@ k_replay_gates(ReplayArgs A, int wave) {
     const size_t fo = (size_t)frame * A.N;
     if (A.long_count[wave] == 0) return;
     for (int j = w0 + blockIdx.x * blockDim.x + threadIdx.x; j < w1; j += gridDim.x * blockDim.x) {
-        const u64 key = A.ev_key[fo + j];
+        const u32 key = A.ev_key[fo + j];
         const u32 r = ev_winner(key, A.eb);
         if (A.long_flag[fo + r] == 0) continue;  // replayed by k_replay_short
         const int s = A.ev_size[fo + j];
         const float2 f = A.ev_flow[fo + j];
         const ushort4 bb = A.ev_bbox[fo + j];
-        replay_gate(A, frame, r, ev_time(key, A.eb), s, f, bb);
+        replay_gate(A, frame, r, A.ev_loser[fo + j], s, f, bb);
         if (j + 1 >= w1 || ev_chain(A.ev_key[fo + j + 1], A.eb) != ev_chain(key, A.eb)) {
             root_store(&A.rstate[fo + r], s, f, bb);
         }
