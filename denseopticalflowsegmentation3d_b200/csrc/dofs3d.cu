@@ -520,7 +520,7 @@ int segment_dev(dofs3d_ctx* ctx, const float* d_flow, int already_blurred, int n
             LAUNCH(ctx, k_bor_root, gS, SEG_THREADS, 0, B, W, N, level);
         }
         LAUNCH(ctx, k_bor_contract, gS, SEG_THREADS, 0, B, N, level);
-        if (level == 0 || !ctx->bor_fold) LAUNCH(ctx, k_bor_relabel, gS, SEG_THREADS, 0, B, N, level);
+        if ((level == 0 && !BOR_L0_COMP) || (level > 0 && !ctx->bor_fold)) LAUNCH(ctx, k_bor_relabel, gS, SEG_THREADS, 0, B, N, level);
     };
     for (int level = 0; level < soft; ++level) bor_level(level);
     if (soft < levels) {

@@ -557,6 +557,15 @@ k_prefix_repair_long(RepairArgs A) {
 // Kernels are grid-stride with a small fixed grid, so a level with nothing left costs microseconds.
 // ---------------------------------------------------------------------------------------------
 #define EV_MAX_WAVES 32
+// Measured knobs of the level kernels (both on; 32 pairs alone: Boruvka 9.13 -> 8.45 ms, bench 1 033 -> 1 058 pairs/s):
+//   BOR_L0_COMP       the level-0 contraction writes `comp` itself (every pixel is a root there): no level-0 relabel pass
+//   BOR_RELABEL_MASK  the relabel pass skips pixels whose edges have all become internal (four mask bytes per load)
+#ifndef BOR_L0_COMP
+#define BOR_L0_COMP 1
+#endif
+#ifndef BOR_RELABEL_MASK
+#define BOR_RELABEL_MASK 1
+#endif
 #ifndef BOR_PIXEL_BLOCKS
 #define BOR_PIXEL_BLOCKS 8  // resident blocks per SM the pixel kernel is compiled for: it is bound by memory latency, so full
                             // occupancy (32 registers, a few spilled words) beats a spill-free 48-register build by 10 %
@@ -919,6 +928,9 @@ k_bor_contract(BorState S, int N, int level) {
             survives = g == c;
             if (survives) S.best[fo + c] = PICK_NONE;  // only live roots collect offers in the next level
             if (!survives || level == 0) S.up[fo + c] = g;  // (level 0 initialises `up`: a survivor points at itself)
+#if BOR_L0_COMP
+            if (level == 0) S.comp[fo + c] = g;  // every pixel is a root here: its component, without a relabel pass
+#endif
         }
         list_append_block(next, &S.n_roots[level * S.F + frame], survives, c);
     }
@@ -935,6 +947,26 @@ k_bor_relabel(BorState S, int N, int level) {
         GRID_STRIDE(p, N) S.comp[fo + p] = S.up[fo + p];
         return;
     }
+#if BOR_RELABEL_MASK
+    // a pixel whose incident edges are all internal is never looked at again (k_bor_pixel skips it and its neighbours
+    // reach it only through an edge that is still external, which it would see too): its entry may go stale
+    if ((N & 3) == 0) {
+        const u32* mask4 = reinterpret_cast<const u32*>(S.mask + fo);
+        uint4* comp4 = reinterpret_cast<uint4*>(S.comp + fo);
+        GRID_STRIDE(i, N / 4) {
+            const u32 m4 = mask4[i];
+            if (m4 == 0) continue;
+            uint4 c = comp4[i];
+            const uint4 c0 = c;
+            if (m4 & 0x000000FFu) c.x = S.up[fo + c.x];
+            if (m4 & 0x0000FF00u) c.y = S.up[fo + c.y];
+            if (m4 & 0x00FF0000u) c.z = S.up[fo + c.z];
+            if (m4 & 0xFF000000u) c.w = S.up[fo + c.w];
+            if (c.x != c0.x || c.y != c0.y || c.z != c0.z || c.w != c0.w) comp4[i] = c;
+        }
+        return;
+    }
+#endif
     GRID_STRIDE(p, N) {
         const u32 c = S.comp[fo + p];
         const u32 g = S.up[fo + c];
