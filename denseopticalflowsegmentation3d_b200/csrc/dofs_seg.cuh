@@ -658,15 +658,25 @@ DOFS_D u32 incident_mask(int x, int y, int W, int H, int neighbors8) {
 }
 
 
-// append to a per-frame list with ONE atomic per block (all threads of the block must call it; `want` selects).
-// One atomic per warp is not enough here: a level-0 contraction appends from every warp of a frame to the same
-// counter, and same-address atomics that return a value serialise in L2.
-DOFS_D void list_append_block(u32* list, int* counter, bool want, u32 value) {
+// append to a per-frame list with ONE atomic per block and BOR_APPEND_ROUNDS items per thread (all threads of the
+// block must call it; bit r of `want` selects value[r]).  One atomic per warp is not enough here: a level-0 contraction
+// appends from every warp of a frame to the same counter, and same-address atomics that return a value serialise in
+// L2.  Batching the rounds divides the three barriers and the atomic by the batch.
+#ifndef BOR_APPEND_ROUNDS
+#define BOR_APPEND_ROUNDS 4
+#endif
+DOFS_D void list_append_block(u32* list, int* counter, u32 want, const u32 (&value)[BOR_APPEND_ROUNDS]) {
     __shared__ int s_count[SEG_THREADS / 32];
     __shared__ int s_base;
     const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
-    const unsigned m = __ballot_sync(0xffffffffu, want);
-    if (lane == 0) s_count[wrp] = __popc(m);
+    const int mine = __popc(want);
+    int incl = mine;  // inclusive scan of the per-thread counts inside the warp
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    if (lane == 31) s_count[wrp] = incl;
     __syncthreads();
     if (threadIdx.x == 0) {
         int tot = 0;
@@ -678,7 +688,10 @@ DOFS_D void list_append_block(u32* list, int* counter, bool want, u32 value) {
         s_base = tot ? atomicAdd(counter, tot) : 0;
     }
     __syncthreads();
-    if (want) list[s_base + s_count[wrp] + __popc(m & ((1u << lane) - 1u))] = value;
+    int pos = s_base + s_count[wrp] + incl - mine;
+#pragma unroll
+    for (int r = 0; r < BOR_APPEND_ROUNDS; ++r)
+        if ((want >> r) & 1u) list[pos++] = value[r];
     __syncthreads();
 }
 
@@ -905,34 +918,40 @@ k_bor_contract(BorState S, int N, int level) {
     u32* next = S.roots[(level + 1) & 1] + fo;
     const int count = level == 0 ? N : S.n_roots[(level - 1) * S.F + frame];
     const int rounds = (count + gridDim.x * blockDim.x - 1) / (gridDim.x * blockDim.x);
-    for (int it = 0; it < rounds; ++it) {
-        const int i = (it * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x;
-        bool survives = false;
-        u32 c = 0;
-        if (i < count) {
-            c = level == 0 ? (u32)i : list[i];
-            // follow the hooks with path halving: concurrent writers only ever replace a pointer by one of its
-            // ancestors, so any interleaving still ends at the same root
-            u32 g = c;
-            for (;;) {
-                const u32 nx = newp[g];
-                if (nx == g) break;
-                const u32 nn = newp[nx];
-                if (nn == nx) {
-                    g = nx;
-                    break;
+    for (int it0 = 0; it0 < rounds; it0 += BOR_APPEND_ROUNDS) {
+        u32 want = 0;
+        u32 live[BOR_APPEND_ROUNDS];
+#pragma unroll
+        for (int r = 0; r < BOR_APPEND_ROUNDS; ++r) {
+            const int i = ((it0 + r) * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x;
+            live[r] = 0;
+            if (it0 + r < rounds && i < count) {
+                const u32 c = level == 0 ? (u32)i : list[i];
+                // follow the hooks with path halving: concurrent writers only ever replace a pointer by one of its
+                // ancestors, so any interleaving still ends at the same root
+                u32 g = c;
+                for (;;) {
+                    const u32 nx = newp[g];
+                    if (nx == g) break;
+                    const u32 nn = newp[nx];
+                    if (nn == nx) {
+                        g = nx;
+                        break;
+                    }
+                    newp[g] = nn;
+                    g = nn;
                 }
-                newp[g] = nn;
-                g = nn;
-            }
-            survives = g == c;
-            if (survives) S.best[fo + c] = PICK_NONE;  // only live roots collect offers in the next level
-            if (!survives || level == 0) S.up[fo + c] = g;  // (level 0 initialises `up`: a survivor points at itself)
+                const bool survives = g == c;
+                if (survives) S.best[fo + c] = PICK_NONE;  // only live roots collect offers in the next level
+                if (!survives || level == 0) S.up[fo + c] = g;  // (level 0 initialises `up`: a survivor points at itself)
 #if BOR_L0_COMP
-            if (level == 0) S.comp[fo + c] = g;  // every pixel is a root here: its component, without a relabel pass
+                if (level == 0) S.comp[fo + c] = g;  // every pixel is a root here: its component, without a relabel pass
 #endif
+                live[r] = c;
+                if (survives) want |= 1u << r;
+            }
         }
-        list_append_block(next, &S.n_roots[level * S.F + frame], survives, c);
+        list_append_block(next, &S.n_roots[level * S.F + frame], want, live);
     }
 }
 
