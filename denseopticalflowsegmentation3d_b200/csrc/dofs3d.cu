@@ -516,7 +516,10 @@ int segment_dev(dofs3d_ctx* ctx, const float* d_flow, int already_blurred, int n
             LAUNCH(ctx, k_bor_level0_pick, gS, SEG_THREADS, 0, B, prefix, ctx->S, ctx->flow_blur, W, H, N);
             LAUNCH(ctx, k_bor_level0_root, gS, SEG_THREADS, 0, B, W, H, N, ctx->seg.neighbors == 8 ? 1 : 0);
         } else {
-            LAUNCH(ctx, k_bor_pixel, gS, SEG_THREADS, 0, B, prefix, ctx->S, ctx->flow_blur, W, N, level, ctx->bor_fold ? 1 : 0);
+            if (level >= BOR_COMPACT_FROM && bor_pixel_packed_ok(N))
+                LAUNCH(ctx, k_bor_pixel_packed, gS, SEG_THREADS, 0, B, prefix, ctx->S, ctx->flow_blur, W, N, level, ctx->bor_fold ? 1 : 0);
+            else
+                LAUNCH(ctx, k_bor_pixel, gS, SEG_THREADS, 0, B, prefix, ctx->S, ctx->flow_blur, W, N, level, ctx->bor_fold ? 1 : 0);
             LAUNCH(ctx, k_bor_root, gS, SEG_THREADS, 0, B, W, N, level);
         }
         LAUNCH(ctx, k_bor_contract, gS, SEG_THREADS, 0, B, N, level);
