@@ -499,11 +499,8 @@ int segment_dev(dofs3d_ctx* ctx, const float* d_flow, int already_blurred, int n
     // enqueued, finished frames skip
     BorState& B = ctx->bor;
     const dim3 gS = grid_stride(ctx, n);
-    // per-root selection state: no score yet (0), no snapshot time (INF), no box (-1); everything else per root is written
-    // by the level-0 kernels
-    CK(cudaMemsetAsync(ctx->best_score, 0, sizeof(u64) * (size_t)n * N, ctx->stream));
-    CK(cudaMemsetAsync(ctx->sel_time, 0xFF, sizeof(u32) * (size_t)n * N, ctx->stream));
-    CK(cudaMemsetAsync(ctx->sel_box, 0xFF, sizeof(int) * (size_t)n * N, ctx->stream));
+    // (the per-root arrays are written by the level-0 kernels; the selection state of a root is reset when it queues a
+    // merge, k_select_reset)
     CK(cudaMemsetAsync(ctx->counters, 0, sizeof(int) * CNT_KINDS * F, ctx->stream));
     CK(cudaMemsetAsync(B.n_roots, 0, sizeof(int) * EV_MAX_WAVES * F, ctx->stream));
     const int levels = ctx->max_levels;
@@ -689,13 +686,14 @@ int segment_dev(dofs3d_ctx* ctx, const float* d_flow, int already_blurred, int n
     A.N = N;
     const dim3 gC128 = grid1(ctx->cand_cap, 128, n);
     const dim3 gC = grid1(ctx->cand_cap, SEG_THREADS, n);
+    LAUNCH(ctx, k_select_reset, gC, SEG_THREADS, 0, A);
     LAUNCH(ctx, k_lift_score, gC128, 128, 0, A, ctx->seg);
     LAUNCH(ctx, k_select_time, gC, SEG_THREADS, 0, A);
     LAUNCH(ctx, k_emit_boxes<dofs3d_box>, gC128, 128, 0, A, ctx->seg, ctx->boxes_tmp, ctx->box_cap);
     mark(ctx, "lifting");
     const dim3 gB = grid1(ctx->box_cap, SEG_THREADS, n);
     LAUNCH(ctx, k_sort_boxes<dofs3d_box>, gB, SEG_THREADS, 0, ctx->boxes_tmp, ctx->boxes, A.n_boxes, ctx->box_cap,
-           ctx->sel_box, N);
+           ctx->sel_box, ctx->win, N);
     LAUNCH(ctx, k_box_parents<dofs3d_box>, gB, SEG_THREADS, 0, ctx->boxes, A.n_boxes, ctx->box_cap, BT.loss_time,
            ctx->win, ctx->sel_time, ctx->sel_box, N);
     ctx->labels_fmt = spec.fmt == DOFS3D_LABELS_I32 ? DOFS3D_LABELS_I32 : DOFS3D_LABELS_U16;

@@ -1968,6 +1968,7 @@ DOFS_D u64 score_key(double s) {
     const u64 b = (u64)__double_as_longlong(s);
     return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
 }
+#define WIN_HAS_BOX 0x80000000u  // in win[root]: the root emitted a box (set by k_sort_boxes, read by first_box_above)
 #define CAND_KEPT 1u  // Candidate::pad bit 0: passed the convexity and score gates (graph.cpp:341-346)
 
 struct SelectArgs {
@@ -1982,6 +1983,19 @@ struct SelectArgs {
     int cand_cap;
     int N;
 };
+
+// The per-root selection state is dense ([F][N]) but only the roots of queued merges ever use it: they are reset here,
+// nothing else is initialised (a root "has a box" through WIN_HAS_BOX in its `win` word, see first_box_above).
+__global__ void __launch_bounds__(SEG_THREADS)
+k_select_reset(SelectArgs A) {
+    const int frame = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = min(A.n_cand[frame], A.cand_cap);
+    if (i >= n) return;
+    const size_t g = (size_t)frame * A.N + A.cand[(size_t)frame * A.cand_cap + i].root;
+    A.best_score[g] = 0;  // "no score yet"
+    A.sel_time[g] = DOFS_INF32;
+}
 
 // graph.cpp:302-348: convexity, get_score, class-dependent convexity gate, score threshold
 __global__ void __launch_bounds__(128)
@@ -2082,7 +2096,7 @@ k_emit_boxes(SelectArgs A, SegParams P, Box* __restrict__ tmp_boxes, int box_cap
 template <typename Box>
 __global__ void __launch_bounds__(SEG_THREADS)
 k_sort_boxes(const Box* __restrict__ tmp_boxes, Box* __restrict__ boxes, const int* __restrict__ n_boxes, int box_cap,
-             int* __restrict__ sel_box, int N) {
+             int* __restrict__ sel_box, u32* __restrict__ win, int N) {
     const int frame = blockIdx.y;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int n = min(n_boxes[frame], box_cap);
@@ -2093,10 +2107,12 @@ k_sort_boxes(const Box* __restrict__ tmp_boxes, Box* __restrict__ boxes, const i
     for (int j = 0; j < n; ++j) pos += src[j].root < root ? 1 : 0;
     boxes[(size_t)frame * box_cap + pos] = src[i];
     sel_box[(size_t)frame * N + root] = pos;
+    win[(size_t)frame * N + root] |= WIN_HAS_BOX;  // (one box per root: no other thread touches this word)
 }
 
 // Walk the union-find link forest (parent = winner at loss time, <= max-rank hops): a pixel / set that
 // entered root a's set at time t_in belongs to a's snapshot taken at sel_time[a] iff t_in <= sel_time[a].
+// `win` carries WIN_HAS_BOX for the roots that emitted a box: only their sel_time / sel_box entries are defined.
 DOFS_D int first_box_above(const u32* loss_time, const u32* win, const u32* sel_time, const int* sel_box, u32 cur,
                            bool include_self) {
     u32 t_in = 0;
@@ -2104,15 +2120,15 @@ DOFS_D int first_box_above(const u32* loss_time, const u32* win, const u32* sel_
     if (!include_self) {
         t_in = loss_time[cur];
         if (t_in == DOFS_INF32) return -1;
-        cur = win[cur];
+        cur = win[cur] & ~WIN_HAS_BOX;
     }
     for (;;) {
-        const u32 st = sel_time[cur];
-        if (st != DOFS_INF32 && (first || st >= t_in)) return sel_box[cur];
+        const u32 w = win[cur];
+        if ((w & WIN_HAS_BOX) && (first || sel_time[cur] >= t_in)) return sel_box[cur];
         first = false;
         t_in = loss_time[cur];
         if (t_in == DOFS_INF32) return -1;
-        cur = win[cur];
+        cur = w & ~WIN_HAS_BOX;
     }
 }
 
