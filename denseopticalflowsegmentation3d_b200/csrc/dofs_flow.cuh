@@ -984,7 +984,8 @@ k_box_solve7f(const float* __restrict__ M, float2* __restrict__ flow, int Wk, in
     const int x0 = blockIdx.x * BS7_COLS;
     const int y_begin = blockIdx.y * BS7F_ROWS, y_end = min(y_begin + BS7F_ROWS, Hk);
     const float* src = M + (size_t)pair * Wk * Hk * 5;
-    const size_t pitch = (size_t)Wk * 5;
+    const int pitch = Wk * 5;  // (row * pitch stays an int product + one wide multiply-add per address: the vertical phase is
+                               //  half of this kernel's instructions, and 64-bit index arithmetic was a third of those)
     const int e = threadIdx.x;
     const bool owner = e < BS7_SPAN * 5;
     const float* col = src;
@@ -997,7 +998,7 @@ k_box_solve7f(const float* __restrict__ M, float2* __restrict__ flow, int Wk, in
     double s = 0;
     if (owner) {
 #pragma unroll
-        for (int j = -m; j <= m; ++j) s += (double)col[(size_t)min(max(y_begin + j, 0), Hk - 1) * pitch];
+        for (int j = -m; j <= m; ++j) s += (double)col[(long long)(min(max(y_begin + j, 0), Hk - 1) * pitch)];
     }
     const double scale = 1.0 / (double)(BS7_WIN * BS7_WIN);
     for (int yb = y_begin; yb < y_end; yb += BS7F_SUB) {
@@ -1009,8 +1010,8 @@ k_box_solve7f(const float* __restrict__ M, float2* __restrict__ flow, int Wk, in
 #pragma unroll
                 for (int r = 0; r < 4; ++r) {
                     const int y = yb + r0 + r;
-                    vin[r] = col[(size_t)min(y + m, Hk - 1) * pitch];
-                    vout[r] = col[(size_t)max(y - m - 1, 0) * pitch];
+                    vin[r] = col[(long long)(min(y + m, Hk - 1) * pitch)];
+                    vout[r] = col[(long long)(max(y - m - 1, 0) * pitch)];
                 }
 #pragma unroll
                 for (int r = 0; r < 4; ++r) {
