@@ -1058,6 +1058,7 @@ static int ensure_flow(dofs3d_ctx* ctx) {
         int rc = farneback_alloc(&ctx->fb, width, height, (int)F, fc, &fbytes);
         ctx->bytes += (long long)fbytes;
         if (const char* e = getenv("DOFS3D_PYR_TILED")) ctx->fb.pyr_untiled = atoi(e) == 0;
+        if (const char* e = getenv("DOFS3D_PYR_GENERIC")) ctx->fb.pyr_generic = atoi(e) != 0;
         if (ctx->carveout >= 0) farneback_set_carveout(ctx->carveout);
         if (rc) {
             ctx->err = farneback_error(rc);

@@ -89,6 +89,7 @@ struct FlowBuffers {
     bool bs7_float = true;   // A/B knob (DOFS3D_BS7_FLOAT=0: double window sums in shared memory, k_box_solve7)
     float2* flowA = nullptr; // [F][N]
     float2* flowB = nullptr; // [F][N]
+    bool pyr_generic = false;            // A/B knob (DOFS3D_PYR_GENERIC=1): the run-time-radius pyramid kernel for every level
     bool pyr_untiled = true;             // A/B knob (DOFS3D_PYR_TILED=1 selects k_pyr_level_tiled): measured on the B200, the
                                          // tiled kernel is 29 % faster alone (pyramid 1.34 -> 0.95 ms per 32 pairs) and costs
                                          // 10 % of the throughput when six contexts share the GPU (964 -> 862 pairs/s): its
@@ -285,6 +286,11 @@ DOFS_D void flow_linear_coord(int d, double scale, int src_n, int* i0, float* fr
     *frac = f;
 }
 
+// RT = the filter radius at compile time (1, 4, 9: the three coarser levels of pyr_scale 0.5), 0 = run time.  With RT
+// the row filter is unrolled: per tap a byte load, a conversion and two fma with the tap as a constant-bank operand,
+// instead of a counted loop that also fetches the tap (the kernel is bound by instruction issue: 19 x 20 taps per
+// output at the coarsest level).  Same fma chains in the same order: bit-identical.
+template <int RT>
 __global__ void __launch_bounds__(256)
 k_pyr_level(ImageSet imgs, float* __restrict__ I, int W, int H, int Wk, int Hk, SmoothTaps taps) {
     const int img = blockIdx.z;
@@ -293,7 +299,7 @@ k_pyr_level(ImageSet imgs, float* __restrict__ I, int W, int H, int Wk, int Hk, 
     if (x >= Wk || y >= Hk) return;
     const size_t N = (size_t)W * H;
     const u8* src = img < imgs.split ? imgs.base0 + (size_t)img * N : imgs.base1 + (size_t)(img - imgs.split) * N;
-    const int r = taps.radius;
+    const int r = RT ? RT : taps.radius;
     int sx, sy;
     float fx, fy;
     if (Wk == W && Hk == H) {  // resize to the same size is a copy
@@ -307,18 +313,31 @@ k_pyr_level(ImageSet imgs, float* __restrict__ I, int W, int H, int Wk, int Hk, 
     const int nx = fx != 0.f ? 2 : 1, ny = fy != 0.f ? 2 : 1;
     // column (vertical) filter of the row-filtered samples, for the nx x ny blurred samples
     float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};  // [dy][dx]
+    const bool interior = sx - r >= 0 && sx + r + 1 < W;
+#pragma unroll 1
     for (int j = -r; j <= r + ny - 1; ++j) {
         const int yy = flow_reflect101(sy + j, H);
-        const u8* row = src + (size_t)yy * W;
+        const u8* row = src + yy * W;  // (an image has fewer than 2^31 pixels)
         float h0 = 0.f, h1 = 0.f;  // row filter at columns sx and sx+1
-        const bool interior = sx - r >= 0 && sx + r + 1 < W;
         if (interior) {
-            float prev = (float)row[sx - r];
-            for (int i = -r; i <= r; ++i) {
-                const float nxt = (float)row[sx + i + 1];
-                h0 = fmaf(taps.k[i + r], prev, h0);
-                h1 = fmaf(taps.k[i + r], nxt, h1);
-                prev = nxt;
+            const u8* p = row + (sx - r);
+            if (RT) {
+                float v[2 * (RT ? RT : 1) + 2];
+#pragma unroll
+                for (int i = 0; i < 2 * RT + 2; ++i) v[i] = (float)p[i];
+#pragma unroll
+                for (int i = 0; i < 2 * RT + 1; ++i) {
+                    h0 = fmaf(taps.k[i], v[i], h0);
+                    h1 = fmaf(taps.k[i], v[i + 1], h1);
+                }
+            } else {
+                float prev = (float)p[0];
+                for (int i = -r; i <= r; ++i) {
+                    const float nxt = (float)p[i + r + 1];
+                    h0 = fmaf(taps.k[i + r], prev, h0);
+                    h1 = fmaf(taps.k[i + r], nxt, h1);
+                    prev = nxt;
+                }
             }
         } else {
             for (int i = -r; i <= r; ++i) {
@@ -502,12 +521,12 @@ k_polyexp(const float* __restrict__ I, float* __restrict__ R, int Wk, int Hk, Po
         const int ty = idx / span, cx = idx - ty * span;
         const int y = min(y0 + ty, Hk - 1);
         const int xs = min(max(x0 + cx - n, 0), Wk - 1);
-        const float c = src[(size_t)y * Wk + xs];
+        const float c = src[y * Wk + xs];  // (32-bit offsets inside an image: a third fewer instructions per load)
         float t0 = xfmul(c, pc.g[0]), t1 = 0.f, t2 = 0.f;
 #pragma unroll
         for (int k = 1; k <= n; ++k) {
-            const float a = src[(size_t)max(y - k, 0) * Wk + xs];
-            const float b = src[(size_t)min(y + k, Hk - 1) * Wk + xs];
+            const float a = src[max(y - k, 0) * Wk + xs];
+            const float b = src[min(y + k, Hk - 1) * Wk + xs];
             const float p = xfadd(a, b);
             t0 = xfadd(t0, xfmul(pc.g[k], p));
             t1 = xfadd(t1, xfmul(pc.xg[k], xfsub(b, a)));
@@ -1046,7 +1065,8 @@ inline int farneback_set_attributes() {
 
 // the same preferred shared-memory carveout for every kernel of the flow stage (see LAUNCH in dofs3d.cu)
 inline void farneback_set_carveout(int pct) {
-    const void* ks[] = {(const void*)k_bgr2gray, (const void*)k_pyr_level0, (const void*)k_pyr_level, (const void*)k_pyr_level_tiled,
+    const void* ks[] = {(const void*)k_bgr2gray, (const void*)k_pyr_level0, (const void*)k_pyr_level<0>, (const void*)k_pyr_level<1>, (const void*)k_pyr_level<4>,
+                        (const void*)k_pyr_level<9>, (const void*)k_pyr_level_tiled,
                         (const void*)k_polyexp<5>, (const void*)k_polyexp<0>, (const void*)k_update_matrices<UM_FLOW>,
                         (const void*)k_update_matrices<UM_START>, (const void*)k_box_solve, (const void*)k_box_solve7<false>,
                         (const void*)k_box_solve7<true>, (const void*)k_box_solve7f<false>, (const void*)k_box_solve7f<true>};
@@ -1106,8 +1126,14 @@ inline int farneback_run(FlowBuffers& fb, const u8* d_gray0, const u8* d_gray1, 
             const size_t smem = (size_t)TH * 64 * sizeof(float) + (size_t)TH * TW;
             if (smem <= PYR_TILED_MAX_SMEM && !fb.pyr_untiled)
                 k_pyr_level_tiled<<<g_img, blk, smem, stream>>>(fresh, I_fresh, fb.W, fb.H, L.w, L.h, L.taps, TW, TH);
+            else if (L.taps.radius == 1 && !fb.pyr_generic)
+                k_pyr_level<1><<<g_img, blk, 0, stream>>>(fresh, I_fresh, fb.W, fb.H, L.w, L.h, L.taps);
+            else if (L.taps.radius == 4 && !fb.pyr_generic)
+                k_pyr_level<4><<<g_img, blk, 0, stream>>>(fresh, I_fresh, fb.W, fb.H, L.w, L.h, L.taps);
+            else if (L.taps.radius == 9 && !fb.pyr_generic)
+                k_pyr_level<9><<<g_img, blk, 0, stream>>>(fresh, I_fresh, fb.W, fb.H, L.w, L.h, L.taps);
             else
-                k_pyr_level<<<g_img, blk, 0, stream>>>(fresh, I_fresh, fb.W, fb.H, L.w, L.h, L.taps);
+                k_pyr_level<0><<<g_img, blk, 0, stream>>>(fresh, I_fresh, fb.W, fb.H, L.w, L.h, L.taps);
         }
         FLOW_MARK(st, "flow.pyramid");
         if (fb.poly.n == 5)

@@ -57,13 +57,14 @@ DOFS_D u32 rs_block_excl_scan(u32 v, u32* s_warp /* >= 8 */, u32* total) {
 #ifndef RS_USE_MATCH_ANY
 #define RS_USE_MATCH_ANY 0  // A/B: the MATCH.ANY instruction instead of nine votes
 #endif
+template <int BITS = 9>
 DOFS_D u32 rs_match9(u32 d) {
 #if RS_USE_MATCH_ANY
     return __match_any_sync(0xffffffffu, d);
 #endif
     u32 peers = 0xffffffffu;
 #pragma unroll
-    for (int b = 0; b < 9; ++b) {
+    for (int b = 0; b < BITS; ++b) {
         const bool bit = (d >> b) & 1u;
         const u32 m = __ballot_sync(0xffffffffu, bit);
         peers &= bit ? m : ~m;
@@ -295,32 +296,58 @@ k_radix_onesweep(const K* __restrict__ keys_in, const u32* __restrict__ vals_in,
 
     // warp-striped load: element order inside the tile is (warp, item, lane) == memory order
     const int wbase = tile * RS_TILE + warp * (32 * RS_ITEMS);
+    const bool full = (tile + 1) * RS_TILE <= n;  // block-uniform: every tile of a frame but the last one
     K key[RS_ITEMS];
     u32 val[RS_ITEMS];
     u32 rnk[RS_ITEMS];
-#pragma unroll
-    for (int i = 0; i < RS_ITEMS; ++i) {
-        const int idx = wbase + i * 32 + lane;
-        const bool ok = idx < n;
-        key[i] = ok ? keys_in[idx] : (K)~(K)0;
-        val[i] = ok ? (iota_vals ? (u32)idx : vals_in[idx]) : 0u;
-    }
     u32* my_hist = s_whist + warp * RS_BINS;
+    if (full) {  // no range checks, eight votes per item
+        const K* kin = keys_in + wbase + lane;
+        const u32* vin = vals_in + wbase + lane;
 #pragma unroll
-    for (int i = 0; i < RS_ITEMS; ++i) {
-        const bool ok = wbase + i * 32 + lane < n;
-        const u32 d = ok ? ((u32)(key[i] >> shift) & 255u) : 256u;  // out-of-range lanes form their own group
-        const u32 peers = rs_match9(d);
-        const u32 below = __popc(peers & ((1u << lane) - 1u));
-        const int leader = __ffs(peers) - 1;
-        u32 pre = 0;
-        if (lane == leader && ok) {
-            pre = my_hist[d];
-            my_hist[d] = pre + __popc(peers);
+        for (int i = 0; i < RS_ITEMS; ++i) {
+            key[i] = kin[i * 32];
+            val[i] = iota_vals ? (u32)(wbase + i * 32 + lane) : vin[i * 32];
         }
-        pre = __shfl_sync(0xffffffffu, pre, leader);
-        rnk[i] = pre + below;
-        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < RS_ITEMS; ++i) {
+            const u32 d = (u32)(key[i] >> shift) & 255u;
+            const u32 peers = rs_match9<8>(d);
+            const u32 below = __popc(peers & ((1u << lane) - 1u));
+            const int leader = __ffs(peers) - 1;
+            u32 pre = 0;
+            if (lane == leader) {
+                pre = my_hist[d];
+                my_hist[d] = pre + __popc(peers);
+            }
+            pre = __shfl_sync(0xffffffffu, pre, leader);
+            rnk[i] = pre + below;
+            __syncwarp();
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < RS_ITEMS; ++i) {
+            const int idx = wbase + i * 32 + lane;
+            const bool ok = idx < n;
+            key[i] = ok ? keys_in[idx] : (K)~(K)0;
+            val[i] = ok ? (iota_vals ? (u32)idx : vals_in[idx]) : 0u;
+        }
+#pragma unroll
+        for (int i = 0; i < RS_ITEMS; ++i) {
+            const bool ok = wbase + i * 32 + lane < n;
+            const u32 d = ok ? ((u32)(key[i] >> shift) & 255u) : 256u;  // out-of-range lanes form their own group
+            const u32 peers = rs_match9<9>(d);
+            const u32 below = __popc(peers & ((1u << lane) - 1u));
+            const int leader = __ffs(peers) - 1;
+            u32 pre = 0;
+            if (lane == leader && ok) {
+                pre = my_hist[d];
+                my_hist[d] = pre + __popc(peers);
+            }
+            pre = __shfl_sync(0xffffffffu, pre, leader);
+            rnk[i] = pre + below;
+            __syncwarp();
+        }
     }
     __syncthreads();
 
@@ -362,8 +389,7 @@ k_radix_onesweep(const K* __restrict__ keys_in, const u32* __restrict__ vals_in,
 
 #pragma unroll
     for (int i = 0; i < RS_ITEMS; ++i) {
-        const int idx = wbase + i * 32 + lane;
-        if (idx < n) {
+        if (full || wbase + i * 32 + lane < n) {
             const u32 d = (u32)(key[i] >> shift) & 255u;
             const u32 pos = s_dlocal[d] + my_hist[d] + rnk[i];
             s_keys[pos] = key[i];
