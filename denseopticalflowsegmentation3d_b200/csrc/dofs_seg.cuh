@@ -744,44 +744,67 @@ DOFS_D void bor_pixel_one(const BorState& S, size_t fo, u32* comp, const u32* up
     // refreshed by its own thread: one hop from a current root is the root itself.  Pixels whose edges are all
     // internal are never read again and stay stale.  Measured on the B200 (32 pairs, alone): the extra random
     // gathers cost more than the streaming relabel pass they replace (Boruvka 9.4 -> 11.2 ms), so it is off.
-    const u32 c0 = comp[p];
+    // (three row pointers and compile-time column offsets: the eight neighbour reads and the four neighbour-slot reads
+    //  share their address arithmetic; the minimum is taken without branches.  Line-level ncu counts had put half of this
+    //  kernel's instructions in these two loops.)
+    const u32* cc = comp + p;
+    const u32* cu = cc - W;
+    const u32* cd = cc + W;
+    const u32 c0 = cc[0];
     const u32 cp = fold ? up[c0] : c0;
     if (cp != c0) comp[p] = cp;
     const u64 seen0 = best[cp];
     // independent loads first (the kernel is bound by memory latency): neighbour components, then their prefixes
+    // incident pixel of edge e: 0 left, 1 up, 2 up-left, 3 down-left, 4 right, 5 down-right, 6 up-right, 7 down
+    u32 q[8];
+    q[0] = (m & 1u) ? cc[-1] : c0;
+    q[1] = (m & 2u) ? cu[0] : c0;
+    q[2] = (m & 4u) ? cu[-1] : c0;
+    q[3] = (m & 8u) ? cd[-1] : c0;
+    q[4] = (m & 16u) ? cc[1] : c0;
+    q[5] = (m & 32u) ? cd[1] : c0;
+    q[6] = (m & 64u) ? cu[1] : c0;
+    q[7] = (m & 128u) ? cd[0] : c0;
     u32 out = 0;
 #pragma unroll
     for (int e = 0; e < 8; ++e)
-        if ((m >> e) & 1u) {
-            const u32 q0 = comp[incident_pixel(p, e, W)];
-            if (q0 != c0 && (!fold || up[q0] != cp)) out |= 1u << e;  // equal stale roots are equal current roots
-        }
+        if (q[e] != c0 && (!fold || up[q[e]] != cp)) out |= 1u << e;  // equal stale roots are equal current roots
     if (out != m) S.mask[fo + p] = (u8)out;  // an edge that became internal stays internal
     if (out == 0) return;
+    // prefixes of the outgoing edges (EDGE_PREFIX_INVALID = the largest value: a NaN / infinite weight is no edge, and
+    // neither is an edge that is not outgoing)
+    const u32* pp = pre + 4 * (size_t)p;
+    const u32* pu = pp - 4 * W;
+    const u32* pd = pp + 4 * W;
     u32 pr[8];
     {
-        uint4 r4 = make_uint4(0u, 0u, 0u, 0u);
-        if (out & 15u) r4 = *reinterpret_cast<const uint4*>(pre + 4 * (size_t)p);
-        pr[0] = r4.x, pr[1] = r4.y, pr[2] = r4.z, pr[3] = r4.w;
+        uint4 r4 = make_uint4(EDGE_PREFIX_INVALID, EDGE_PREFIX_INVALID, EDGE_PREFIX_INVALID, EDGE_PREFIX_INVALID);
+        if (out & 15u) r4 = *reinterpret_cast<const uint4*>(pp);
+        pr[0] = (out & 1u) ? r4.x : EDGE_PREFIX_INVALID;
+        pr[1] = (out & 2u) ? r4.y : EDGE_PREFIX_INVALID;
+        pr[2] = (out & 4u) ? r4.z : EDGE_PREFIX_INVALID;
+        pr[3] = (out & 8u) ? r4.w : EDGE_PREFIX_INVALID;
     }
+    pr[4] = (out & 16u) ? pp[4] : EDGE_PREFIX_INVALID;       // right neighbour's left edge
+    pr[5] = (out & 32u) ? pd[4 + 2] : EDGE_PREFIX_INVALID;   // down-right: its up-left edge
+    pr[6] = (out & 64u) ? pu[4 + 3] : EDGE_PREFIX_INVALID;   // up-right: its down-left edge
+    pr[7] = (out & 128u) ? pd[1] : EDGE_PREFIX_INVALID;      // lower neighbour's up edge
+    // smallest (prefix, slot) among the outgoing edges; ties on the prefix go to the smallest slot, i.e. the first in
+    // ascending slot order 6, 0, 1, 2, 3, 4, 7, 5
+    const u32 pmin = min(min(min(pr[0], pr[1]), min(pr[2], pr[3])), min(min(pr[4], pr[5]), min(pr[6], pr[7])));
+    if (pmin == EDGE_PREFIX_INVALID) return;
+    int emin = 5;
+    u32 same = 0;  // how many other candidates share the smallest prefix
 #pragma unroll
-    for (int e = 4; e < 8; ++e) pr[e] = ((out >> e) & 1u) ? pre[incident_slot(p, e, W)] : 0u;
-    // smallest (prefix, slot) among the outgoing edges: visited in ascending slot order, so '<' keeps the first
-    u32 pmin = 0xFFFFFFFFu, smin = 0, same = 0;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
+    for (int k = 7; k >= 0; --k) {
         constexpr int order[8] = {6, 0, 1, 2, 3, 4, 7, 5};
         const int e = order[k];
-        if (((out >> e) & 1u) && pr[e] != EDGE_PREFIX_INVALID) {  // (a NaN / infinite weight is no edge)
-            same += pr[e] == pmin ? 1u : 0u;
-            if (pr[e] < pmin) {
-                pmin = pr[e];
-                smin = incident_slot(p, e, W);
-                same = 0;
-            }
-        }
+        const bool hit = pr[e] == pmin;
+        emin = hit ? e : emin;
+        same += hit ? 1u : 0u;
     }
-    if (pmin == EDGE_PREFIX_INVALID) return;
+    same -= 1u;
+    const u32 smin = incident_slot(p, emin, W);
     const u64 mine = make_pick(pmin, smin);
     u32 flags = (same != 0 && pmin != 0u) ? PIX_TIE_LOCAL : 0u;
     u64 seen = seen0;
