@@ -492,7 +492,7 @@ int segment_dev(dofs3d_ctx* ctx, const float* d_flow, int already_blurred, int n
 
     // K7: one 32-bit order-preserving prefix of the weight per edge slot (lives in keysB until the events need it)
     u32* prefix = reinterpret_cast<u32*>(ctx->keysB);
-    LAUNCH(ctx, k_edge_prefix, gN, SEG_THREADS, 0, ctx->flow_blur, prefix, ctx->S, W, H, ctx->seg.neighbors == 8 ? 1 : 0);
+    LAUNCH(ctx, k_edge_prefix, gN, SEG_THREADS, 0, ctx->flow_blur, prefix, ctx->S, W, H, ctx->seg.neighbors == 8 ? 1 : 0, fastdiv_magic((u32)ctx->W));
     mark(ctx, "edge_keys");
 
     // K9a Boruvka levels (== union-by-rank ranks) on direct edge comparisons: the guaranteed bound of levels is
@@ -632,6 +632,7 @@ int segment_dev(dofs3d_ctx* ctx, const float* d_flow, int already_blurred, int n
     R.W = W;
     R.H = H;
     R.N = N;
+    R.wm = fastdiv_magic((u32)W);
     R.min_size = ctx->seg.min_size;
     R.eb = eb;
     R.long_list = ctx->long_list;

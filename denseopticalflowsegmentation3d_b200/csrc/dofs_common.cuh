@@ -20,6 +20,21 @@ typedef uint64_t u64;
 #define DOFS_HD __host__ __device__ __forceinline__
 #define DOFS_D __device__ __forceinline__
 
+// x / d and x % d for a run-time divisor that stays the same for a whole launch (the image width): one multiply-high
+// and one correction step instead of the ~25-instruction integer division.  m = fastdiv_magic(d) = floor((2^32 - 1) / d);
+// floor(x m / 2^32) is floor(x / d) or one less for every x < 2^31.
+DOFS_HD u32 fastdiv_magic(u32 d) { return 0xFFFFFFFFu / d; }
+DOFS_D int fastdiv(int x, int d, u32 m, int* rem) {
+    int q = (int)__umulhi((u32)x, m);
+    int r = x - q * d;
+    if (r >= d) {
+        ++q;
+        r -= d;
+    }
+    *rem = r;
+    return q;
+}
+
 // float ops, one rounding each
 DOFS_D float xfadd(float a, float b) { return __fadd_rn(a, b); }
 DOFS_D float xfsub(float a, float b) { return __fsub_rn(a, b); }

@@ -324,12 +324,14 @@ DOFS_D int edge_other(int s, int d, int W) {
 // them by comparing edges directly (below), and only they are sorted afterwards (k_time_*).  So the per-slot state
 // is just the 32-bit prefix; the exact weight of a slot is recomputed from the flow field when two prefixes tie.
 __global__ void __launch_bounds__(SEG_THREADS)
-k_edge_prefix(const float2* __restrict__ flow, u32* __restrict__ prefix, size_t stride, int W, int H, int neighbors8) {
+k_edge_prefix(const float2* __restrict__ flow, u32* __restrict__ prefix, size_t stride, int W, int H, int neighbors8,
+              u32 wm /* fastdiv_magic(W) */) {
     const int frame = blockIdx.y;
     const int N = W * H;
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= N) return;
-    const int y = p / W, x = p - y * W;
+    int x;
+    const int y = fastdiv(p, W, wm, &x);
     const float2* f = flow + (size_t)frame * N;
     const float2 c = f[p];
     u32 k0 = EDGE_PREFIX_INVALID, k1 = EDGE_PREFIX_INVALID, k2 = EDGE_PREFIX_INVALID, k3 = EDGE_PREFIX_INVALID;
@@ -909,8 +911,10 @@ k_bor_level0_pick(BorState S, const u32* __restrict__ prefix, size_t prefix_stri
     const size_t fo = (size_t)frame * N;
     const u32* pre = prefix + (size_t)frame * prefix_stride;
     const float2* f = flow + fo;
+    const u32 wm = fastdiv_magic((u32)W);  // (once per thread: the loop below visits about a hundred pixels)
     PIXEL_TILES(p, W, H) {
-        const int y = p / W, x = p - y * W;
+        int x;
+        const int y = fastdiv(p, W, wm, &x);
         const uint4 r4 = *reinterpret_cast<const uint4*>(pre + 4 * (size_t)p);
         u64 b = PICK_NONE;
 #define L0_CONSIDER(pr, slot)                                     \
@@ -943,8 +947,10 @@ __global__ void __launch_bounds__(SEG_THREADS)
 k_bor_level0_root(BorState S, int W, int H, int N, int neighbors8) {
     const int frame = blockIdx.y;
     const size_t fo = (size_t)frame * N;
+    const u32 wm = fastdiv_magic((u32)W);
     GRID_STRIDE(p, N) {
-        const int y = p / W, x = p - y * W;
+        int x;
+        const int y = fastdiv(p, W, wm, &x);
         S.mask[fo + p] = (u8)incident_mask(x, y, W, H, neighbors8);
         S.lvl[fo + p] = 0;
         const u64 t = S.best[fo + p];
@@ -1461,6 +1467,7 @@ struct ReplayArgs {
     int list_cap;
     int cand_cap;
     int W, H, N;
+    u32 wm;                // fastdiv_magic(W)
     int min_size;
     EvBits eb;
     const double* rcp;     // [RCP_TABLE] 1.0 / n, correctly rounded (filled on the host: IEEE division), for the small set
@@ -1500,7 +1507,8 @@ DOFS_D void push_candidate(const ReplayArgs& A, int frame, u32 root, u32 time, i
 DOFS_D RootState root_initial(const ReplayArgs& A, size_t fo, u32 c) {
     RootState r;
     const float2 f = A.flow[fo + c];
-    const int y = (int)c / A.W, x = (int)c - y * A.W;
+    int x;
+    const int y = fastdiv((int)c, A.W, A.wm, &x);
     r.size = 1;
     r.fx = f.x;
     r.fy = f.y;
@@ -1518,7 +1526,8 @@ DOFS_D RootState root_absorbed(const ReplayArgs& A, size_t fo, u32 a, int wave) 
 #define EV_FLAG_STARTED 0x80000000u  // in ev_size after k_replay_scan: the event's chain started inside its tile
 
 DOFS_D void replay_gate(const ReplayArgs& A, int frame, u32 r, u32 loser, int s, float2 f, ushort4 bb) {
-    const int y = (int)r / A.W;
+    int x_;
+    const int y = fastdiv((int)r, A.W, A.wm, &x_);
     if (s >= A.min_size && !(y < A.H / 10)) {                                       // graph.cpp:280, 288
         const double move = norm2d(f.x, f.y);
         if (!(move < xddiv((double)(3 * (y + 1)), (double)A.H)))                     // graph.cpp:296
