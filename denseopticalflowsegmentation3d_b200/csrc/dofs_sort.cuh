@@ -57,6 +57,9 @@ DOFS_D u32 rs_block_excl_scan(u32 v, u32* s_warp /* >= 8 */, u32* total) {
 #ifndef RS_USE_MATCH_ANY
 #define RS_USE_MATCH_ANY 0  // A/B: the MATCH.ANY instruction instead of nine votes
 #endif
+#ifndef RS_MATCH_PTX
+#define RS_MATCH_PTX 1
+#endif
 template <int BITS = 9>
 DOFS_D u32 rs_match9(u32 d) {
 #if RS_USE_MATCH_ANY
@@ -65,9 +68,25 @@ DOFS_D u32 rs_match9(u32 d) {
     u32 peers = 0xffffffffu;
 #pragma unroll
     for (int b = 0; b < BITS; ++b) {
+#if RS_MATCH_PTX
+        // four instructions per bit (test -> predicate, vote, complement under the predicate, and) where the compiler's
+        // select form takes six: the ranking is a third of the one-sweep kernel's instructions
+        asm volatile(
+            "{\n"
+            " .reg .pred p;\n"
+            " .reg .b32 m;\n"
+            " setp.ne.u32 p, %1, 0;\n"
+            " vote.sync.ballot.b32 m, p, 0xffffffff;\n"
+            " @!p not.b32 m, m;\n"
+            " and.b32 %0, %0, m;\n"
+            "}\n"
+            : "+r"(peers)
+            : "r"(d & (1u << b)));
+#else
         const bool bit = (d >> b) & 1u;
         const u32 m = __ballot_sync(0xffffffffu, bit);
         peers &= bit ? m : ~m;
+#endif
     }
     return peers;
 }
