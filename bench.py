@@ -536,7 +536,7 @@ def ours(args):
         value = world * B * K / (ms_total / 1e3)
         e2e_value = world * B * K / (e2e_ms / 1e3)
         peak, peak_src = measured_peak_gbs()
-        # Dominant bandwidth-bound kernel of the path: k_box_solve (FarnebackUpdateFlow_Blur: 15x15 box mean of the five
+        # Dominant bandwidth-bound kernel of the path: k_box_solve7f (FarnebackUpdateFlow_Blur: 15x15 box mean of the five
         # matrix channels + the 2x2 solve).  The roofline figure is taken on its full-resolution launches (3 per call, one per
         # iteration of pyramid level 0): algorithmic bytes per launch = (20 B of M read once + 8 B of flow written) per pixel.
         box_bytes = 28 * N * Bc
@@ -569,7 +569,7 @@ def ours(args):
             # the per-kernel figure is the kernel alone on the GPU (CUDA events around every launch, one context, right after
             # the timed region): inside the timed region NC contexts overlap, so an event-bracketed launch there also contains
             # the time it spends sharing the SMs and HBM with the other contexts' kernels (reported as in_timed_region)
-            roof = {"bound": "hbm", "kernel": "k_box_solve7 (15x15 box mean of M + 2x2 solve), full-resolution launches",
+            roof = {"bound": "hbm", "kernel": "k_box_solve7f (15x15 box mean of M + 2x2 solve), full-resolution launches",
                     "achieved": iso["achieved"], "peak": peak, "unit": "GB/s", "frac": iso["frac"],
                     "traffic": box_traffic, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": box_bytes,
@@ -581,7 +581,8 @@ def ours(args):
                             stage_gbs(iso_ms, "flow_blur", 16 * N * Bc),
                         "k_radix_onesweep<u32> (one 8-bit pass of the merge-time sort, key+payload read and written)":
                             stage_gbs(iso_ms, "time_sort.scatter", 16 * N * Bc),
-                        "k_radix_onesweep<u64> (one 8-bit pass of the event sort)": stage_gbs(iso_ms, "event_sort.scatter", 24 * N * Bc)}}
+                        "k_radix_onesweep<u32> (one 8-bit pass of the event sort, 32-bit (wave, winner) keys)":
+                            stage_gbs(iso_ms, "event_sort.scatter", 16 * N * Bc)}}
         stages = {k: round(v[0] / K, 4) for k, v in sorted(stage_ms.items(), key=lambda kv: -kv[1][0])}
         stages_iso = {k: round(v[0] / n_iso, 4) for k, v in sorted(iso_ms.items(), key=lambda kv: -kv[1][0])}
         # whole path: the DRAM bytes the path actually moves (ncu, per kernel, profiles/r02_traffic*.json), not SURVEY's
