@@ -563,7 +563,7 @@ def ours(args):
         if traffic and traffic.get("pairs") and box_keys:
             # ncu DRAM bytes of the three full-resolution launches: the kernel's bytes scale with the pixel count
             kb = traffic["kernels"][box_keys[0]]
-            box_traffic = (kb["dram_read_MB"] + kb["dram_write_MB"]) * 1e6 / traffic["pairs"] * Bc / (3 * 1.328125)
+            box_traffic = (kb["dram_read_MB"] + kb["dram_write_MB"]) * 1e6 / traffic["pairs"] * Bc / (3 * 1.328125) * N / (1920 * 1080)
         roof = None
         if iso:
             # the per-kernel figure is the kernel alone on the GPU (CUDA events around every launch, one context, right after
