@@ -517,6 +517,24 @@ def ours(args):
     torch.cuda.synchronize()
     e2e_ms = 1e3 * (time.perf_counter() - t0)
     barrier()
+    # the same gather once more, all ranks lined up by the barrier and timed on the device: the figure inside the e2e
+    # region above also contains the ranks' arrival skew (they finish their last chunk a few ms apart)
+    gather_aligned_ms = None
+    if world > 1:
+        from denseopticalflowsegmentation3d_b200 import shard
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        ev0.record()
+        for c in range(NC):
+            ctxs[c].pack_boxes_dev(Bc, g_boxes[c].data_ptr(), CAPC, g_counts[c:c + 1].data_ptr())
+            pack_done[c].record(streams[c])
+        for c in range(NC):
+            torch.cuda.current_stream().wait_event(pack_done[c])
+        shard.gather_packed(g_counts, g_boxes)
+        ev1.record()
+        torch.cuda.synchronize()
+        gather_aligned_ms = ev0.elapsed_time(ev1)
     n_boxes_host = int(sum(h["boxes_seen"] for h in host))
     label_bytes = {"rle": MAXR * RUN_DTYPE.itemsize + 4, "u16": N * 2, "i32": N * 4}[args.labels]
     h2d = B * N * 3  # steady state: the boundary frame of a chunk stays on the device
@@ -608,7 +626,7 @@ def ours(args):
                            + ("; NCCL gather of the last step's boxes inside the timed region" if world > 1 else "")},
             "gpu_launches": int(t[2].item()), "clocks": clk, "roofline": roof, "whole_path": whole,
             "timeline": timeline, "stage_ms_per_step_context0_live": stages, "stage_ms_per_call_alone": stages_iso,
-            "boxes_found": total_boxes, "boxes_found_e2e_rank0": n_boxes_host, "nccl_gather_boxes_ms": gather_ms,
+            "boxes_found": total_boxes, "boxes_found_e2e_rank0": n_boxes_host, "nccl_gather_boxes_ms": gather_ms, "nccl_gather_boxes_ms_ranks_aligned": gather_aligned_ms,
             "device_bytes": sum(c.device_bytes for c in ctxs),
         }
         if world == 1 and not args.no_cpu_baseline:
