@@ -609,11 +609,11 @@ k_polyexp(const float* __restrict__ I, float* __restrict__ R, int Wk, int Hk, Po
 // ---------------------------------------------------------------------------------------------
 // one pixel of resize(prev_flow, (Wk, Hk), INTER_LINEAR) * mul
 DOFS_D float2 flow_upsampled(const float2* __restrict__ src /* [Hp][Wp] of the pair */, int x, int y, int Wp, int Hp, int Wk,
-                             int Hk, double mul) {
+                             int Hk, double mul, double scx, double scy) {
     int sx, sy;
     float fx, fy;
-    flow_linear_coord(x, (double)Wp / Wk, Wp, &sx, &fx);
-    flow_linear_coord(y, (double)Hp / Hk, Hp, &sy, &fy);
+    flow_linear_coord(x, scx, Wp, &sx, &fx);
+    flow_linear_coord(y, scy, Hp, &sy, &fy);
     const int sx1 = min(sx + 1, Wp - 1), sy1 = min(sy + 1, Hp - 1);
     const float2 a = src[(size_t)sy * Wp + sx], b = src[(size_t)sy * Wp + sx1];
     const float2 c = src[(size_t)sy1 * Wp + sx], d = src[(size_t)sy1 * Wp + sx1];
@@ -648,6 +648,7 @@ struct FlowStart {
     const float2* prev;  // flow of the coarser level, or nullptr: the level starts from zero
     int Wp, Hp;
     double mul;
+    double scx, scy;  // (double)Wp / Wk, (double)Hp / Hk: divided once on the host, not twice per pixel
 };
 enum { UM_FLOW = 0, UM_START = 1 };
 
@@ -716,7 +717,7 @@ k_update_matrices(const float* __restrict__ R, const float2* __restrict__ flow, 
     const size_t npx = (size_t)Wk * Hk;
     float2 d;
     if (MODE == UM_FLOW) d = flow[(size_t)pair * npx + (size_t)y * Wk + x];
-    else if (fs.prev) d = flow_upsampled(fs.prev + (size_t)pair * fs.Wp * fs.Hp, x, y, fs.Wp, fs.Hp, Wk, Hk, fs.mul);
+    else if (fs.prev) d = flow_upsampled(fs.prev + (size_t)pair * fs.Wp * fs.Hp, x, y, fs.Wp, fs.Hp, Wk, Hk, fs.mul, fs.scx, fs.scy);
     else d = make_float2(0.f, 0.f);
     update_matrices_pixel(R, M, Wk, Hk, ps, pair, x, y, d);
 }
@@ -1157,6 +1158,8 @@ inline int farneback_run(FlowBuffers& fb, const u8* d_gray0, const u8* d_gray1, 
         start.Wp = Wp;
         start.Hp = Hp;
         start.mul = 1.0 / fb.cfg.pyr_scale;
+        start.scx = Wp > 0 ? (double)Wp / L.w : 1.0;
+        start.scy = Hp > 0 ? (double)Hp / L.h : 1.0;
         if (L.w == fb.W && L.h == fb.H && L.taps.radius == 1)
             k_pyr_level0<<<g_img, blk, 0, stream>>>(fresh, I_fresh, fb.W, fb.H, L.taps);
         else {

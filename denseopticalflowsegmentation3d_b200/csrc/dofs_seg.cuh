@@ -197,6 +197,9 @@ DOFS_D bool mbar_try_wait(u64* bar, u32 phase) {
     return ok != 0;
 }
 
+#ifndef BLUR_TMA_WARP_ISSUE
+#define BLUR_TMA_WARP_ISSUE 1
+#endif
 template <int R>
 __global__ void __launch_bounds__(256)
 k_blur_fused_tma(const float2* __restrict__ src, float2* __restrict__ dst, int W, int H, BlurTaps taps) {
@@ -212,11 +215,21 @@ k_blur_fused_tma(const float2* __restrict__ src, float2* __restrict__ dst, int W
     if (x0 >= R && y0 >= R && x0 + FB_T + R <= W && y0 + FB_T + R <= H) {  // no border in reach (block-uniform)
         if (threadIdx.x == 0) mbar_init(&s_bar, 1);
         __syncthreads();
+#if BLUR_TMA_WARP_ISSUE
+        if (wrp == 0) {  // the first warp issues the row copies, two rows a lane (one thread issuing all 56 was a third of
+                         // the kernel's stall samples); the byte count is armed before any copy can complete
+            if (lane == 0) mbar_expect_tx(&s_bar, (u32)(C * C * sizeof(float2)));
+            __syncwarp();
+            const float2* row = img + (size_t)(y0 - R) * W + (x0 - R);
+            for (int ry = lane; ry < C; ry += 32) bulk_copy_g2s(&s_in[ry][0], row + (size_t)ry * W, (u32)(C * sizeof(float2)), &s_bar);
+        }
+#else
         if (threadIdx.x == 0) {
             mbar_expect_tx(&s_bar, (u32)(C * C * sizeof(float2)));
             const float2* row = img + (size_t)(y0 - R) * W + (x0 - R);
             for (int ry = 0; ry < C; ++ry) bulk_copy_g2s(&s_in[ry][0], row + (size_t)ry * W, (u32)(C * sizeof(float2)), &s_bar);
         }
+#endif
         while (!mbar_try_wait(&s_bar, 0u)) {
         }
     } else {
