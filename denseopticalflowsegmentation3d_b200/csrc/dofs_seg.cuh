@@ -578,6 +578,9 @@ k_prefix_repair_long(RepairArgs A) {
 #ifndef BOR_L0_COMP
 #define BOR_L0_COMP 1
 #endif
+#ifndef BOR_CHASE_LOCKSTEP
+#define BOR_CHASE_LOCKSTEP 1
+#endif
 #ifndef BOR_RELABEL_MASK
 #define BOR_RELABEL_MASK 1
 #endif
@@ -1031,6 +1034,57 @@ k_bor_contract(BorState S, int N, int level) {
     for (int it0 = 0; it0 < rounds; it0 += BOR_APPEND_ROUNDS) {
         u32 want = 0;
         u32 live[BOR_APPEND_ROUNDS];
+#if BOR_CHASE_LOCKSTEP
+        // The chases of the thread's BOR_APPEND_ROUNDS roots advance in lockstep: every trip of the loop issues the next
+        // link of ALL unfinished chases before any is consumed, so a thread has that many loads in flight instead of one
+        // (the kernel is bound by the latency of these dependent loads).  Path halving as below.
+        u32 g[BOR_APPEND_ROUNDS];
+        u32 busy = 0;
+#pragma unroll
+        for (int r = 0; r < BOR_APPEND_ROUNDS; ++r) {
+            const int i = ((it0 + r) * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x;
+            live[r] = 0;
+            g[r] = 0;
+            if (it0 + r < rounds && i < count) {
+                live[r] = level == 0 ? (u32)i : list[i];
+                g[r] = live[r];
+                busy |= 1u << r;
+            }
+        }
+        const u32 valid = busy;
+        while (busy) {
+            u32 nx[BOR_APPEND_ROUNDS], nn[BOR_APPEND_ROUNDS];
+#pragma unroll
+            for (int r = 0; r < BOR_APPEND_ROUNDS; ++r) nx[r] = ((busy >> r) & 1u) ? newp[g[r]] : 0u;
+#pragma unroll
+            for (int r = 0; r < BOR_APPEND_ROUNDS; ++r) nn[r] = ((busy >> r) & 1u) ? newp[nx[r]] : 0u;
+#pragma unroll
+            for (int r = 0; r < BOR_APPEND_ROUNDS; ++r) {
+                if (!((busy >> r) & 1u)) continue;
+                if (nx[r] == g[r]) {
+                    busy &= ~(1u << r);
+                } else if (nn[r] == nx[r]) {
+                    g[r] = nx[r];
+                    busy &= ~(1u << r);
+                } else {
+                    newp[g[r]] = nn[r];
+                    g[r] = nn[r];
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < BOR_APPEND_ROUNDS; ++r) {
+            if (!((valid >> r) & 1u)) continue;
+            const u32 c = live[r];
+            const bool survives = g[r] == c;
+            if (survives) S.best[fo + c] = PICK_NONE;  // only live roots collect offers in the next level
+            if (!survives || level == 0) S.up[fo + c] = g[r];  // (level 0 initialises `up`: a survivor points at itself)
+#if BOR_L0_COMP
+            if (level == 0) S.comp[fo + c] = g[r];  // every pixel is a root here: its component, without a relabel pass
+#endif
+            if (survives) want |= 1u << r;
+        }
+#else
 #pragma unroll
         for (int r = 0; r < BOR_APPEND_ROUNDS; ++r) {
             const int i = ((it0 + r) * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x;
@@ -1061,6 +1115,7 @@ k_bor_contract(BorState S, int N, int level) {
                 if (survives) want |= 1u << r;
             }
         }
+#endif
         list_append_block(next, &S.n_roots[level * S.F + frame], want, live);
     }
 }
@@ -1347,10 +1402,61 @@ DOFS_D u32 ev_chain(u32 key, EvBits) { return key; }  // wave | winner
 DOFS_D u32 ev_winner(u32 key, EvBits b) { return key & ((1u << b.wb) - 1u); }
 DOFS_D int ev_wave(u32 key, EvBits b) { return key == EV_KEY_NONE ? EV_MAX_WAVES - 1 : (int)(key >> b.wb); }
 
+#ifndef EV_KEYS_ILP
+#define EV_KEYS_ILP 4
+#endif
 __global__ void __launch_bounds__(SEG_THREADS)
 k_event_keys(BorState S, u32* __restrict__ win, u32* __restrict__ key_by_root, int N, EvBits eb) {
     const int frame = blockIdx.y;
     const size_t fo = (size_t)frame * N;
+#if EV_KEYS_ILP > 1
+    // EV_KEYS_ILP roots per thread climb in lockstep: the climb is a chain of dependent gathers (time of the candidate,
+    // then its `up` link), and one climb per thread leaves the memory system idle between them
+    const u32* tm = S.loss_time + fo;
+    const u32* up = S.up + fo;
+    const int stride = gridDim.x * blockDim.x;
+    for (int c0 = blockIdx.x * blockDim.x + threadIdx.x; c0 < N; c0 += EV_KEYS_ILP * stride) {
+        u32 t[EV_KEYS_ILP], cur[EV_KEYS_ILP];
+        u32 busy = 0;
+#pragma unroll
+        for (int k = 0; k < EV_KEYS_ILP; ++k) {
+            const int c = c0 + k * stride;
+            t[k] = DOFS_INF32;
+            cur[k] = 0;
+            if (c < N) {
+                t[k] = tm[c];
+                cur[k] = up[c];
+                if (t[k] != DOFS_INF32) busy |= 1u << k;
+            }
+        }
+        while (busy) {
+            u32 tc[EV_KEYS_ILP], nx[EV_KEYS_ILP];
+#pragma unroll
+            for (int k = 0; k < EV_KEYS_ILP; ++k) {
+                tc[k] = ((busy >> k) & 1u) ? tm[cur[k]] : DOFS_INF32;
+                nx[k] = ((busy >> k) & 1u) ? up[cur[k]] : 0u;  // (speculative: used only if the climb goes on)
+            }
+#pragma unroll
+            for (int k = 0; k < EV_KEYS_ILP; ++k) {
+                if (!((busy >> k) & 1u)) continue;
+                if (tc[k] < t[k]) cur[k] = nx[k];
+                else busy &= ~(1u << k);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < EV_KEYS_ILP; ++k) {
+            const int c = c0 + k * stride;
+            if (c >= N) continue;
+            if (t[k] == DOFS_INF32) {
+                win[fo + c] = (u32)c;
+                key_by_root[fo + c] = EV_KEY_NONE;
+            } else {
+                win[fo + c] = cur[k];
+                key_by_root[fo + c] = ((u32)S.lvl[fo + cur[k]] << eb.wb) | cur[k];
+            }
+        }
+    }
+#else
     GRID_STRIDE(c, N) {
         const u32 t = S.loss_time[fo + c];
         if (t == DOFS_INF32) {
@@ -1363,6 +1469,7 @@ k_event_keys(BorState S, u32* __restrict__ win, u32* __restrict__ key_by_root, i
         win[fo + c] = cur;
         key_by_root[fo + c] = ((u32)S.lvl[fo + cur] << eb.wb) | cur;
     }
+#endif
 }
 
 // position i of the time-ordered list of losing roots -> the key of that root (roots that never lose are its tail)
