@@ -239,7 +239,8 @@ def test_kernel_variants_are_bit_identical(dofs, monkeypatch):
     the Boruvka pixel kernel against the separate pass, the next iteration's update-matrices fused into the box filter +
     solve kernel against separate kernels; and the conditional graph nodes that skip the late Boruvka
     levels / replay waves against unconditional launches, with their IF bodies forced to run (two levels enqueued
-    unconditionally, the rest behind the condition).  Results must not change by a bit."""
+    unconditionally, the rest behind the condition); the pyramid kernel with its filter radius at run time against the
+    radius-templated instances.  Results must not change by a bit."""
     from denseopticalflowsegmentation3d_b200 import synth
     W, H, n = 328, 190, 2      # not a multiple of the tile sizes; W a multiple of 4 (word-aligned fast path taken)
     fr = synth.frames(21, 6, 0, n + 1, W, H)
@@ -258,7 +259,7 @@ def test_kernel_variants_are_bit_identical(dofs, monkeypatch):
     base = {k: run(v) for k, v in (("even", fr), ("odd", fr_odd))}
     for knob, val in (("DOFS3D_PYR_TILED", "1"), ("DOFS3D_BLUR_TMA", "0"), ("DOFS3D_BOR_FOLD", "1"), ("DOFS3D_STRIDE_BLOCKS", "5"),
                       ("DOFS3D_FLOW_FUSE", "1"), ("DOFS3D_COND_GRAPHS", "0"), ("DOFS3D_SOFT_LEVELS", "2"),
-                      ("DOFS3D_SOFT_LEVELS", "1")):
+                      ("DOFS3D_SOFT_LEVELS", "1"), ("DOFS3D_PYR_GENERIC", "1")):
         monkeypatch.setenv(knob, val)
         for k, v in (("even", fr), ("odd", fr_odd)):
             f, out = run(v)
