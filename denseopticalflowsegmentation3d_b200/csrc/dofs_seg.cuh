@@ -564,12 +564,16 @@ k_prefix_repair_long(RepairArgs A) {
 // K9a  Boruvka levels.  No host round trip: the host enqueues the guaranteed bound of levels
 // (components at least halve per level) and every kernel of a level returns at once for a frame that
 // is already one component.  Work shrinks with the forest:
-//   * the pixel kernel skips pixels whose back-edges have all become internal (one byte of mask each:
-//     an edge that became internal stays internal);
-//   * the root kernels run over the list of live roots, rebuilt every level;
-//   * `comp` (root of every pixel) is refreshed by one streaming pass per level: one hop through the
-//     `up` link its root received in the contraction.
+//   * the pixel kernel skips pixels whose incident edges have all become internal (one byte of mask each:
+//     an edge that became internal stays internal); from level 2 on it first packs the live pixels of a
+//     chunk so that every lane has work (k_bor_pixel_packed);
+//   * the root kernels run over the list of live roots, rebuilt every level (k_bor_contract chases the
+//     hooks of four roots per thread in lockstep and appends the survivors with one atomic per block);
+//   * `comp` (root of every pixel) is written by the level-0 contraction and refreshed by one streaming
+//     pass per later level: one hop through the `up` link its root received in the contraction, for the
+//     pixels that still have an external edge (nobody reads the others again).
 // Kernels are grid-stride with a small fixed grid, so a level with nothing left costs microseconds.
+// (The late levels sit behind a CUDA-graph IF node, see launch_conditional in dofs3d.cu.)
 // ---------------------------------------------------------------------------------------------
 #define EV_MAX_WAVES 32
 // Measured knobs of the level kernels (both on; 32 pairs alone: Boruvka 9.13 -> 8.45 ms, bench 1 033 -> 1 058 pairs/s):
