@@ -2,8 +2,8 @@
 // 32-bit and 64-bit keys.
 //
 // Used for the merge times (dofs_seg.cuh: the <= N-1 accepted edges on a 32-bit key, 4 passes, then an exact repair of
-// the short runs that share a prefix), for the merge events by (wave, winner root, time) (64-bit keys), for the exact
-// 64-bit fallback of the merge times, and — parity hook dofs3d_edges_sorted only — for the reference's whole edge list
+// the short runs that share a prefix), for the merge events (a stable sort of the time-ordered losers on a 32-bit
+// (wave, winner root) key, 4 passes at 1080p), for the exact 64-bit fallback of the merge times, and — parity hook dofs3d_edges_sorted only — for the reference's whole edge list
 // in std::multiset order (graph.cpp:55-60): ascending f64 weight (non-negative doubles order like their bit patterns),
 // equal weights in insertion order, i.e. a STABLE sort of the insertion sequence by weight.
 //
